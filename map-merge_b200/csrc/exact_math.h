@@ -1,0 +1,444 @@
+// exact_math.h — IEEE-only scalar math shared by host and device code.
+//
+// Every routine here is built from +, -, *, /, sqrt, rint and integer bit
+// operations only, so it evaluates to the SAME bits on x86-64 (g++ with
+// -ffp-contract=off) and on sm_100a (nvcc with -fmad=false).  The registration
+// path makes discrete decisions from floating-point values (DoG extrema,
+// histogram bins, RANSAC inlier votes, ICP iteration counts); routing the few
+// transcendental functions through this header is what lets the CUDA path and
+// the CPU checker agree on those decisions bit-for-bit instead of "almost".
+//
+// The functions are accurate to the last float bit in all but a vanishing
+// fraction of inputs (tests/test_exact_math.py pins them against libm/numpy).
+//
+// Reference call sites these stand in for ([PCL-recall]):
+//   expf   — pcl/keypoints/impl/sift_keypoint.hpp (Gaussian weights)
+//   atan2f — pcl/features/impl/pfh.hpp computePairFeatures (f1)
+//   atan2/cos/sin — pcl/common/impl/eigen.hpp computeRoots (normals, RANSAC)
+//   JacobiSVD 3x3 — Eigen::umeyama via pcl::umeyama (RANSAC, ICP, final SVD)
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define MM_HD __host__ __device__ __forceinline__
+#else
+#define MM_HD inline
+#endif
+
+namespace mm3d {
+namespace em {
+
+MM_HD double bits_to_double(uint64_t u)
+{
+  double d;
+  memcpy(&d, &u, sizeof(d));
+  return d;
+}
+
+// exp(x) for float x, evaluated in double and rounded once.
+MM_HD float expf_(float x)
+{
+  if (x != x) return x;
+  if (x < -104.0f) return 0.0f;
+  if (x > 88.8f) return INFINITY;
+  const double xd = (double)x;
+  const double n = rint(xd * 1.4426950408889634074);
+  const double r = xd - n * 0.69314718055994530942;
+  // Taylor, |r| <= 0.347: r^12/12! < 7e-15
+  double p = 1.0 / 39916800.0;
+  p = p * r + 1.0 / 3628800.0;
+  p = p * r + 1.0 / 362880.0;
+  p = p * r + 1.0 / 40320.0;
+  p = p * r + 1.0 / 5040.0;
+  p = p * r + 1.0 / 720.0;
+  p = p * r + 1.0 / 120.0;
+  p = p * r + 1.0 / 24.0;
+  p = p * r + 1.0 / 6.0;
+  p = p * r + 0.5;
+  p = p * r + 1.0;
+  p = p * r + 1.0;
+  const int ni = (int)n;  // in [-151, 129]
+  const double s = bits_to_double((uint64_t)(1023 + ni) << 52);
+  return (float)(p * s);
+}
+
+// atan(z) for z in [0, 1], double.
+MM_HD double atan01_(double z)
+{
+  z = z / (1.0 + sqrt(1.0 + z * z));
+  z = z / (1.0 + sqrt(1.0 + z * z));  // now z <= 0.1990
+  const double z2 = z * z;
+  double s = 1.0 / 23.0;
+  s = 1.0 / 21.0 - z2 * s;
+  s = 1.0 / 19.0 - z2 * s;
+  s = 1.0 / 17.0 - z2 * s;
+  s = 1.0 / 15.0 - z2 * s;
+  s = 1.0 / 13.0 - z2 * s;
+  s = 1.0 / 11.0 - z2 * s;
+  s = 1.0 / 9.0 - z2 * s;
+  s = 1.0 / 7.0 - z2 * s;
+  s = 1.0 / 5.0 - z2 * s;
+  s = 1.0 / 3.0 - z2 * s;
+  s = 1.0 - z2 * s;
+  return 4.0 * (z * s);
+}
+
+MM_HD double atan2d_(double y, double x)
+{
+  const double kPi = 3.14159265358979323846;
+  if (x != x || y != y) return x + y;
+  const double ax = fabs(x), ay = fabs(y);
+  double a;
+  if (ax == 0.0 && ay == 0.0)
+    a = 0.0;
+  else if (ay <= ax)
+    a = atan01_(ay / ax);
+  else
+    a = 0.5 * kPi - atan01_(ax / ay);
+  if (signbit(x)) a = kPi - a;
+  return signbit(y) ? -a : a;
+}
+
+MM_HD float atan2f_(float y, float x)
+{
+  return (float)atan2d_((double)y, (double)x);
+}
+
+// sin/cos for |t| <= ~1.2 (the eigen-solver only needs [0, pi/3]).
+MM_HD double cos_small_(double t)
+{
+  const double t2 = t * t;
+  double s = 1.0 / 6402373705728000.0;  // 1/18!
+  s = 1.0 / 20922789888000.0 - t2 * s;  // 1/16!
+  s = 1.0 / 87178291200.0 - t2 * s;     // 1/14!
+  s = 1.0 / 479001600.0 - t2 * s;       // 1/12!
+  s = 1.0 / 3628800.0 - t2 * s;         // 1/10!
+  s = 1.0 / 40320.0 - t2 * s;           // 1/8!
+  s = 1.0 / 720.0 - t2 * s;             // 1/6!
+  s = 1.0 / 24.0 - t2 * s;              // 1/4!
+  s = 0.5 - t2 * s;
+  return 1.0 - t2 * s;
+}
+
+MM_HD double sin_small_(double t)
+{
+  const double t2 = t * t;
+  double s = 1.0 / 121645100408832000.0;  // 1/19!
+  s = 1.0 / 355687428096000.0 - t2 * s;   // 1/17!
+  s = 1.0 / 1307674368000.0 - t2 * s;     // 1/15!
+  s = 1.0 / 6227020800.0 - t2 * s;        // 1/13!
+  s = 1.0 / 39916800.0 - t2 * s;          // 1/11!
+  s = 1.0 / 362880.0 - t2 * s;            // 1/9!
+  s = 1.0 / 5040.0 - t2 * s;              // 1/7!
+  s = 1.0 / 120.0 - t2 * s;               // 1/5!
+  s = 1.0 / 6.0 - t2 * s;                 // 1/3!
+  return t * (1.0 - t2 * s);
+}
+
+MM_HD float cosf_small_(float t) { return (float)cos_small_((double)t); }
+MM_HD float sinf_small_(float t) { return (float)sin_small_((double)t); }
+
+template <typename T>
+MM_HD T sqrt_(T v);
+template <>
+MM_HD float sqrt_<float>(float v) { return sqrtf(v); }
+template <>
+MM_HD double sqrt_<double>(double v) { return sqrt(v); }
+
+// ---------------------------------------------------------------------------
+// 3x3 helpers (row-major m[9]).
+// ---------------------------------------------------------------------------
+template <typename T>
+MM_HD T det3(const T* m)
+{
+  return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) +
+         m[2] * (m[3] * m[7] - m[4] * m[6]);
+}
+
+// One-sided (Hestenes) Jacobi SVD of a 3x3 matrix: A = U diag(s) V^T with
+// s[0] >= s[1] >= s[2] >= 0.  Rank-deficient columns of U are completed to an
+// orthonormal basis deterministically (zero matrix -> U = V = I, which is what
+// Eigen::JacobiSVD returns for it).
+template <typename T>
+MM_HD void svd3(const T* A, T* U, T* s, T* V)
+{
+  T a[9];
+  for (int i = 0; i < 9; ++i) {
+    a[i] = A[i];
+    V[i] = T(0);
+  }
+  V[0] = V[4] = V[8] = T(1);
+  const T eps = sizeof(T) == 4 ? T(1.1920929e-7) : T(2.220446049250313e-16);
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    bool rotated = false;
+    for (int p = 0; p < 2; ++p) {
+      for (int q = p + 1; q < 3; ++q) {
+        T alpha = T(0), beta = T(0), gamma = T(0);
+        for (int i = 0; i < 3; ++i) {
+          alpha += a[i * 3 + p] * a[i * 3 + p];
+          beta += a[i * 3 + q] * a[i * 3 + q];
+          gamma += a[i * 3 + p] * a[i * 3 + q];
+        }
+        if (gamma == T(0)) continue;
+        if (fabs(gamma) <= eps * sqrt_<T>(alpha * beta)) continue;
+        rotated = true;
+        const T zeta = (beta - alpha) / (T(2) * gamma);
+        const T t = (zeta >= T(0) ? T(1) : T(-1)) / (fabs(zeta) + sqrt_<T>(T(1) + zeta * zeta));
+        const T c = T(1) / sqrt_<T>(T(1) + t * t);
+        const T sn = c * t;
+        for (int i = 0; i < 3; ++i) {
+          const T ap = a[i * 3 + p], aq = a[i * 3 + q];
+          a[i * 3 + p] = c * ap - sn * aq;
+          a[i * 3 + q] = sn * ap + c * aq;
+          const T vp = V[i * 3 + p], vq = V[i * 3 + q];
+          V[i * 3 + p] = c * vp - sn * vq;
+          V[i * 3 + q] = sn * vp + c * vq;
+        }
+      }
+    }
+    if (!rotated) break;
+  }
+  T n[3];
+  for (int j = 0; j < 3; ++j)
+    n[j] = sqrt_<T>(a[j] * a[j] + a[3 + j] * a[3 + j] + a[6 + j] * a[6 + j]);
+  // sort columns by descending norm (stable selection)
+  int ord[3] = {0, 1, 2};
+  for (int i = 0; i < 2; ++i)
+    for (int j = i + 1; j < 3; ++j)
+      if (n[ord[j]] > n[ord[i]]) {
+        int tmp = ord[i];
+        ord[i] = ord[j];
+        ord[j] = tmp;
+      }
+  T Vs[9], As[9];
+  for (int j = 0; j < 3; ++j) {
+    s[j] = n[ord[j]];
+    for (int i = 0; i < 3; ++i) {
+      Vs[i * 3 + j] = V[i * 3 + ord[j]];
+      As[i * 3 + j] = a[i * 3 + ord[j]];
+    }
+  }
+  for (int i = 0; i < 9; ++i) V[i] = Vs[i];
+  const T tiny = s[0] * eps * T(8);
+  int rank = 0;
+  for (int j = 0; j < 3; ++j)
+    if (s[j] > tiny) ++rank;
+  if (rank == 0) {
+    for (int i = 0; i < 9; ++i) U[i] = T(0);
+    U[0] = U[4] = U[8] = T(1);
+    return;
+  }
+  for (int j = 0; j < rank; ++j)
+    for (int i = 0; i < 3; ++i) U[i * 3 + j] = As[i * 3 + j] / s[j];
+  if (rank == 1) {
+    // pick the axis least aligned with u0, orthogonalise, normalise
+    const T x = fabs(U[0]), y = fabs(U[3]), z = fabs(U[6]);
+    T e[3] = {T(0), T(0), T(0)};
+    if (x <= y && x <= z)
+      e[0] = T(1);
+    else if (y <= z)
+      e[1] = T(1);
+    else
+      e[2] = T(1);
+    const T d = e[0] * U[0] + e[1] * U[3] + e[2] * U[6];
+    T w[3] = {e[0] - d * U[0], e[1] - d * U[3], e[2] - d * U[6]};
+    const T wn = sqrt_<T>(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    U[1] = w[0] / wn;
+    U[4] = w[1] / wn;
+    U[7] = w[2] / wn;
+  }
+  if (rank <= 2) {
+    U[2] = U[3] * U[7] - U[6] * U[4];
+    U[5] = U[6] * U[1] - U[0] * U[7];
+    U[8] = U[0] * U[4] - U[3] * U[1];
+  }
+}
+
+// Rigid (no scale) Umeyama from the 3x3 cross-covariance sigma = E[(q-qm)(p-pm)^T]
+// and the two means; writes a row-major 4x4.  Follows Eigen::umeyama
+// (Eigen/src/Geometry/Umeyama.h) step by step [PCL-recall: pcl::umeyama].
+template <typename T>
+MM_HD void umeyama_from_sigma(const T* sigma, const T* src_mean, const T* dst_mean, T* Rt)
+{
+  T U[9], V[9], d[3];
+  svd3<T>(sigma, U, d, V);
+  T S[3] = {T(1), T(1), T(1)};
+  if (det3<T>(sigma) < T(0)) S[2] = T(-1);
+  const T prec = sizeof(T) == 4 ? T(1e-5) : T(1e-12);
+  int rank = 0;
+  for (int i = 0; i < 3; ++i)
+    if (!(fabs(d[i]) <= fabs(d[0]) * prec)) ++rank;
+  if (rank == 2) {
+    if (det3<T>(U) * det3<T>(V) > T(0)) {
+      S[2] = T(1);
+    } else {
+      S[2] = T(-1);
+    }
+  }
+  T R[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      // (U * S.asDiagonal()) * V^T
+      T acc = (U[i * 3 + 0] * S[0]) * V[j * 3 + 0];
+      acc += (U[i * 3 + 1] * S[1]) * V[j * 3 + 1];
+      acc += (U[i * 3 + 2] * S[2]) * V[j * 3 + 2];
+      R[i * 3 + j] = acc;
+    }
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) Rt[i * 4 + j] = R[i * 3 + j];
+    T rs = R[i * 3 + 0] * src_mean[0];
+    rs += R[i * 3 + 1] * src_mean[1];
+    rs += R[i * 3 + 2] * src_mean[2];
+    Rt[i * 4 + 3] = dst_mean[i] - rs;
+  }
+  Rt[12] = Rt[13] = Rt[14] = T(0);
+  Rt[15] = T(1);
+}
+
+// ---------------------------------------------------------------------------
+// pcl::eigen33 / computeRoots restated in float [PCL-recall
+// pcl/common/impl/eigen.hpp].  m is a symmetric row-major 3x3.
+// ---------------------------------------------------------------------------
+MM_HD void compute_roots2_(float b, float c, float* roots)
+{
+  roots[0] = 0.0f;
+  float d = (float)((double)(b * b) - 4.0 * (double)c);
+  if (d < 0.0f) d = 0.0f;
+  const float sd = sqrtf(d);
+  roots[2] = 0.5f * (b + sd);
+  roots[1] = 0.5f * (b - sd);
+}
+
+MM_HD void compute_roots_(const float* m, float* roots)
+{
+  const float c0 = m[0] * m[4] * m[8] + 2.0f * m[1] * m[2] * m[5] - m[0] * m[5] * m[5] -
+                   m[4] * m[2] * m[2] - m[8] * m[1] * m[1];
+  const float c1 = m[0] * m[4] - m[1] * m[1] + m[0] * m[8] - m[2] * m[2] + m[4] * m[8] - m[5] * m[5];
+  const float c2 = m[0] + m[4] + m[8];
+  if (fabsf(c0) < 1.1920929e-7f) {
+    compute_roots2_(c2, c1, roots);
+    return;
+  }
+  const float s_inv3 = (float)(1.0 / 3.0);
+  const float s_sqrt3 = sqrtf(3.0f);
+  const float c2_over_3 = c2 * s_inv3;
+  float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+  if (a_over_3 > 0.0f) a_over_3 = 0.0f;
+  const float half_b = 0.5f * (c0 + c2_over_3 * (2.0f * c2_over_3 * c2_over_3 - c1));
+  float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+  if (q > 0.0f) q = 0.0f;
+  const float rho = sqrtf(-a_over_3);
+  const float theta = atan2f_(sqrtf(-q), half_b) * s_inv3;
+  const float cos_theta = cosf_small_(theta);
+  const float sin_theta = sinf_small_(theta);
+  roots[0] = c2_over_3 + 2.0f * rho * cos_theta;
+  roots[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+  roots[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+  if (roots[0] >= roots[1]) {
+    float t = roots[0];
+    roots[0] = roots[1];
+    roots[1] = t;
+  }
+  if (roots[1] >= roots[2]) {
+    float t = roots[1];
+    roots[1] = roots[2];
+    roots[2] = t;
+    if (roots[0] >= roots[1]) {
+      t = roots[0];
+      roots[0] = roots[1];
+      roots[1] = t;
+    }
+  }
+  if (roots[0] <= 0.0f) compute_roots2_(c2, c1, roots);
+}
+
+// eigenvalues only (ascending), pcl::eigen33(mat, evals)
+MM_HD void eigen33_values(const float* mat, float* evals)
+{
+  float scale = 0.0f;
+  for (int i = 0; i < 9; ++i) scale = fmaxf(scale, fabsf(mat[i]));
+  if (scale <= 1.17549435e-38f) scale = 1.0f;
+  float sm[9];
+  for (int i = 0; i < 9; ++i) sm[i] = mat[i] / scale;
+  compute_roots_(sm, evals);
+  for (int i = 0; i < 3; ++i) evals[i] *= scale;
+}
+
+// smallest eigenpair, pcl::eigen33(mat, eigenvalue, eigenvector)
+MM_HD void eigen33_smallest(const float* mat, float* eigenvalue, float* vec)
+{
+  float scale = 0.0f;
+  for (int i = 0; i < 9; ++i) scale = fmaxf(scale, fabsf(mat[i]));
+  if (scale <= 1.17549435e-38f) scale = 1.0f;
+  float sm[9];
+  for (int i = 0; i < 9; ++i) sm[i] = mat[i] / scale;
+  float ev[3];
+  compute_roots_(sm, ev);
+  *eigenvalue = ev[0] * scale;
+  sm[0] -= ev[0];
+  sm[4] -= ev[0];
+  sm[8] -= ev[0];
+  const float* r0 = sm;
+  const float* r1 = sm + 3;
+  const float* r2 = sm + 6;
+  float v1[3] = {r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0]};
+  float v2[3] = {r0[1] * r2[2] - r0[2] * r2[1], r0[2] * r2[0] - r0[0] * r2[2], r0[0] * r2[1] - r0[1] * r2[0]};
+  float v3[3] = {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
+  const float l1 = v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2];
+  const float l2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
+  const float l3 = v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2];
+  const float* v;
+  float l;
+  if (l1 >= l2 && l1 >= l3) {
+    v = v1;
+    l = l1;
+  } else if (l2 >= l1 && l2 >= l3) {
+    v = v2;
+    l = l2;
+  } else {
+    v = v3;
+    l = l3;
+  }
+  const float inv = sqrtf(l);
+  vec[0] = v[0] / inv;
+  vec[1] = v[1] / inv;
+  vec[2] = v[2] / inv;
+}
+
+// FLANN L2_Simple in 3-D: sequential float accumulation, no contraction.
+MM_HD float dist2_3(float ax, float ay, float az, float bx, float by, float bz)
+{
+  const float dx = ax - bx, dy = ay - by, dz = az - bz;
+  float r = dx * dx;
+  r += dy * dy;
+  r += dz * dz;
+  return r;
+}
+
+// row-major 4x4 applied to a point the way Eigen/PCL evaluate it:
+// ((m0*x + m1*y) + m2*z) + m3
+MM_HD void transform_point(const float* m, float x, float y, float z, float* ox, float* oy, float* oz)
+{
+  *ox = ((m[0] * x + m[1] * y) + m[2] * z) + m[3];
+  *oy = ((m[4] * x + m[5] * y) + m[6] * z) + m[7];
+  *oz = ((m[8] * x + m[9] * y) + m[10] * z) + m[11];
+}
+
+// Order-independent accumulation: every term is rounded to a fixed-point grid
+// and summed in int64, so any summation order gives the same bits.
+#define MM3D_FIX1_SCALE 4294967296.0  /* 2^32: first-order sums (metres)   */
+#define MM3D_FIX2_SCALE 16777216.0    /* 2^24: second-order sums (metres^2) */
+#define MM3D_FIXD_SCALE 68719476736.0 /* 2^36: squared NN distances         */
+MM_HD long long to_fix(double v, double scale)
+{
+#if defined(__CUDA_ARCH__)
+  return __double2ll_rn(v * scale);
+#else
+  return (long long)rint(v * scale);
+#endif
+}
+
+}  // namespace em
+}  // namespace mm3d
