@@ -1,0 +1,627 @@
+// features.cu — per-map feature pipeline kernels (all maps per launch):
+//   K3 radius outlier removal   <- pcl::RadiusOutlierRemoval  (map_merge_3d/src/features.cpp:31-43)
+//   K4 surface normals          <- pcl::NormalEstimation      (src/features.cpp:168-179)
+//   K5 SIFT3D keypoints         <- pcl::SIFTKeypoint          (src/features.cpp:45-62, 85-96)
+//   K7 FPFH descriptors         <- pcl::FPFHEstimation        (src/features.cpp:99-166, src/dispatch_descriptors.h:40)
+// One thread owns one query point and walks its neighbourhood in ascending
+// point index, so every float accumulation happens in the canonical order.
+#include <algorithm>
+#include <cmath>
+
+#include "mm3d_internal.cuh"
+
+namespace mm3d {
+
+namespace {
+
+constexpr int FB = 128;  // block size of the neighbourhood kernels
+
+static int radius_voxels(double radius, float leaf) { return (int)std::ceil(radius / (double)leaf) + 1; }
+
+static int max_n(const std::vector<CloudView>& in)
+{
+  int mx = 0;
+  for (const CloudView& v : in) mx = std::max(mx, v.n);
+  return mx;
+}
+
+static std::vector<Seg> make_segs(const std::vector<int>& ns, int* total)
+{
+  std::vector<Seg> segs(ns.size());
+  int off = 0;
+  for (size_t m = 0; m < ns.size(); ++m) {
+    segs[m].off = off;
+    segs[m].n = ns[m];
+    off += ns[m];
+  }
+  *total = off;
+  return segs;
+}
+
+// ---------------------------------------------------------------- K3 outliers
+struct OutlierJob {
+  GridView g;
+  uint32_t* flags;  // per original point
+  int* counts;      // optional
+};
+
+__global__ void __launch_bounds__(FB) outlier_kernel(const OutlierJob* __restrict__ jobs, float r2, int rv, int min_nb)
+{
+  const OutlierJob& j = jobs[blockIdx.y];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= j.g.n) return;
+  const float4 q = j.g.pts[k];
+  int cnt = 0;
+  for_each_in_radius(j.g, q.x, q.y, q.z, r2, rv, [&](int, const float4&, float) { ++cnt; });
+  const int oi = j.g.orig ? j.g.orig[k] : k;
+  j.flags[oi] = cnt > min_nb ? 1u : 0u;  // "k <= min_pts_radius_" is an outlier
+  if (j.counts) j.counts[oi] = cnt;
+}
+
+struct CompactJob {
+  const float4* src;
+  const uint32_t* flags;
+  const uint32_t* pos;
+  float4* dst;
+  int n;
+};
+__global__ void __launch_bounds__(256) compact_points_kernel(const CompactJob* __restrict__ jobs)
+{
+  const CompactJob& j = jobs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= j.n) return;
+  if (j.flags[i]) j.dst[j.pos[i]] = j.src[i];
+}
+
+// ---------------------------------------------------------------- K4 normals
+struct NormalJob {
+  GridView g;
+  float4* normals;  // per original point
+};
+
+__global__ void __launch_bounds__(FB) normals_kernel(const NormalJob* __restrict__ jobs, float r2, int rv)
+{
+  const NormalJob& j = jobs[blockIdx.y];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= j.g.n) return;
+  const float4 q = j.g.pts[k];
+  // pcl::computeMeanAndCovarianceMatrix, single pass, float accumulators
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f, a8 = 0.f;
+  int cnt = 0;
+  for_each_in_radius(j.g, q.x, q.y, q.z, r2, rv, [&](int, const float4& p, float) {
+    a0 += p.x * p.x; a1 += p.x * p.y; a2 += p.x * p.z;
+    a3 += p.y * p.y; a4 += p.y * p.z; a5 += p.z * p.z;
+    a6 += p.x; a7 += p.y; a8 += p.z;
+    ++cnt;
+  });
+  const int oi = j.g.orig ? j.g.orig[k] : k;
+  if (cnt < 3) {
+    const float nanv = __int_as_float(0x7fc00000);
+    j.normals[oi] = make_float4(nanv, nanv, nanv, nanv);
+    return;
+  }
+  const float n = (float)cnt;
+  a0 /= n; a1 /= n; a2 /= n; a3 /= n; a4 /= n; a5 /= n; a6 /= n; a7 /= n; a8 /= n;
+  float cov[9];
+  cov[0] = a0 - a6 * a6;
+  cov[1] = a1 - a6 * a7;
+  cov[2] = a2 - a6 * a8;
+  cov[4] = a3 - a7 * a7;
+  cov[5] = a4 - a7 * a8;
+  cov[8] = a5 - a8 * a8;
+  cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+  float ev, vec[3];
+  em::eigen33_smallest(cov, &ev, vec);
+  float nx = vec[0], ny = vec[1], nz = vec[2];
+  const float eig_sum = cov[0] + cov[4] + cov[8];
+  const float curv = (eig_sum != 0.f) ? fabsf(ev / eig_sum) : 0.f;
+  const float vx = 0.0f - q.x, vy = 0.0f - q.y, vz = 0.0f - q.z;  // viewpoint (0,0,0)
+  const float cos_theta = (vx * nx + vy * ny + vz * nz);
+  if (cos_theta < 0.f) { nx *= -1.f; ny *= -1.f; nz *= -1.f; }
+  j.normals[oi] = make_float4(nx, ny, nz, curv);
+}
+
+// ---------------------------------------------------------------- K5 SIFT
+struct SiftJob {
+  GridView g;
+  float* dog;       // n x 5
+  uint32_t* flags;  // n x 3 (levels 1..3)
+};
+struct SiftScales {
+  float sigma_sqr[6];
+};
+
+__device__ __forceinline__ float sift_intensity(float w)
+{
+  const uint32_t c = __float_as_uint(w);
+  const int r = (c >> 16) & 0xff, g = (c >> 8) & 0xff, b = c & 0xff;
+  return (float)(299 * r + 587 * g + 114 * b) / 1000.0f;
+}
+
+__global__ void __launch_bounds__(FB) sift_scale_space_kernel(const SiftJob* __restrict__ jobs, SiftScales sc, float r2, int rv)
+{
+  const SiftJob& j = jobs[blockIdx.y];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= j.g.n) return;
+  const float4 q = j.g.pts[k];
+  float num[6], den[6];
+#pragma unroll
+  for (int s = 0; s < 6; ++s) { num[s] = 0.f; den[s] = 0.f; }
+  for_each_in_radius(j.g, q.x, q.y, q.z, r2, rv, [&](int, const float4& p, float d2) {
+    const float value = sift_intensity(p.w);
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+      const float ss = sc.sigma_sqr[s];
+      if (d2 <= 9 * ss) {
+        const float w = em::expf_(-0.5f * d2 / ss);
+        num[s] += value * w;
+        den[s] += w;
+      }
+    }
+  });
+  float prev = 0.f, resp = 0.f;
+#pragma unroll
+  for (int s = 0; s < 6; ++s) {
+    prev = resp;
+    resp = num[s] / den[s];
+    if (s > 0) j.dog[(size_t)k * 5 + (s - 1)] = resp - prev;
+  }
+}
+
+__global__ void __launch_bounds__(FB) sift_extrema_kernel(const SiftJob* __restrict__ jobs, float min_contrast)
+{
+  const SiftJob& j = jobs[blockIdx.y];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= j.g.n) return;
+  const float4 q = j.g.pts[k];
+  constexpr int K = 25;
+  float bd[K];
+  int bi[K];
+  int cnt = 0;
+  int rv = 3;
+  const int rv_max = max(max(j.g.div_v[0], j.g.div_v[1]), j.g.div_v[2]) + 2;
+  for (;;) {
+    cnt = 0;
+    const float rad = (float)rv * j.g.leaf;
+    for_each_in_radius(j.g, q.x, q.y, q.z, rad * rad, rv + 1, [&](int idx, const float4&, float d2) {
+      if (cnt == K && !(d2 < bd[K - 1] || (d2 == bd[K - 1] && idx < bi[K - 1]))) return;
+      int pos = (cnt < K) ? cnt : K - 1;
+      while (pos > 0 && (d2 < bd[pos - 1] || (d2 == bd[pos - 1] && idx < bi[pos - 1]))) {
+        bd[pos] = bd[pos - 1];
+        bi[pos] = bi[pos - 1];
+        --pos;
+      }
+      bd[pos] = d2;
+      bi[pos] = idx;
+      if (cnt < K) ++cnt;
+    });
+    if (cnt == K || rv > rv_max) break;
+    rv *= 2;
+  }
+  float mn[5], mx[5];
+#pragma unroll
+  for (int s = 0; s < 5; ++s) { mn[s] = 3.402823466e+38f; mx[s] = -3.402823466e+38f; }
+  for (int t = 0; t < cnt; ++t) {
+    const float* d = j.dog + (size_t)bi[t] * 5;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+      const float v = d[s];
+      mn[s] = fminf(mn[s], v);
+      mx[s] = fmaxf(mx[s], v);
+    }
+  }
+#pragma unroll
+  for (int s = 1; s < 4; ++s) {
+    const float val = j.dog[(size_t)k * 5 + s];
+    uint32_t f = 0;
+    if (fabsf(val) >= min_contrast) {
+      if ((val == mn[s]) && (val < mn[s - 1]) && (val < mn[s + 1])) f = 1;
+      else if ((val == mx[s]) && (val > mx[s - 1]) && (val > mx[s + 1])) f = 1;
+    }
+    j.flags[(size_t)k * 3 + (s - 1)] = f;
+  }
+}
+
+struct SiftEmitJob {
+  const float4* pts;
+  const uint32_t* flags;  // n x 3
+  const uint32_t* pos;
+  float4* dst;
+  int n3;
+};
+__global__ void __launch_bounds__(256) sift_emit_kernel(const SiftEmitJob* __restrict__ jobs)
+{
+  const SiftEmitJob& j = jobs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= j.n3) return;
+  if (!j.flags[i]) return;
+  const float4 p = j.pts[i / 3];
+  j.dst[j.pos[i]] = make_float4(p.x, p.y, p.z, __uint_as_float(0xff000000u));  // copyPointCloud: default colour
+}
+
+// ---------------------------------------------------------------- K7 FPFH
+struct FpfhJob {
+  GridView g;             // surface index
+  const float4* normals;  // per original surface point
+  const float4* kp;       // keypoints
+  int nk;
+  uint32_t* need;         // per slot
+  float* spfh;            // n x 33 per slot
+  float* desc_raw;        // nk x 33
+  uint32_t* valid3;       // nk x 3
+};
+
+__global__ void __launch_bounds__(FB) fpfh_mark_kernel(const FpfhJob* __restrict__ jobs, float r2, int rv)
+{
+  const FpfhJob& j = jobs[blockIdx.y];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= j.nk) return;
+  const float4 q = j.kp[t];
+  for_each_in_radius(j.g, q.x, q.y, q.z, r2, rv, [&](int k, const float4&, float) { j.need[k] = 1u; });
+}
+
+// pcl::computePairFeatures [PCL-recall pcl/features/impl/pfh.hpp]; the FPFH member ignores its return
+// value, so degenerate pairs still vote with f1 = f2 = f3 = 0.
+__device__ __forceinline__ void pair_features(const float4& p1, const float4& n1, const float4& p2, const float4& n2, float* f1, float* f2,
+                                              float* f3)
+{
+  float dx = p2.x - p1.x, dy = p2.y - p1.y, dz = p2.z - p1.z;
+  const float f4 = sqrtf((dx * dx + dy * dy) + dz * dz);
+  if (f4 == 0.0f) { *f1 = *f2 = *f3 = 0.0f; return; }
+  float ax = n1.x, ay = n1.y, az = n1.z, bx = n2.x, by = n2.y, bz = n2.z;
+  const float angle1 = ((ax * dx + ay * dy) + az * dz) / f4;
+  const float angle2 = ((bx * dx + by * dy) + bz * dz) / f4;
+  const float fa1 = fabsf(angle1), fa2 = fabsf(angle2);
+  // acos(|a1|) > acos(|a2|)  <=>  |a1| < |a2| with both inside [0, 1] (NaN otherwise)
+  if ((fa1 <= 1.0f) && (fa2 <= 1.0f) && (fa1 < fa2)) {
+    float t;
+    t = ax; ax = bx; bx = t;
+    t = ay; ay = by; by = t;
+    t = az; az = bz; bz = t;
+    dx *= -1.f; dy *= -1.f; dz *= -1.f;
+    *f3 = -angle2;
+  } else {
+    *f3 = angle1;
+  }
+  float vx = dy * az - dz * ay, vy = dz * ax - dx * az, vz = dx * ay - dy * ax;
+  const float v_norm = sqrtf((vx * vx + vy * vy) + vz * vz);
+  if (v_norm == 0.0f) { *f1 = *f2 = *f3 = 0.0f; return; }
+  vx /= v_norm; vy /= v_norm; vz /= v_norm;
+  const float wx = ay * vz - az * vy, wy = az * vx - ax * vz, wz = ax * vy - ay * vx;
+  *f2 = (vx * bx + vy * by) + vz * bz;
+  *f1 = em::atan2f_((wx * bx + wy * by) + wz * bz, (ax * bx + ay * by) + az * bz);
+}
+
+__device__ __forceinline__ int clampbin(int h)
+{
+  return h < 0 ? 0 : (h > 10 ? 10 : h);
+}
+
+__global__ void __launch_bounds__(FB) spfh_kernel(const FpfhJob* __restrict__ jobs, float r2, int rv)
+{
+  __shared__ unsigned short cnt[33 * FB];
+  const FpfhJob& j = jobs[blockIdx.y];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= j.g.n) return;
+  if (!j.need[k]) return;
+  for (int b = 0; b < 33; ++b) cnt[b * FB + threadIdx.x] = 0;
+  const float4 p = j.g.pts[k];
+  const float4 np = j.normals[j.g.orig ? j.g.orig[k] : k];
+  const float d_pi = 1.0f / (2.0f * 3.14159265358979323846f);
+  int n = 0;
+  for_each_in_radius(j.g, p.x, p.y, p.z, r2, rv, [&](int q, const float4& pq, float) {
+    ++n;
+    if (q == k) return;
+    const float4 nq = j.normals[j.g.orig ? j.g.orig[q] : q];
+    float f1, f2, f3;
+    pair_features(p, np, pq, nq, &f1, &f2, &f3);
+    const int h1 = clampbin((int)floor(11 * (((double)f1 + 3.14159265358979323846) * (double)d_pi)));
+    const int h2 = clampbin((int)floor(11 * (((double)f2 + 1.0) * 0.5)));
+    const int h3 = clampbin((int)floor(11 * (((double)f3 + 1.0) * 0.5)));
+    cnt[h1 * FB + threadIdx.x]++;
+    cnt[(11 + h2) * FB + threadIdx.x]++;
+    cnt[(22 + h3) * FB + threadIdx.x]++;
+  });
+  // every increment of one histogram is the same float, so a bin's value depends
+  // only on its vote count: replay the additions.
+  const float hist_incr = 100.0f / (float)(n - 1);
+  float* out = j.spfh + (size_t)k * 33;
+  for (int b = 0; b < 33; ++b) {
+    const int c = cnt[b * FB + threadIdx.x];
+    float h = 0.f;
+    for (int t = 0; t < c; ++t) h += hist_incr;
+    out[b] = h;
+  }
+}
+
+// weightPointSPFHSignature: one thread per (keypoint, feature block of 11 bins)
+__global__ void __launch_bounds__(FB) fpfh_weight_kernel(const FpfhJob* __restrict__ jobs, float r2, int rv)
+{
+  const FpfhJob& j = jobs[blockIdx.y];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= j.nk * 3) return;
+  const int kp = t / 3, f = t - kp * 3;
+  const float4 q = j.kp[kp];
+  float acc[11];
+#pragma unroll
+  for (int i = 0; i < 11; ++i) acc[i] = 0.f;
+  double sum = 0.0;
+  int found = 0;
+  for_each_in_radius(j.g, q.x, q.y, q.z, r2, rv, [&](int k, const float4&, float d2) {
+    ++found;
+    if (d2 == 0.f) return;
+    const float weight = 1.0f / d2;
+    const float* h = j.spfh + (size_t)k * 33 + f * 11;
+#pragma unroll
+    for (int i = 0; i < 11; ++i) {
+      const float val = h[i] * weight;
+      sum += (double)val;
+      acc[i] += val;
+    }
+  });
+  if (sum != 0.0) sum = 100.0 / sum;
+  bool ok = found > 0;
+#pragma unroll
+  for (int i = 0; i < 11; ++i) {
+    const float v = acc[i] * (float)sum;
+    if (!isfinite(v)) ok = false;
+    j.desc_raw[(size_t)kp * 33 + f * 11 + i] = v;
+  }
+  j.valid3[t] = ok ? 1u : 0u;
+}
+
+struct FpfhFlagJob {
+  const uint32_t* valid3;
+  uint32_t* flags;
+  int nk;
+};
+__global__ void __launch_bounds__(256) fpfh_flag_kernel(const FpfhFlagJob* __restrict__ jobs)
+{
+  const FpfhFlagJob& j = jobs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= j.nk) return;
+  j.flags[i] = (j.valid3[3 * i] & j.valid3[3 * i + 1] & j.valid3[3 * i + 2]);
+}
+
+struct FpfhEmitJob {
+  const float4* kp;
+  const float* desc_raw;
+  const uint32_t* flags;
+  const uint32_t* pos;
+  float4* kp_out;
+  float* desc_out;
+  int nk;
+};
+__global__ void __launch_bounds__(256) fpfh_emit_kernel(const FpfhEmitJob* __restrict__ jobs)
+{
+  const FpfhEmitJob& j = jobs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= j.nk * 33) return;
+  const int kp = i / 33, b = i - kp * 33;
+  if (!j.flags[kp]) return;
+  const uint32_t o = j.pos[kp];
+  j.desc_out[(size_t)o * 33 + b] = j.desc_raw[i];
+  if (b == 0) j.kp_out[o] = j.kp[kp];
+}
+
+}  // namespace
+
+// ===========================================================================
+void remove_outliers_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, double radius, int min_nb,
+                           std::vector<DCloud>& out, std::vector<DBuf<int>>* counts)
+{
+  const int M = (int)clouds.size();
+  out.clear();
+  out.resize(M);
+  if (counts) { counts->clear(); counts->resize(M); }
+  if (M == 0) return;
+  std::vector<int> ns(M);
+  for (int m = 0; m < M; ++m) ns[m] = clouds[m].n;
+  int total = 0;
+  std::vector<Seg> segs = make_segs(ns, &total);
+  if (total == 0) return;
+  DBuf<uint32_t> flags(c, total), pos(c, total);
+  std::vector<OutlierJob> jobs(M);
+  for (int m = 0; m < M; ++m) {
+    jobs[m].g = idx[m].v;
+    jobs[m].flags = flags.p + segs[m].off;
+    jobs[m].counts = nullptr;
+    if (counts) {
+      (*counts)[m].alloc(c, ns[m]);
+      jobs[m].counts = (*counts)[m].p;
+    }
+  }
+  DBuf<OutlierJob> dj = to_device(c, jobs);
+  const float r2 = (float)(radius * radius);
+  const int rv = radius_voxels(radius, idx[0].v.leaf);
+  const int mx = max_n(clouds);
+  MM_LAUNCH(c, outlier_kernel, dim3((mx + FB - 1) / FB, M), FB, 0, dj.p, r2, rv, min_nb);
+  std::vector<int> totals;
+  scan_flags_batch(c, flags.p, pos.p, segs, totals);
+  std::vector<CompactJob> cj(M);
+  for (int m = 0; m < M; ++m) {
+    out[m].n = totals[m];
+    out[m].pts.alloc(c, totals[m]);
+    cj[m] = CompactJob{clouds[m].pts, flags.p + segs[m].off, pos.p + segs[m].off, out[m].pts.p, ns[m]};
+  }
+  DBuf<CompactJob> dcj = to_device(c, cj);
+  MM_LAUNCH(c, compact_points_kernel, dim3((mx + 255) / 256, M), 256, 0, dcj.p);
+}
+
+void normals_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, double radius,
+                   std::vector<DBuf<float4>>& normals)
+{
+  const int M = (int)clouds.size();
+  normals.clear();
+  normals.resize(M);
+  if (M == 0) return;
+  std::vector<NormalJob> jobs(M);
+  for (int m = 0; m < M; ++m) {
+    normals[m].alloc(c, clouds[m].n);
+    jobs[m].g = idx[m].v;
+    jobs[m].normals = normals[m].p;
+  }
+  const int mx = max_n(clouds);
+  if (mx == 0) return;
+  DBuf<NormalJob> dj = to_device(c, jobs);
+  const float r2 = (float)(radius * radius);
+  const int rv = radius_voxels(radius, idx[0].v.leaf);
+  MM_LAUNCH(c, normals_kernel, dim3((mx + FB - 1) / FB, M), FB, 0, dj.p, r2, rv);
+}
+
+void sift_batch(Ctx& c, const std::vector<CloudView>& clouds, float min_scale, int n_octaves, int n_scales, float min_contrast,
+                std::vector<DCloud>& keypoints, std::vector<DBuf<float>>* dog0)
+{
+  const int M = (int)clouds.size();
+  keypoints.clear();
+  keypoints.resize(M);
+  if (dog0) { dog0->clear(); dog0->resize(M); }
+  if (M == 0) return;
+  if (n_scales != 3) throw std::runtime_error("sift_batch: the reference path uses 3 scales per octave");
+  std::vector<char> active(M, 1);
+  std::vector<CloudView> cur = clouds;
+  std::vector<std::vector<DCloud>> octave_kp(M);
+  std::vector<std::vector<DCloud>> keep_alive;  // octave clouds stay alive until the stream drains
+  float scale = min_scale;
+  for (int oct = 0; oct < n_octaves; ++oct) {
+    const float s = 1.0f * scale;
+    // maps that dropped out keep an empty view
+    std::vector<CloudView> in(M);
+    for (int m = 0; m < M; ++m) in[m] = active[m] ? cur[m] : CloudView{nullptr, 0};
+    keep_alive.emplace_back();
+    std::vector<DCloud>& oc = keep_alive.back();
+    voxel_downsample_batch(c, in, s, oc, nullptr);
+    bool any = false;
+    std::vector<CloudView> ov(M);
+    for (int m = 0; m < M; ++m) {
+      if (active[m] && oc[m].n < 25) active[m] = 0;  // "break": no further octaves for this cloud
+      ov[m] = active[m] ? oc[m].view() : CloudView{nullptr, 0};
+      cur[m] = oc[m].view();
+      any = any || active[m];
+    }
+    if (!any) break;
+    std::vector<DIndex> idx;
+    build_index_batch(c, ov, s, 2, 0, 0, idx);
+    // scales[i] = base * 2^((i-1)/3), i = 0..5 ; sigma^2 = powf(scale, 2)
+    float scales[6];
+    SiftScales sc;
+    for (int i = 0; i < 6; ++i) {
+      scales[i] = scale * powf(2.0f, (1.0f * (float)i - 1.0f) / (float)n_scales);
+      sc.sigma_sqr[i] = powf(scales[i], 2.0f);
+    }
+    const float max_radius = 3.0f * scales[5];
+    const float r2 = (float)((double)max_radius * (double)max_radius);
+    const int rv = radius_voxels((double)max_radius, s);
+    std::vector<int> ns(M), n3(M);
+    for (int m = 0; m < M; ++m) { ns[m] = ov[m].n; n3[m] = ov[m].n * 3; }
+    int total3 = 0;
+    std::vector<Seg> segs3 = make_segs(n3, &total3);
+    DBuf<uint32_t> flags(c, total3), pos(c, total3);
+    std::vector<DBuf<float>> dog(M);
+    std::vector<SiftJob> jobs(M);
+    for (int m = 0; m < M; ++m) {
+      dog[m].alloc(c, (size_t)ns[m] * 5);
+      jobs[m].g = idx[m].v;
+      jobs[m].dog = dog[m].p;
+      jobs[m].flags = flags.p + segs3[m].off;
+    }
+    DBuf<SiftJob> dj = to_device(c, jobs);
+    const int mx = max_n(ov);
+    const dim3 grid((mx + FB - 1) / FB, M);
+    MM_LAUNCH(c, sift_scale_space_kernel, grid, FB, 0, dj.p, sc, r2, rv);
+    MM_LAUNCH(c, sift_extrema_kernel, grid, FB, 0, dj.p, min_contrast);
+    std::vector<int> totals;
+    scan_flags_batch(c, flags.p, pos.p, segs3, totals);
+    std::vector<SiftEmitJob> ej(M);
+    for (int m = 0; m < M; ++m) {
+      octave_kp[m].emplace_back();
+      DCloud& k = octave_kp[m].back();
+      k.n = totals[m];
+      k.pts.alloc(c, totals[m]);
+      ej[m] = SiftEmitJob{ov[m].pts, flags.p + segs3[m].off, pos.p + segs3[m].off, k.pts.p, n3[m]};
+    }
+    DBuf<SiftEmitJob> dej = to_device(c, ej);
+    MM_LAUNCH(c, sift_emit_kernel, dim3((mx * 3 + 255) / 256, M), 256, 0, dej.p);
+    if (dog0 && oct == 0)
+      for (int m = 0; m < M; ++m) (*dog0)[m] = std::move(dog[m]);
+    scale *= 2;
+  }
+  for (int m = 0; m < M; ++m) {
+    int tot = 0;
+    for (const DCloud& k : octave_kp[m]) tot += k.n;
+    keypoints[m].n = tot;
+    keypoints[m].pts.alloc(c, tot);
+    int off = 0;
+    for (const DCloud& k : octave_kp[m]) {
+      if (k.n) MM_CUDA(cudaMemcpyAsync(keypoints[m].pts.p + off, k.pts.p, (size_t)k.n * sizeof(float4), cudaMemcpyDeviceToDevice, c.stream));
+      off += k.n;
+    }
+  }
+}
+
+void fpfh_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<const float4*>& normals,
+                std::vector<DCloud>& keypoints, double radius, std::vector<DBuf<float>>& desc, std::vector<DBuf<float>>* spfh_dbg)
+{
+  const int M = (int)clouds.size();
+  desc.clear();
+  desc.resize(M);
+  if (spfh_dbg) { spfh_dbg->clear(); spfh_dbg->resize(M); }
+  if (M == 0) return;
+  std::vector<int> nks(M);
+  int mxk = 0;
+  for (int m = 0; m < M; ++m) { nks[m] = keypoints[m].n; mxk = std::max(mxk, nks[m]); }
+  int totalk = 0;
+  std::vector<Seg> segk = make_segs(nks, &totalk);
+  const int mx = max_n(clouds);
+  if (totalk == 0 || mx == 0) {
+    for (int m = 0; m < M; ++m) { keypoints[m].n = 0; keypoints[m].pts.release(); }
+    return;
+  }
+  std::vector<DBuf<uint32_t>> need(M), valid3(M);
+  std::vector<DBuf<float>> spfh(M), raw(M);
+  std::vector<FpfhJob> jobs(M);
+  for (int m = 0; m < M; ++m) {
+    need[m].alloc(c, clouds[m].n);
+    need[m].zero(c);
+    spfh[m].alloc(c, (size_t)clouds[m].n * 33);
+    if (spfh_dbg) spfh[m].zero(c);
+    raw[m].alloc(c, (size_t)nks[m] * 33);
+    valid3[m].alloc(c, (size_t)nks[m] * 3);
+    jobs[m].g = idx[m].v;
+    jobs[m].normals = normals[m];
+    jobs[m].kp = keypoints[m].pts.p;
+    jobs[m].nk = nks[m];
+    jobs[m].need = need[m].p;
+    jobs[m].spfh = spfh[m].p;
+    jobs[m].desc_raw = raw[m].p;
+    jobs[m].valid3 = valid3[m].p;
+  }
+  DBuf<FpfhJob> dj = to_device(c, jobs);
+  const float r2 = (float)(radius * radius);
+  const int rv = radius_voxels(radius, idx[0].v.leaf);
+  MM_LAUNCH(c, fpfh_mark_kernel, dim3((mxk + FB - 1) / FB, M), FB, 0, dj.p, r2, rv);
+  MM_LAUNCH(c, spfh_kernel, dim3((mx + FB - 1) / FB, M), FB, 0, dj.p, r2, rv);
+  MM_LAUNCH(c, fpfh_weight_kernel, dim3((mxk * 3 + FB - 1) / FB, M), FB, 0, dj.p, r2, rv);
+  DBuf<uint32_t> flags(c, totalk), pos(c, totalk);
+  std::vector<FpfhFlagJob> fj(M);
+  for (int m = 0; m < M; ++m) fj[m] = FpfhFlagJob{valid3[m].p, flags.p + segk[m].off, nks[m]};
+  DBuf<FpfhFlagJob> dfj = to_device(c, fj);
+  MM_LAUNCH(c, fpfh_flag_kernel, dim3((mxk + 255) / 256, M), 256, 0, dfj.p);
+  std::vector<int> totals;
+  scan_flags_batch(c, flags.p, pos.p, segk, totals);
+  std::vector<DCloud> kept(M);
+  std::vector<FpfhEmitJob> ej(M);
+  for (int m = 0; m < M; ++m) {
+    kept[m].n = totals[m];
+    kept[m].pts.alloc(c, totals[m]);
+    desc[m].alloc(c, (size_t)totals[m] * 33);
+    ej[m] = FpfhEmitJob{keypoints[m].pts.p, raw[m].p, flags.p + segk[m].off, pos.p + segk[m].off, kept[m].pts.p, desc[m].p, nks[m]};
+  }
+  DBuf<FpfhEmitJob> dej = to_device(c, ej);
+  MM_LAUNCH(c, fpfh_emit_kernel, dim3((mxk * 33 + 255) / 256, M), 256, 0, dej.p);
+  for (int m = 0; m < M; ++m) keypoints[m] = std::move(kept[m]);
+  if (spfh_dbg)
+    for (int m = 0; m < M; ++m) (*spfh_dbg)[m] = std::move(spfh[m]);
+}
+
+}  // namespace mm3d

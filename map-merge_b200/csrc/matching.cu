@@ -1,0 +1,569 @@
+// matching.cu — per-pair descriptor matching and RANSAC (all pairs per launch).
+//   K9  reciprocal k-NN cross-matching  <- map_merge_3d/src/matching.cpp:31-93 (the reference's own algorithm;
+//       pcl::search::KdTree<DescriptorT> == exact L2 k-NN, flann::L2_Simple accumulation order)
+//   K10 RANSAC + final SVD              <- src/matching.cpp:110-140
+//       (pcl::registration::CorrespondenceRejectorSampleConsensus, pcl::RandomSampleConsensus,
+//        pcl::SampleConsensusModelRegistration, boost::mt19937(12345))
+#include <algorithm>
+
+#include "mm3d_internal.cuh"
+
+namespace mm3d {
+
+namespace {
+
+constexpr int KMAX = 16;
+
+struct KnnJob {
+  const float* A;
+  int na;
+  const float* B;
+  int nb;
+  int k;
+  int* idx;     // na x k
+  float* dist;  // na x k
+};
+
+// Exact FP32 k-NN of every row of A among the rows of B.  One thread owns one
+// query row (registers); B streams through shared memory, every thread reads the
+// same B element at a time (broadcast).  Distances accumulate dimension by
+// dimension without contraction, like flann::L2_Simple; ties keep the lower index.
+template <int D>
+__global__ void __launch_bounds__(128) knn_small_kernel(const KnnJob* __restrict__ jobs)
+{
+  constexpr int TB = 64;
+  __shared__ float sb[TB * D];
+  const KnnJob j = jobs[blockIdx.y];
+  if (blockIdx.x * blockDim.x >= j.na) return;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = row < j.na;
+  float a[D];
+#pragma unroll
+  for (int t = 0; t < D; ++t) a[t] = live ? j.A[(size_t)row * D + t] : 0.f;
+  float bd[KMAX];
+  int bi[KMAX];
+  int cnt = 0;
+  const int k = j.k;
+  for (int base = 0; base < j.nb; base += TB) {
+    const int tb = min(TB, j.nb - base);
+    __syncthreads();
+    for (int e = threadIdx.x; e < tb * D; e += blockDim.x) sb[e] = j.B[(size_t)base * D + e];
+    __syncthreads();
+    if (!live) continue;
+    for (int r = 0; r < tb; ++r) {
+      const float* b = sb + r * D;
+      float acc = 0.f;
+#pragma unroll
+      for (int t = 0; t < D; ++t) {
+        const float diff = a[t] - b[t];
+        acc += diff * diff;
+      }
+      if (cnt == k && !(acc < bd[k - 1])) continue;
+      int pos = (cnt < k) ? cnt : k - 1;
+      while (pos > 0 && acc < bd[pos - 1]) {
+        bd[pos] = bd[pos - 1];
+        bi[pos] = bi[pos - 1];
+        --pos;
+      }
+      bd[pos] = acc;
+      bi[pos] = base + r;
+      if (cnt < k) ++cnt;
+    }
+  }
+  if (live)
+    for (int t = 0; t < k; ++t) {
+      j.idx[(size_t)row * k + t] = t < cnt ? bi[t] : -1;
+      j.dist[(size_t)row * k + t] = t < cnt ? bd[t] : 0.f;
+    }
+}
+
+// Any dimension (PFH 125 ... SHOT 1344): a block owns 64 query rows and a tile of
+// 32 B rows; the dimension loop runs in chunks staged through shared memory while
+// each thread keeps the running sums for (its row) x (16 of the 32 B rows).
+__global__ void __launch_bounds__(128) knn_generic_kernel(const KnnJob* __restrict__ jobs, int D)
+{
+  constexpr int QA = 64, TB = 32, DC = 32;
+  __shared__ float sa[QA][DC + 1];
+  __shared__ float sbm[TB][DC + 1];
+  __shared__ float sd[QA][TB + 1];
+  const KnnJob j = jobs[blockIdx.y];
+  const int row0 = blockIdx.x * QA;
+  if (row0 >= j.na) return;
+  const int q = threadIdx.x & (QA - 1);  // query row within the block
+  const int half = threadIdx.x >> 6;     // which 16 B rows
+  const int row = row0 + q;
+  float bd[KMAX];
+  int bi[KMAX];
+  int cnt = 0;
+  const int k = j.k;
+  for (int base = 0; base < j.nb; base += TB) {
+    float acc[TB / 2];
+#pragma unroll
+    for (int r = 0; r < TB / 2; ++r) acc[r] = 0.f;
+    for (int d0 = 0; d0 < D; d0 += DC) {
+      const int dc = min(DC, D - d0);
+      __syncthreads();
+      for (int e = threadIdx.x; e < QA * DC; e += blockDim.x) {
+        const int rr = e / DC, dd = e - rr * DC;
+        sa[rr][dd] = (row0 + rr < j.na && dd < dc) ? j.A[(size_t)(row0 + rr) * D + d0 + dd] : 0.f;
+      }
+      for (int e = threadIdx.x; e < TB * DC; e += blockDim.x) {
+        const int rr = e / DC, dd = e - rr * DC;
+        sbm[rr][dd] = (base + rr < j.nb && dd < dc) ? j.B[(size_t)(base + rr) * D + d0 + dd] : 0.f;
+      }
+      __syncthreads();
+      for (int dd = 0; dd < dc; ++dd) {
+        const float av = sa[q][dd];
+#pragma unroll
+        for (int r = 0; r < TB / 2; ++r) {
+          const float diff = av - sbm[half * (TB / 2) + r][dd];
+          acc[r] += diff * diff;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < TB / 2; ++r) sd[q][half * (TB / 2) + r] = acc[r];
+    __syncthreads();
+    if (half == 0 && row < j.na) {
+      const int tb = min(TB, j.nb - base);
+      for (int r = 0; r < tb; ++r) {
+        const float v = sd[q][r];
+        if (cnt == k && !(v < bd[k - 1])) continue;
+        int pos = (cnt < k) ? cnt : k - 1;
+        while (pos > 0 && v < bd[pos - 1]) {
+          bd[pos] = bd[pos - 1];
+          bi[pos] = bi[pos - 1];
+          --pos;
+        }
+        bd[pos] = v;
+        bi[pos] = base + r;
+        if (cnt < k) ++cnt;
+      }
+    }
+  }
+  if (half == 0 && row < j.na)
+    for (int t = 0; t < k; ++t) {
+      j.idx[(size_t)row * k + t] = t < cnt ? bi[t] : -1;
+      j.dist[(size_t)row * k + t] = t < cnt ? bd[t] : 0.f;
+    }
+}
+
+struct CrossJob {
+  const int* fwd_idx;
+  const float* fwd_dist;
+  const int* back_idx;
+  int ns, kf, kb;
+  uint32_t* flags;  // ns
+  int* match;       // ns
+  float* dist;      // ns
+};
+// matching.cpp:65-90: first forward match (ascending distance) whose backward k-NN contains i
+__global__ void __launch_bounds__(256) cross_match_kernel(const CrossJob* __restrict__ jobs)
+{
+  const CrossJob& j = jobs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= j.ns) return;
+  uint32_t f = 0;
+  int mm = -1;
+  float dd = 0.f;
+  for (int t = 0; t < j.kf && !f; ++t) {
+    const int m = j.fwd_idx[(size_t)i * j.kf + t];
+    if (m < 0) break;
+    for (int b = 0; b < j.kb; ++b)
+      if (j.back_idx[(size_t)m * j.kb + b] == i) {
+        f = 1;
+        mm = m;
+        dd = j.fwd_dist[(size_t)i * j.kf + t];
+        break;
+      }
+  }
+  j.flags[i] = f;
+  j.match[i] = mm;
+  j.dist[i] = dd;
+}
+
+struct CorrEmitJob {
+  const uint32_t* flags;
+  const uint32_t* pos;
+  const int* match;
+  const float* dist;
+  int2* pairs;
+  float* odist;
+  int ns;
+};
+__global__ void __launch_bounds__(256) corr_emit_kernel(const CorrEmitJob* __restrict__ jobs)
+{
+  const CorrEmitJob& j = jobs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= j.ns) return;
+  if (!j.flags[i]) return;
+  const uint32_t o = j.pos[i];
+  j.pairs[o] = make_int2(i, j.match[i]);
+  j.odist[o] = j.dist[i];
+}
+
+// ---------------------------------------------------------------- RANSAC
+constexpr int MAX_HYP = 1001;  // iterations_ > max_iterations_(1000) breaks after the 1001st
+
+struct RansacJob {
+  const float4* skp;
+  const float4* tkp;
+  const int2* corr;
+  int nc;
+  int* shuffled;   // nc scratch
+  int* samples;    // MAX_HYP x 3 (positions into corr)
+  int* n_samples;  // 1
+  int* counts;     // MAX_HYP
+  float* models;   // MAX_HYP x 12
+  int* inliers;    // nc
+  RansacOut* out;
+};
+
+struct Mt19937 {
+  uint32_t* s;  // 624 words in shared memory
+  int idx;
+  __device__ void seed(uint32_t v)
+  {
+    s[0] = v;
+    for (int i = 1; i < 624; ++i) s[i] = 1812433253u * (s[i - 1] ^ (s[i - 1] >> 30)) + (uint32_t)i;
+    idx = 624;
+  }
+  __device__ uint32_t next()
+  {
+    if (idx >= 624) {
+      for (int i = 0; i < 624; ++i) {
+        const uint32_t y = (s[i] & 0x80000000u) | (s[(i + 1) % 624] & 0x7fffffffu);
+        s[i] = s[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      idx = 0;
+    }
+    uint32_t y = s[idx++];
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+  }
+};
+
+// One block per pair, thread 0 works: sample-distance threshold, then the whole
+// sample sequence the sequential RANSAC would draw (it depends only on the RNG
+// and on source keypoint coordinates, never on inlier counts).
+__global__ void __launch_bounds__(32) ransac_sample_kernel(const RansacJob* __restrict__ jobs)
+{
+  __shared__ uint32_t mt_state[624];
+  const RansacJob& j = jobs[blockIdx.x];
+  if (threadIdx.x != 0) return;
+  const int nc = j.nc;
+  j.out->sample_dist_thresh = 0.0;
+  if (nc < 3) {
+    *j.n_samples = 0;
+    return;
+  }
+  // computeSampleDistanceThreshold: PCA of the source correspondences
+  float a[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i = 0; i < nc; ++i) {
+    const float4 p = j.skp[j.corr[i].x];
+    a[0] += p.x * p.x; a[1] += p.x * p.y; a[2] += p.x * p.z;
+    a[3] += p.y * p.y; a[4] += p.y * p.z; a[5] += p.z * p.z;
+    a[6] += p.x; a[7] += p.y; a[8] += p.z;
+  }
+  const float n = (float)nc;
+  for (int k = 0; k < 9; ++k) a[k] /= n;
+  float cov[9];
+  cov[0] = a[0] - a[6] * a[6];
+  cov[1] = a[1] - a[6] * a[7];
+  cov[2] = a[2] - a[6] * a[8];
+  cov[4] = a[3] - a[7] * a[7];
+  cov[5] = a[4] - a[7] * a[8];
+  cov[8] = a[5] - a[8] * a[8];
+  cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+  float ev[3];
+  em::eigen33_values(cov, ev);
+  double thr = (double)((sqrtf(ev[0]) + sqrtf(ev[1])) + sqrtf(ev[2])) / 3.0;
+  thr *= thr;
+  j.out->sample_dist_thresh = thr;
+
+  Mt19937 rng;
+  rng.s = mt_state;
+  rng.seed(12345u);
+  for (int i = 0; i < nc; ++i) j.shuffled[i] = i;
+  int ns = 0;
+  for (int h = 0; h < MAX_HYP; ++h) {
+    bool good = false;
+    int s0 = 0, s1 = 0, s2 = 0;
+    for (int iter = 0; iter < 1000; ++iter) {
+      for (int i = 0; i < 3; ++i) {
+        const uint32_t rnd = rng.next() >> 1;  // uniform_int<>(0, INT_MAX) on mt19937
+        const int o = i + (int)((unsigned long long)rnd % (unsigned long long)(nc - i));
+        const int t = j.shuffled[i];
+        j.shuffled[i] = j.shuffled[o];
+        j.shuffled[o] = t;
+      }
+      s0 = j.shuffled[0]; s1 = j.shuffled[1]; s2 = j.shuffled[2];
+      const float4 pa = j.skp[j.corr[s0].x], pb = j.skp[j.corr[s1].x], pc = j.skp[j.corr[s2].x];
+      const float ax = pb.x - pa.x, ay = pb.y - pa.y, az = pb.z - pa.z;
+      const float bx = pc.x - pa.x, by = pc.y - pa.y, bz = pc.z - pa.z;
+      const float cx = pc.x - pb.x, cy = pc.y - pb.y, cz = pc.z - pb.z;
+      if ((double)(ax * ax + ay * ay + az * az) > thr && (double)(bx * bx + by * by + bz * bz) > thr &&
+          (double)(cx * cx + cy * cy + cz * cz) > thr) {
+        good = true;
+        break;
+      }
+    }
+    if (!good) break;
+    j.samples[h * 3 + 0] = s0;
+    j.samples[h * 3 + 1] = s1;
+    j.samples[h * 3 + 2] = s2;
+    ++ns;
+  }
+  *j.n_samples = ns;
+}
+
+// literal Eigen::umeyama (no scaling) over n points, sequential sums
+template <typename T, typename GetS, typename GetD>
+__device__ void umeyama_seq(int n, GetS src, GetD dst, T* Rt)
+{
+  const T one_over_n = T(1) / (T)n;
+  T sm[3] = {0, 0, 0}, dm[3] = {0, 0, 0};
+  for (int i = 0; i < n; ++i) {
+    T s[3], d[3];
+    src(i, s);
+    dst(i, d);
+    for (int a = 0; a < 3; ++a) { sm[a] += s[a]; dm[a] += d[a]; }
+  }
+  for (int a = 0; a < 3; ++a) { sm[a] *= one_over_n; dm[a] *= one_over_n; }
+  T sigma[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < n; ++i) {
+    T s[3], d[3];
+    src(i, s);
+    dst(i, d);
+    for (int a = 0; a < 3; ++a) { s[a] -= sm[a]; d[a] -= dm[a]; }
+    for (int r = 0; r < 3; ++r)
+      for (int cc = 0; cc < 3; ++cc) sigma[r * 3 + cc] += (one_over_n * d[r]) * s[cc];
+  }
+  em::umeyama_from_sigma<T>(sigma, sm, dm, Rt);
+}
+
+// one warp per hypothesis: lane 0 solves the 3-point Umeyama in double, all lanes vote
+__global__ void __launch_bounds__(128) ransac_score_kernel(const RansacJob* __restrict__ jobs, double thresh)
+{
+  const RansacJob& j = jobs[blockIdx.y];
+  const int h = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (h >= *j.n_samples) return;
+  float m[12];
+  if (lane == 0) {
+    const int* smp = j.samples + h * 3;
+    double Rt[16];
+    umeyama_seq<double>(
+        3,
+        [&](int i, double* o) { const float4 p = j.skp[j.corr[smp[i]].x]; o[0] = p.x; o[1] = p.y; o[2] = p.z; },
+        [&](int i, double* o) { const float4 p = j.tkp[j.corr[smp[i]].y]; o[0] = p.x; o[1] = p.y; o[2] = p.z; }, Rt);
+    for (int i = 0; i < 12; ++i) m[i] = (float)Rt[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 12; ++i) m[i] = __shfl_sync(0xffffffffu, m[i], 0);
+  int cnt = 0;
+  for (int i = lane; i < j.nc; i += 32) {
+    const int2 cr = j.corr[i];
+    const float4 s = j.skp[cr.x], t = j.tkp[cr.y];
+    float px, py, pz;
+    em::transform_point(m, s.x, s.y, s.z, &px, &py, &pz);
+    const float ex = px - t.x, ey = py - t.y, ez = pz - t.z;
+    if ((double)((ex * ex + ey * ey) + ez * ez) < thresh) ++cnt;
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (lane == 0) {
+    j.counts[h] = cnt;
+    for (int i = 0; i < 12; ++i) j.models[h * 12 + i] = m[i];
+  }
+}
+
+__device__ bool is_identity4(const float* t)
+{
+  for (int i = 0; i < 4; ++i)
+    for (int c = 0; c < 4; ++c) {
+      const float v = t[i * 4 + c];
+      if (i == c) {
+        if (!(fabsf(v - 1.0f) <= 1e-5f * fminf(fabsf(v), 1.0f))) return false;
+      } else {
+        if (!(fabsf(v) <= 1e-5f)) return false;
+      }
+    }
+  return true;
+}
+
+// replay of pcl::RandomSampleConsensus::computeModel's adaptive loop over the
+// pre-scored hypotheses, then inlier selection and the final float SVD.
+__global__ void __launch_bounds__(32) ransac_select_kernel(const RansacJob* __restrict__ jobs, double thresh)
+{
+  const RansacJob& j = jobs[blockIdx.x];
+  if (threadIdx.x != 0) return;
+  RansacOut& o = *j.out;
+  for (int i = 0; i < 16; ++i) { o.T[i] = 0.f; o.best_model[i] = (i % 5 == 0) ? 1.f : 0.f; }
+  o.iterations = 0;
+  o.best_count = -2147483647;
+  o.n_inliers = 0;
+  const int nc = j.nc;
+  const int ns = *j.n_samples;
+  if (nc < 3) return;
+  int iterations = 0, n_best = -2147483647, best_h = -1;
+  double k = 1.0;
+  const double log_probability = log(1.0 - 0.99);
+  const double one_over_indices = 1.0 / (double)nc;
+  while ((double)iterations < k) {
+    if (iterations >= ns) break;  // getSamples came back empty
+    const int c = j.counts[iterations];
+    if (c > n_best) {
+      n_best = c;
+      best_h = iterations;
+      const double w = (double)n_best * one_over_indices;
+      double p_no_outliers = 1.0 - w * w * w;
+      p_no_outliers = fmax(2.220446049250313e-16, p_no_outliers);
+      p_no_outliers = fmin(1.0 - 2.220446049250313e-16, p_no_outliers);
+      k = log_probability / log(p_no_outliers);
+    }
+    ++iterations;
+    if (iterations > 1000) break;
+  }
+  o.iterations = iterations;
+  o.best_count = n_best;
+  if (best_h < 0) return;
+  float bm[16];
+  for (int i = 0; i < 12; ++i) bm[i] = j.models[best_h * 12 + i];
+  bm[12] = bm[13] = bm[14] = 0.f;
+  bm[15] = 1.f;
+  for (int i = 0; i < 16; ++i) o.best_model[i] = bm[i];
+  int ni = 0;
+  for (int i = 0; i < nc; ++i) {
+    const int2 cr = j.corr[i];
+    const float4 s = j.skp[cr.x], t = j.tkp[cr.y];
+    float px, py, pz;
+    em::transform_point(bm, s.x, s.y, s.z, &px, &py, &pz);
+    const float ex = px - t.x, ey = py - t.y, ez = pz - t.z;
+    if ((double)((ex * ex + ey * ey) + ez * ez) < thresh) j.inliers[ni++] = i;
+  }
+  if (ni < 3 || is_identity4(bm)) return;  // matching.cpp:128-133 -> zero matrix, inliers cleared
+  o.n_inliers = ni;
+  umeyama_seq<float>(
+      ni, [&](int i, float* v) { const float4 p = j.skp[j.corr[j.inliers[i]].x]; v[0] = p.x; v[1] = p.y; v[2] = p.z; },
+      [&](int i, float* v) { const float4 p = j.tkp[j.corr[j.inliers[i]].y]; v[0] = p.x; v[1] = p.y; v[2] = p.z; }, o.T);
+}
+
+}  // namespace
+
+void match_batch(Ctx& c, const std::vector<const float*>& desc, const std::vector<int>& nk, int dim, const std::vector<PairJob>& jobs,
+                 size_t k_in, std::vector<DCorr>& corr)
+{
+  const int P = (int)jobs.size();
+  corr.clear();
+  corr.resize(P);
+  if (P == 0) return;
+  if (k_in > (size_t)KMAX) throw std::runtime_error("match_batch: matching_k > 16 is not supported");
+  // forward and backward k-NN problems, 2 per pair
+  std::vector<KnnJob> kj(2 * P);
+  std::vector<DBuf<int>> idxb(2 * P);
+  std::vector<DBuf<float>> distb(2 * P);
+  int max_rows = 0, max_ns = 0;
+  for (int p = 0; p < P; ++p) {
+    const int a = jobs[p].a, b = jobs[p].b;
+    const int ns = nk[a], nt = nk[b];
+    const int kf = (int)std::min<size_t>(k_in, (size_t)nt), kb = (int)std::min<size_t>(k_in, (size_t)ns);  // KdTreeFLANN clamps k
+    idxb[2 * p].alloc(c, (size_t)ns * std::max(kf, 1));
+    distb[2 * p].alloc(c, (size_t)ns * std::max(kf, 1));
+    idxb[2 * p + 1].alloc(c, (size_t)nt * std::max(kb, 1));
+    distb[2 * p + 1].alloc(c, (size_t)nt * std::max(kb, 1));
+    kj[2 * p] = KnnJob{desc[a], (kf > 0 && k_in > 0) ? ns : 0, desc[b], nt, kf, idxb[2 * p].p, distb[2 * p].p};
+    kj[2 * p + 1] = KnnJob{desc[b], (kb > 0 && k_in > 0) ? nt : 0, desc[a], ns, kb, idxb[2 * p + 1].p, distb[2 * p + 1].p};
+    max_rows = std::max(max_rows, std::max(kj[2 * p].na, kj[2 * p + 1].na));
+    max_ns = std::max(max_ns, ns);
+  }
+  DBuf<KnnJob> dkj = to_device(c, kj);
+  if (max_rows > 0) {
+    if (dim == 33) {
+      MM_LAUNCH(c, knn_small_kernel<33>, dim3((max_rows + 127) / 128, 2 * P), 128, 0, dkj.p);
+    } else {
+      MM_LAUNCH(c, knn_generic_kernel, dim3((max_rows + 63) / 64, 2 * P), 128, 0, dkj.p, dim);
+    }
+  }
+  std::vector<int> nss(P);
+  for (int p = 0; p < P; ++p) nss[p] = (k_in > 0 && nk[jobs[p].b] > 0) ? nk[jobs[p].a] : 0;
+  std::vector<Seg> segs(P);
+  int total = 0;
+  for (int p = 0; p < P; ++p) { segs[p].off = total; segs[p].n = nss[p]; total += nss[p]; }
+  if (total == 0) return;
+  DBuf<uint32_t> flags(c, total), pos(c, total);
+  DBuf<int> match(c, total);
+  DBuf<float> mdist(c, total);
+  std::vector<CrossJob> cj(P);
+  for (int p = 0; p < P; ++p)
+    cj[p] = CrossJob{idxb[2 * p].p, distb[2 * p].p, idxb[2 * p + 1].p, nss[p], kj[2 * p].k, kj[2 * p + 1].k,
+                     flags.p + segs[p].off, match.p + segs[p].off, mdist.p + segs[p].off};
+  DBuf<CrossJob> dcj = to_device(c, cj);
+  MM_LAUNCH(c, cross_match_kernel, dim3((max_ns + 255) / 256, P), 256, 0, dcj.p);
+  std::vector<int> totals;
+  scan_flags_batch(c, flags.p, pos.p, segs, totals);
+  std::vector<CorrEmitJob> ej(P);
+  for (int p = 0; p < P; ++p) {
+    corr[p].n = totals[p];
+    corr[p].pairs.alloc(c, totals[p]);
+    corr[p].dist.alloc(c, totals[p]);
+    ej[p] = CorrEmitJob{flags.p + segs[p].off, pos.p + segs[p].off, match.p + segs[p].off, mdist.p + segs[p].off,
+                        corr[p].pairs.p, corr[p].dist.p, nss[p]};
+  }
+  DBuf<CorrEmitJob> dej = to_device(c, ej);
+  MM_LAUNCH(c, corr_emit_kernel, dim3((max_ns + 255) / 256, P), 256, 0, dej.p);
+}
+
+void ransac_batch(Ctx& c, const std::vector<CloudView>& keypoints, const std::vector<PairJob>& jobs, const std::vector<DCorr>& corr,
+                  double inlier_threshold, std::vector<RansacOut>& out, std::vector<std::vector<int>>* inliers)
+{
+  const int P = (int)jobs.size();
+  out.assign(P, RansacOut());
+  if (inliers) { inliers->clear(); inliers->resize(P); }
+  if (P == 0) return;
+  size_t tot_c = 0;
+  for (int p = 0; p < P; ++p) tot_c += (size_t)corr[p].n;
+  DBuf<int> shuffled(c, tot_c + 1), inl(c, tot_c + 1);
+  DBuf<int> samples(c, (size_t)P * MAX_HYP * 3), nsamp(c, P), counts(c, (size_t)P * MAX_HYP);
+  DBuf<float> models(c, (size_t)P * MAX_HYP * 12);
+  DBuf<RansacOut> dout(c, P);
+  std::vector<RansacJob> rj(P);
+  size_t off = 0;
+  for (int p = 0; p < P; ++p) {
+    rj[p].skp = keypoints[jobs[p].a].pts;
+    rj[p].tkp = keypoints[jobs[p].b].pts;
+    rj[p].corr = corr[p].pairs.p;
+    rj[p].nc = corr[p].n;
+    rj[p].shuffled = shuffled.p + off;
+    rj[p].inliers = inl.p + off;
+    rj[p].samples = samples.p + (size_t)p * MAX_HYP * 3;
+    rj[p].n_samples = nsamp.p + p;
+    rj[p].counts = counts.p + (size_t)p * MAX_HYP;
+    rj[p].models = models.p + (size_t)p * MAX_HYP * 12;
+    rj[p].out = dout.p + p;
+    off += (size_t)corr[p].n;
+  }
+  DBuf<RansacJob> drj = to_device(c, rj);
+  const double thresh = inlier_threshold * inlier_threshold;
+  MM_LAUNCH(c, ransac_sample_kernel, P, 32, 0, drj.p);
+  MM_LAUNCH(c, ransac_score_kernel, dim3((MAX_HYP + 3) / 4, P), 128, 0, drj.p, thresh);
+  MM_LAUNCH(c, ransac_select_kernel, P, 32, 0, drj.p, thresh);
+  dout.download(c, out.data(), P);
+  std::vector<int> hinl;
+  if (inliers) {
+    hinl.resize(tot_c + 1);
+    inl.download(c, hinl.data(), tot_c);
+  }
+  c.sync();
+  if (inliers) {
+    off = 0;
+    for (int p = 0; p < P; ++p) {
+      (*inliers)[p].assign(hinl.begin() + off, hinl.begin() + off + out[p].n_inliers);
+      off += (size_t)corr[p].n;
+    }
+  }
+}
+
+}  // namespace mm3d

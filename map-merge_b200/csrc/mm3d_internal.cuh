@@ -1,0 +1,329 @@
+// mm3d_internal.cuh — shared declarations for the sm_100a registration library.
+//
+// Design: every per-map stage runs ONCE for all maps in a 2-D
+// launch (blockIdx.y = map, or = pair in the registration loop), all work is
+// queued on one stream, and the host synchronises only where a stage's output
+// size is needed to size the next allocation.  Neighbourhood queries go through
+// a "voxel-row" index: the clouds on this path are voxel-grid outputs, i.e.
+// already sorted by (z, y, x) voxel key, so a dense table of row-bucket start
+// offsets turns a radius query into a walk over contiguous, ascending-index
+// runs — which is also the canonical summation order the parity checker uses.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "exact_math.h"
+
+namespace mm3d {
+
+#define MM_CUDA(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess)                                                                              \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " __FILE__ ":" + \
+                               std::to_string(__LINE__) + " (" #expr ")");                              \
+  } while (0)
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  long long launches = 0;  // kernels launched through this context (bench.py's gpu_launches)
+  void sync() { MM_CUDA(cudaStreamSynchronize(stream)); }
+};
+
+#define MM_LAUNCH(ctx, kernel, grid, block, smem, ...)                 \
+  do {                                                                 \
+    kernel<<<(grid), (block), (smem), (ctx).stream>>>(__VA_ARGS__);    \
+    (ctx).launches++;                                                  \
+    MM_CUDA(cudaGetLastError());                                       \
+  } while (0)
+
+// Stream-ordered device buffer.
+template <typename T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaStream_t s = nullptr;
+  DBuf() {}
+  DBuf(Ctx& c, size_t count) { alloc(c, count); }
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  DBuf(DBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+  DBuf& operator=(DBuf&& o) noexcept
+  {
+    if (this != &o) {
+      release();
+      p = o.p; n = o.n; s = o.s;
+      o.p = nullptr; o.n = 0;
+    }
+    return *this;
+  }
+  ~DBuf() { release(); }
+  void alloc(Ctx& c, size_t count)
+  {
+    release();
+    s = c.stream;
+    n = count;
+    if (count) MM_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), s));
+  }
+  void release()
+  {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr;
+    n = 0;
+  }
+  void zero(Ctx& c) { if (n) MM_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), c.stream)); }
+  void upload(Ctx& c, const T* h, size_t count) { if (count) MM_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, c.stream)); }
+  void download(Ctx& c, T* h, size_t count) const { if (count) MM_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, c.stream)); }
+};
+
+template <typename T>
+inline DBuf<T> to_device(Ctx& c, const std::vector<T>& v)
+{
+  DBuf<T> b(c, v.size());
+  b.upload(c, v.data(), v.size());
+  return b;
+}
+
+struct Seg {  // one map's slice of a concatenated array
+  int off;
+  int n;
+};
+
+struct CloudView {
+  const float4* pts;
+  int n;
+};
+
+// Voxel-grid geometry of one cloud (pcl::VoxelGrid's min_b_/div_b_).
+struct VoxGeom {
+  int min_b[3];
+  int div_b[3];
+  int passthrough;  // overflow guard hit: output = input
+  int nbits;        // bits needed for a voxel key
+};
+
+// Neighbour index over one cloud.
+struct GridView {
+  const float4* pts;      // points in cell order (the cloud itself when orig == nullptr)
+  const int* orig;        // original index of each slot, or nullptr = identity
+  const int* cell_start;  // ncell + 1 entries
+  int n;
+  float inv_leaf;
+  float leaf;
+  int min_b[3];
+  int div_v[3];
+  int shift[3];
+  int dim[3];
+};
+
+struct DIndex {
+  GridView v;
+  DBuf<int> cell_start;
+  DBuf<float4> pts_sorted;
+  DBuf<int> orig;
+};
+
+__host__ __device__ __forceinline__ int floor_to_int(float v) { return (int)floorf(v); }
+
+// ---------------------------------------------------------------------------
+// Device-side neighbourhood walks.
+// ---------------------------------------------------------------------------
+#if defined(__CUDACC__)
+
+// Visit every point with d^2 < r2, in ascending (cell z, cell y, cell x, slot)
+// order — ascending point index for a voxel-sorted cloud indexed with
+// shift y = z = 0.  rv = ceil(r / leaf) + 1 voxels.
+template <typename F>
+__device__ __forceinline__ void for_each_in_radius(const GridView& g, float qx, float qy, float qz, float r2, int rv, F f)
+{
+  const int vx = floor_to_int(qx * g.inv_leaf) - g.min_b[0];
+  const int vy = floor_to_int(qy * g.inv_leaf) - g.min_b[1];
+  const int vz = floor_to_int(qz * g.inv_leaf) - g.min_b[2];
+  int zlo = vz - rv, zhi = vz + rv, ylo = vy - rv, yhi = vy + rv;
+  if (zhi < 0 || yhi < 0 || vx + rv < 0 || zlo >= g.div_v[2] || ylo >= g.div_v[1] || vx - rv >= g.div_v[0]) return;
+  zlo = max(zlo, 0) >> g.shift[2];
+  zhi = min(zhi, g.div_v[2] - 1) >> g.shift[2];
+  ylo = max(ylo, 0) >> g.shift[1];
+  yhi = min(yhi, g.div_v[1] - 1) >> g.shift[1];
+  const float r2v = r2 * g.inv_leaf * g.inv_leaf;  // radius^2 in voxel units (pruning only)
+  for (int cz = zlo; cz <= zhi; ++cz) {
+    const int z0 = cz << g.shift[2], z1 = z0 + (1 << g.shift[2]) - 1;
+    const int dz = max(max(z0 - vz, vz - z1), 0);
+    const float fz = (float)max(dz - 1, 0);
+    for (int cy = ylo; cy <= yhi; ++cy) {
+      const int y0 = cy << g.shift[1], y1 = y0 + (1 << g.shift[1]) - 1;
+      const int dy = max(max(y0 - vy, vy - y1), 0);
+      const float fy = (float)max(dy - 1, 0);
+      const float rem = r2v - fz * fz - fy * fy;
+      if (rem < 0.0f) continue;
+      const int rx = (int)sqrtf(rem) + 2;
+      int xlo = vx - rx, xhi = vx + rx;
+      if (xhi < 0 || xlo >= g.div_v[0]) continue;
+      xlo = max(xlo, 0) >> g.shift[0];
+      xhi = min(xhi, g.div_v[0] - 1) >> g.shift[0];
+      const int base = (cz * g.dim[1] + cy) * g.dim[0];
+      const int s = g.cell_start[base + xlo], e = g.cell_start[base + xhi + 1];
+      for (int k = s; k < e; ++k) {
+        const float4 p = g.pts[k];
+        const float d2 = em::dist2_3(qx, qy, qz, p.x, p.y, p.z);
+        if (d2 < r2) f(k, p, d2);
+      }
+    }
+  }
+}
+
+// Nearest neighbour among points with (double)d2 <= bound; ties -> lower
+// original index.  Rows are visited outward from the query row so the running
+// best prunes the rest.  rv = ceil(sqrt(bound) / leaf) + 1 voxels.
+__device__ __forceinline__ bool nearest_bounded(const GridView& g, float qx, float qy, float qz, double bound, int rv, int* out_idx,
+                                                float* out_d2, float4* out_pt)
+{
+  const int vx = floor_to_int(qx * g.inv_leaf) - g.min_b[0];
+  const int vy = floor_to_int(qy * g.inv_leaf) - g.min_b[1];
+  const int vz = floor_to_int(qz * g.inv_leaf) - g.min_b[2];
+  if (vz + rv < 0 || vy + rv < 0 || vx + rv < 0 || vz - rv >= g.div_v[2] || vy - rv >= g.div_v[1] || vx - rv >= g.div_v[0]) return false;
+  const int zlo = max(vz - rv, 0) >> g.shift[2], zhi = min(vz + rv, g.div_v[2] - 1) >> g.shift[2];
+  const int ylo = max(vy - rv, 0) >> g.shift[1], yhi = min(vy + rv, g.div_v[1] - 1) >> g.shift[1];
+  const int czq = min(max(vz, 0), g.div_v[2] - 1) >> g.shift[2];
+  const int cyq = min(max(vy, 0), g.div_v[1] - 1) >> g.shift[1];
+  bool found = false;
+  float best = 0.0f;
+  int best_idx = 0x7fffffff;
+  float4 best_pt = make_float4(0.f, 0.f, 0.f, 0.f);
+  // pruning threshold in voxel units; starts at the bound
+  float lim_v = (float)bound * g.inv_leaf * g.inv_leaf * 1.0001f + 1e-3f;
+  const int nz = zhi - zlo + 1, ny = yhi - ylo + 1;
+  for (int iz = 0; iz < 2 * nz + 1; ++iz) {
+    const int cz = czq + ((iz & 1) ? (iz + 1) / 2 : -(iz / 2));
+    if (cz < zlo || cz > zhi) continue;
+    const int z0 = cz << g.shift[2], z1 = z0 + (1 << g.shift[2]) - 1;
+    const int dz = max(max(z0 - vz, vz - z1), 0);
+    const float fz = (float)max(dz - 1, 0);
+    if (fz * fz > lim_v) continue;
+    for (int iy = 0; iy < 2 * ny + 1; ++iy) {
+      const int cy = cyq + ((iy & 1) ? (iy + 1) / 2 : -(iy / 2));
+      if (cy < ylo || cy > yhi) continue;
+      const int y0 = cy << g.shift[1], y1 = y0 + (1 << g.shift[1]) - 1;
+      const int dy = max(max(y0 - vy, vy - y1), 0);
+      const float fy = (float)max(dy - 1, 0);
+      const float rem = lim_v - fz * fz - fy * fy;
+      if (rem < 0.0f) continue;
+      const int rx = (int)sqrtf(rem) + 2;
+      int xlo = vx - rx, xhi = vx + rx;
+      if (xhi < 0 || xlo >= g.div_v[0]) continue;
+      xlo = max(xlo, 0) >> g.shift[0];
+      xhi = min(xhi, g.div_v[0] - 1) >> g.shift[0];
+      const int base = (cz * g.dim[1] + cy) * g.dim[0];
+      const int s = g.cell_start[base + xlo], e = g.cell_start[base + xhi + 1];
+      for (int k = s; k < e; ++k) {
+        const float4 p = g.pts[k];
+        const float d2 = em::dist2_3(qx, qy, qz, p.x, p.y, p.z);
+        if ((double)d2 > bound) continue;
+        const int oi = g.orig ? g.orig[k] : k;
+        if (!found || d2 < best || (d2 == best && oi < best_idx)) {
+          found = true;
+          best = d2;
+          best_idx = oi;
+          best_pt = p;
+          lim_v = d2 * g.inv_leaf * g.inv_leaf * 1.0001f + 1e-3f;
+        }
+      }
+    }
+  }
+  *out_idx = best_idx;
+  *out_d2 = best;
+  *out_pt = best_pt;
+  return found;
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v)
+{
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------------------
+// Host-side batched stage entry points (one call = all maps / all pairs).
+// ---------------------------------------------------------------------------
+struct DCloud {
+  DBuf<float4> pts;
+  int n = 0;
+  CloudView view() const { return CloudView{pts.p, n}; }
+};
+
+// primitives.cu
+void radix_sort_pairs_batch(Ctx& c, uint32_t* keys, uint32_t* vals, uint32_t* keys_tmp, uint32_t* vals_tmp, const std::vector<Seg>& segs,
+                            int nbits, uint32_t** keys_sorted, uint32_t** vals_sorted);
+// exclusive scan of flags per segment; pos[i] = #set flags before i (within its segment); totals on host
+void scan_flags_batch(Ctx& c, const uint32_t* flags, uint32_t* pos, const std::vector<Seg>& segs, std::vector<int>& totals);
+
+// voxel.cu — K1
+void voxel_downsample_batch(Ctx& c, const std::vector<CloudView>& in, float leaf, std::vector<DCloud>& out, std::vector<VoxGeom>* geom);
+void build_index_batch(Ctx& c, const std::vector<CloudView>& clouds, float leaf, int sx, int sy, int sz, std::vector<DIndex>& out,
+                       std::vector<int>* was_sorted = nullptr);
+void transform_concat(Ctx& c, const std::vector<CloudView>& in, const std::vector<const float*>& transforms_rowmajor_host, DCloud& out);
+
+// features.cu — K3, K4, K5, K7
+void remove_outliers_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, double radius, int min_nb,
+                           std::vector<DCloud>& out, std::vector<DBuf<int>>* counts);
+void normals_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, double radius, std::vector<DBuf<float4>>& normals);
+void sift_batch(Ctx& c, const std::vector<CloudView>& clouds, float min_scale, int n_octaves, int n_scales, float min_contrast,
+                std::vector<DCloud>& keypoints, std::vector<DBuf<float>>* dog0);
+// keypoints are filtered in place; desc[m] = K' x 33
+void fpfh_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<const float4*>& normals,
+                std::vector<DCloud>& keypoints, double radius, std::vector<DBuf<float>>& desc, std::vector<DBuf<float>>* spfh_dbg);
+
+// matching.cu — K9, K10
+struct PairJob {
+  int a, b;  // indices into the per-map arrays
+};
+struct DCorr {
+  DBuf<int2> pairs;
+  DBuf<float> dist;
+  int n = 0;
+};
+void match_batch(Ctx& c, const std::vector<const float*>& desc, const std::vector<int>& nk, int dim, const std::vector<PairJob>& jobs,
+                 size_t k, std::vector<DCorr>& corr);
+struct RansacOut {
+  float T[16];         // row-major
+  float best_model[16];
+  int iterations;
+  int best_count;
+  int n_inliers;
+  double sample_dist_thresh;
+};
+void ransac_batch(Ctx& c, const std::vector<CloudView>& keypoints, const std::vector<PairJob>& jobs, const std::vector<DCorr>& corr,
+                  double inlier_threshold, std::vector<RansacOut>& out, std::vector<std::vector<int>>* inliers);
+
+// icp.cu — K11, K12
+struct IcpOut {
+  float T[16];  // row-major
+  int iterations;
+  int converged;
+};
+void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<PairJob>& jobs,
+               const std::vector<const float*>& T0_rowmajor, double max_dist, int max_it, double eps, std::vector<IcpOut>& out,
+               std::vector<std::vector<long long>>* sums_dbg);
+void score_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<PairJob>& jobs,
+                 const std::vector<const float*>& T_rowmajor, double max_range, std::vector<double>& scores);
+
+// graph.cpp — host pose graph (a14, a15)
+struct HostEstimate {
+  size_t source_idx, target_idx;
+  float T[16];  // row-major
+  double confidence;
+};
+std::vector<std::vector<float>> compute_global_transforms(const std::vector<HostEstimate>& pairwise, double confidence_threshold,
+                                                          int* reference_frame, std::vector<int>* in_component,
+                                                          std::vector<std::pair<int, int>>* tree_edges, std::vector<int>* centers);
+
+}  // namespace mm3d

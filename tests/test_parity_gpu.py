@@ -1,0 +1,336 @@
+"""CUDA path vs CPU oracle, stage by stage and end to end, through the C ABI (libmm3d.so).
+
+Every stage gets the ORACLE's output of the previous stage as input, so a mismatch
+points at exactly one kernel.  Integer / index outputs must be bit-exact; float
+outputs are compared bit-exact as well wherever the two sides evaluate the same
+IEEE operations in the same order (which is the design: see DESIGN.md "parity").
+"""
+import numpy as np
+import pytest
+
+from conftest import rot_err
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def assert_same_bits(a, b, what):
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    bad = bits(a) != bits(b)
+    # NaN payloads may differ; treat NaN == NaN
+    bad &= ~(np.isnan(a) & np.isnan(b))
+    assert not bad.any(), f"{what}: {int(bad.sum())} of {bad.size} values differ, first at {np.argwhere(bad)[0]}: {a[bad][0]} vs {b[bad][0]}"
+
+
+# ---------------------------------------------------------------- K1 voxel grid
+def test_downsample_bit_exact(ctx, oracle, tiny_maps):
+    maps, _ = tiny_maps
+    for m in maps:
+        for res in (0.1, 0.05, 0.37):
+            want, meta = oracle.downsample(m, res)
+            got = ctx.downsample(m, res)
+            assert_same_bits(got, want, f"downsample res={res}")
+
+
+def test_downsample_edge_cases(ctx, oracle):
+    empty = np.zeros((0, 4), np.float32)
+    assert ctx.downsample(empty, 0.1).shape == (0, 4)
+    assert ctx.downsample(empty, 0.0).shape == (0, 4)
+    rng = np.random.default_rng(0)
+    one = rng.normal(size=(1, 4)).astype(np.float32)
+    assert_same_bits(ctx.downsample(one, 0.1), oracle.downsample(one, 0.1)[0], "single point")
+    # overflow guard: leaf far too small for the extent -> input returned unchanged
+    big = (rng.uniform(-500, 500, size=(1000, 4))).astype(np.float32)
+    want, meta = oracle.downsample(big, 0.001)
+    assert meta["passthrough"] == 1
+    assert_same_bits(ctx.downsample(big, 0.001), want, "overflow guard passthrough")
+    # many points in one voxel, unsorted input, negative coordinates
+    pts = rng.uniform(-0.3, 0.3, size=(5000, 4)).astype(np.float32)
+    pts[:, 3] = rng.integers(0, 2 ** 32, size=5000, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    assert_same_bits(ctx.downsample(pts, 0.25), oracle.downsample(pts, 0.25)[0], "dense voxels")
+
+
+def test_downsample_idempotent_full_size(ctx, synth):
+    """Size-independent property at BASELINE scale: voxelising a voxelised cloud at the same leaf keeps it."""
+    maps, _ = synth.make_maps(seed=5, n_maps=1, n_points=500_000, size_x=28.0, size_y=20.0, rooms_x=2, rooms_y=2)
+    once = ctx.downsample(maps[0], 0.1)
+    twice = ctx.downsample(once, 0.1)
+    assert len(once) == len(twice)
+    np.testing.assert_allclose(twice[:, :3], once[:, :3], rtol=0, atol=1e-6)
+    # ascending voxel order: z-major, then y, then x
+    inv = np.float32(1.0) / np.float32(0.1)
+    ijk = np.floor(once[:, :3] * inv).astype(np.int64)
+    key = (ijk[:, 2] - ijk[:, 2].min()) * 10 ** 8 + (ijk[:, 1] - ijk[:, 1].min()) * 10 ** 4 + (ijk[:, 0] - ijk[:, 0].min())
+    assert (np.diff(key) > 0).mean() > 0.9999
+
+
+# ---------------------------------------------------------------- K3 outliers
+def test_remove_outliers_bit_exact(ctx, oracle, tiny_stages):
+    for st in tiny_stages:
+        got, counts = ctx.remove_outliers(st["ds"], 0.8, 50, index_leaf=0.1, with_counts=True)
+        assert np.array_equal(counts, st["counts"]), "neighbour counts differ"
+        assert_same_bits(got, st["filtered"], "filtered cloud")
+    # a threshold that actually removes points
+    st = tiny_stages[0]
+    med = int(np.median(st["counts"]))
+    want, kept, _ = oracle.remove_outliers(st["ds"], 0.8, med)
+    got = ctx.remove_outliers(st["ds"], 0.8, med, index_leaf=0.1)
+    assert 0 < len(want) < len(st["ds"])
+    assert_same_bits(got, want, "filtered cloud (median threshold)")
+
+
+def test_remove_outliers_unsorted_input(ctx, oracle, tiny_stages):
+    """A shuffled cloud takes the re-sorting index path; counts are order-free so still exact."""
+    st = tiny_stages[0]
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(len(st["ds"]))
+    shuffled = st["ds"][perm]
+    want, kept, counts = oracle.remove_outliers(shuffled, 0.5, 60)
+    got, gc = ctx.remove_outliers(shuffled, 0.5, 60, index_leaf=0.1, with_counts=True)
+    assert np.array_equal(gc, counts)
+    assert_same_bits(got, want, "filtered cloud (shuffled)")
+
+
+# ---------------------------------------------------------------- K4 normals
+def test_normals_bit_exact(ctx, tiny_stages):
+    for st in tiny_stages:
+        got = ctx.normals(st["filtered"], 0.6, index_leaf=0.1)
+        assert_same_bits(got, st["normals"], "normals")
+
+
+def test_normals_sparse_nan(ctx, oracle):
+    pts = np.array([[0, 0, 0, 0], [10, 0, 0, 0], [10.1, 0, 0, 0], [10, 0.1, 0, 0], [10, 0, 0.15, 0]], np.float32)
+    want = oracle.normals(pts, 0.6)
+    got = ctx.normals(pts, 0.6, index_leaf=0.1)
+    assert np.isnan(want[0]).all() and np.isnan(got[0]).all()
+    assert_same_bits(got, want, "sparse normals")
+
+
+# ---------------------------------------------------------------- K5 SIFT
+def test_sift_bit_exact(ctx, tiny_stages):
+    for st in tiny_stages:
+        kp, dog = ctx.keypoints(st["filtered"], type="SIFT", threshold=5.0, resolution=0.1, debug=True)
+        assert_same_bits(dog, st["dog0"], "octave-0 DoG")
+        assert_same_bits(kp, st["kp_sift"], "SIFT keypoints")
+        assert len(kp) > 50
+
+
+# ---------------------------------------------------------------- K7 FPFH
+def test_fpfh_bit_exact(ctx, tiny_stages):
+    for st in tiny_stages:
+        kp, desc, spfh = ctx.descriptors(st["filtered"], st["normals"], st["kp_sift"], type="FPFH", radius=0.8, index_leaf=0.1, debug=True)
+        assert_same_bits(spfh, st["spfh"], "SPFH")
+        assert_same_bits(kp, st["kp"], "kept keypoints")
+        assert_same_bits(desc, st["desc"], "FPFH descriptors")
+        np.testing.assert_allclose(desc.reshape(len(desc), 3, 11).sum(-1), 100.0, rtol=1e-4)
+
+
+def test_fpfh_drops_isolated_keypoints(ctx, oracle, tiny_stages):
+    st = tiny_stages[0]
+    kp = np.concatenate([st["kp_sift"][:10], np.array([[100, 100, 100, 0]], np.float32), st["kp_sift"][10:20]])
+    wk, wd = oracle.fpfh(st["filtered"], st["normals"], kp, 0.8)
+    gk, gd = ctx.descriptors(st["filtered"], st["normals"], kp, radius=0.8, index_leaf=0.1)
+    assert len(wk) == 20
+    assert_same_bits(gk, wk, "kept keypoints")
+    assert_same_bits(gd, wd, "descriptors")
+
+
+# ---------------------------------------------------------------- K9 matching
+def test_match_bit_exact(ctx, oracle, tiny_stages):
+    a, b = tiny_stages[0]["desc"], tiny_stages[1]["desc"]
+    for k in (1, 5, 8):
+        wp, wd = oracle.match(a, b, k)
+        gp, gd = ctx.match(a, b, k)
+        assert np.array_equal(gp, wp), f"correspondence indices differ (k={k})"
+        assert_same_bits(gd, wd, "correspondence distances")
+    assert len(wp) > 10
+
+
+def test_match_small_sets_and_generic_dim(ctx, oracle):
+    rng = np.random.default_rng(7)
+    # fewer descriptors than k on either side (the reference reads out of bounds here; both sides clamp k)
+    a = rng.uniform(0, 100, size=(3, 33)).astype(np.float32)
+    b = rng.uniform(0, 100, size=(40, 33)).astype(np.float32)
+    for x, y in ((a, b), (b, a)):
+        wp, wd = oracle.match(x, y, 5)
+        gp, gd = ctx.match(x, y, 5)
+        assert np.array_equal(gp, wp)
+        assert_same_bits(gd, wd, "distances")
+    # exact duplicates -> ties resolved to the lower index
+    c = np.repeat(rng.uniform(0, 100, size=(50, 33)).astype(np.float32), 2, axis=0)
+    wp, wd = oracle.match(c, c[::-1].copy(), 5)
+    gp, gd = ctx.match(c, c[::-1].copy(), 5)
+    assert np.array_equal(gp, wp)
+    # other descriptor widths go through the generic kernel (PFH 125, SHOT 1344)
+    for dim in (125, 1344):
+        s = rng.uniform(0, 1, size=(150, dim)).astype(np.float32)
+        t = rng.uniform(0, 1, size=(170, dim)).astype(np.float32)
+        wp, wd = oracle.match(s, t, 5)
+        gp, gd = ctx.match(s, t, 5)
+        assert np.array_equal(gp, wp), f"dim {dim}"
+        assert_same_bits(gd, wd, f"distances dim {dim}")
+    assert ctx.match(np.zeros((0, 33), np.float32), b, 5)[0].shape == (0, 2)
+
+
+# ---------------------------------------------------------------- K10 RANSAC
+def test_ransac_bit_exact(ctx, oracle, tiny_stages):
+    s, t = tiny_stages
+    pairs, dist = oracle.match(s["desc"], t["desc"], 5)
+    for thr in (0.5, 0.2):
+        wT, winl, wdbg = oracle.ransac(s["kp"], t["kp"], pairs, dist, thr)
+        gT, ginl, gdbg = ctx.ransac(s["kp"], t["kp"], pairs, thr)
+        assert gdbg["sample_dist_thresh"] == wdbg["sample_dist_thresh"]
+        assert gdbg["iterations"] == wdbg["iterations"]
+        assert gdbg["best_count"] == wdbg["best_count"]
+        assert_same_bits(gdbg["best_model"], wdbg["best_model"], "best RANSAC model")
+        assert np.array_equal(ginl, winl), "inlier set differs"
+        assert_same_bits(gT, wT, "final SVD transform")
+        assert len(winl) >= 3
+
+
+def test_ransac_degenerate(ctx, oracle, tiny_stages):
+    s, t = tiny_stages
+    pairs, dist = oracle.match(s["desc"], t["desc"], 5)
+    for n in (0, 1, 2):
+        gT, ginl, _ = ctx.ransac(s["kp"], t["kp"], pairs[:n], 0.5)
+        assert not gT.any() and len(ginl) == 0  # zero matrix = "could not estimate" (matching.h:41-42)
+    # random (inconsistent) correspondences: whatever happens must match the oracle
+    rng = np.random.default_rng(1)
+    rp = np.stack([rng.permutation(len(s["kp"]))[:60], rng.integers(0, len(t["kp"]), 60)], 1).astype(np.int32)
+    rp = rp[np.argsort(rp[:, 0])]
+    wT, winl, wdbg = oracle.ransac(s["kp"], t["kp"], rp, np.zeros(60, np.float32), 0.05)
+    gT, ginl, gdbg = ctx.ransac(s["kp"], t["kp"], rp, 0.05)
+    assert gdbg["iterations"] == wdbg["iterations"] and gdbg["best_count"] == wdbg["best_count"]
+    assert np.array_equal(ginl, winl)
+    assert_same_bits(gT, wT, "transform (random correspondences)")
+
+
+# ---------------------------------------------------------------- K11 ICP / K12 score
+def _truth_pair(tiny_maps):
+    _, truth = tiny_maps
+    return (np.linalg.inv(truth[1]) @ truth[0]).astype(np.float32)
+
+
+def test_icp_bit_exact(ctx, oracle, tiny_stages, tiny_maps):
+    s, t = tiny_stages
+    gt = _truth_pair(tiny_maps)
+    # perturbed ground truth as the initial guess
+    c, sn = np.cos(0.05), np.sin(0.05)
+    pert = np.array([[c, -sn, 0, 0.08], [sn, c, 0, -0.05], [0, 0, 1, 0.03], [0, 0, 0, 1]], np.float32)
+    for T0, eps in ((pert @ gt, 1e-2), (pert @ gt, 1e-6), (gt, 1e-4)):
+        wT, wdbg = oracle.icp(s["filtered"], t["filtered"], T0, 1.0, 30, eps)
+        gT, gdbg = ctx.icp(s["filtered"], t["filtered"], T0, 1.0, 30, eps, index_leaf=0.1)
+        assert gdbg["iterations"] == wdbg["iterations"], (gdbg["iterations"], wdbg["iterations"])
+        assert gdbg["converged"] == wdbg["converged"]
+        n = min(len(gdbg["sums"]), len(wdbg["sums"]))
+        assert n >= 1 and np.array_equal(gdbg["sums"][:n], wdbg["sums"][:n]), "per-iteration reductions differ"
+        assert_same_bits(gT, wT, "ICP transform")
+    assert rot_err(gT, gt) < 0.02
+
+
+def test_icp_zero_guess_and_no_overlap(ctx, oracle, tiny_stages):
+    s, t = tiny_stages
+    zero = np.zeros((4, 4), np.float32)
+    gT, gdbg = ctx.icp(s["filtered"], t["filtered"], zero, 1.0, 30, 1e-2, index_leaf=0.1)
+    wT, _ = oracle.icp(s["filtered"], t["filtered"], zero, 1.0, 30, 1e-2)
+    assert not gT.any() and not wT.any()  # anything * 0 (matching.cpp:220)
+    far = np.eye(4, dtype=np.float32)
+    far[:3, 3] = 500.0
+    wT, wdbg = oracle.icp(s["filtered"], t["filtered"], far, 1.0, 30, 1e-2)
+    gT, gdbg = ctx.icp(s["filtered"], t["filtered"], far, 1.0, 30, 1e-2, index_leaf=0.1)
+    assert wdbg["converged"] == 0 and gdbg["converged"] == 0
+    assert_same_bits(gT, wT, "ICP without correspondences returns the guess")
+
+
+def test_score_bit_exact(ctx, oracle, tiny_stages, tiny_maps):
+    s, t = tiny_stages
+    gt = _truth_pair(tiny_maps)
+    for T, rng_ in ((gt, 1.0), (gt, 0.01), (np.eye(4, dtype=np.float32), 1.0), (np.zeros((4, 4), np.float32), 1.0)):
+        want = oracle.score(s["filtered"], t["filtered"], T, rng_)
+        got = ctx.score(s["filtered"], t["filtered"], T, rng_, index_leaf=0.1)
+        assert got == want, (got, want)
+    far = np.eye(4, dtype=np.float32)
+    far[:3, 3] = 500.0
+    assert ctx.score(s["filtered"], t["filtered"], far, 1.0, index_leaf=0.1) == np.finfo(np.float64).max
+
+
+# ---------------------------------------------------------------- end to end
+def _check_against_truth(T, truth, tol_rot=0.08, tol_t=0.35):
+    ref = [i for i in range(len(T)) if np.allclose(T[i], np.eye(4))]
+    assert len(ref) == 1
+    r = ref[0]
+    for i in range(len(T)):
+        want = np.linalg.inv(truth[r]) @ truth[i]
+        assert rot_err(T[i], want) < tol_rot
+        assert np.linalg.norm(T[i][:3, 3] - want[:3, 3]) < tol_t
+
+
+@pytest.mark.parametrize("cfg", ["tiny", "small"])
+def test_estimate_maps_transforms_matches_oracle(ctx, mm, oracle, synth, cfg):
+    import oracle_py
+    maps, truth = synth.make_maps(**synth.CONFIGS[cfg])
+    want = oracle.estimate_maps_transforms(maps, oracle_py.default_params(descriptor_type=2))
+    got = ctx.estimate_maps_transforms(maps, mm.default_params(descriptor_type="FPFH"))
+    assert got.shape == want["transforms"].shape
+    # pairwise results are bit-exact (test_resident_and_sharded_paths_agree); the chained global transforms go through
+    # a general 4x4 float inverse (Eigen::Matrix4f::inverse() in the reference) whose evaluation order is a choice
+    np.testing.assert_allclose(got, want["transforms"], rtol=0, atol=1e-5)
+    _check_against_truth(got, truth)
+
+
+def test_resident_and_sharded_paths_agree(ctx, mm, oracle, small_maps):
+    """mm3d_estimate_resident == features_compute on two 'ranks' + register_pairs on a split pair list + host graph."""
+    import oracle_py
+    maps, truth = small_maps
+    p = mm.default_params(descriptor_type="FPFH")
+    dm = ctx.maps_upload(maps)
+    whole, stage_ms = ctx.estimate_resident(dm, p, stage_times=True)
+    assert all(v >= 0 for v in stage_ms.values()) and sum(stage_ms.values()) > 0
+    fa = ctx.features_compute(dm, 0, 2, p)
+    fb = ctx.features_compute(dm, 2, 1, p)
+    want = oracle.estimate_maps_transforms(maps, oracle_py.default_params(descriptor_type=2))
+    # host export of the features matches what the oracle pipeline would produce for map 0
+    pts0, kp0, desc0 = fa.export_host(0)
+    ds, _ = oracle.downsample(maps[0], 0.1)
+    fo, _, _ = oracle.remove_outliers(ds, 0.8, 50)
+    assert_same_bits(pts0, fo, "resident features: cloud")
+    # re-assemble on "one rank" through the device import path using torch buffers
+    import torch
+    bufs, npt, nk, pp, kp_, dp = [], [], [], [], [], []
+    for f, cnt in ((fa, 2), (fb, 1)):
+        a, b, dim = f.sizes()
+        for m in range(cnt):
+            tp = torch.empty((int(a[m]), 4), dtype=torch.float32, device="cuda")
+            tk = torch.empty((int(b[m]), 4), dtype=torch.float32, device="cuda")
+            td = torch.empty((int(b[m]), dim), dtype=torch.float32, device="cuda")
+            f.export_dev(m, tp.data_ptr(), tk.data_ptr(), td.data_ptr())
+            bufs += [tp, tk, td]
+            npt.append(int(a[m])); nk.append(int(b[m])); pp.append(tp.data_ptr()); kp_.append(tk.data_ptr()); dp.append(td.data_ptr())
+    torch.cuda.synchronize()
+    allf = ctx.features_import_dev(npt, pp, nk, kp_, dp, 33)
+    T1, c1, s1 = ctx.register_pairs(allf, [[0, 1]], p)
+    T2, c2, s2 = ctx.register_pairs(allf, [[0, 2], [1, 2]], p)
+    ij = np.array([[0, 1], [0, 2], [1, 2]], np.int32)
+    Tp = np.concatenate([T1, T2]); conf = np.concatenate([c1, c2])
+    np.testing.assert_array_equal(Tp, want["pair_T"])
+    np.testing.assert_array_equal(conf, want["pair_conf"])
+    np.testing.assert_array_equal(np.concatenate([s1, s2])[:, :2], want["pairs"][:, 2:4])
+    G, ref = mm.global_transforms(ij, Tp, conf, 0.0)
+    np.testing.assert_array_equal(G, whole)
+    np.testing.assert_allclose(G, want["transforms"], rtol=0, atol=1e-5)
+
+
+def test_compose_maps_bit_exact(ctx, oracle, tiny_maps):
+    maps, truth = tiny_maps
+    T = np.stack([np.eye(4), (np.linalg.inv(truth[0]) @ truth[1])]).astype(np.float32)
+    want = oracle.compose_maps(maps, T, 0.05)
+    got = ctx.compose_maps(maps, T, 0.05)
+    assert_same_bits(got, want, "composed map")
+    # zero transform => that cloud is skipped (map_merging.cpp:293-295)
+    T[1] = 0
+    assert_same_bits(ctx.compose_maps(maps, T, 0.05), oracle.compose_maps(maps, T, 0.05), "composed map, one skipped")
