@@ -68,6 +68,10 @@ int mm3d_create(mm3d_ctx** ctx, int device, void* cuda_stream);
 void mm3d_destroy(mm3d_ctx* ctx);
 const char* mm3d_last_error(mm3d_ctx* ctx);
 void mm3d_free(void* p);
+/* Per-kernel device timing: between begin and end every kernel launch is bracketed by a CUDA event pair on the
+ * launching stream.  *json (mm3d_free) = [{"kernel", "launches", "ms", "algorithmic_bytes", "ms_annotated"}, ...]. */
+int mm3d_profile_begin(mm3d_ctx* ctx);
+int mm3d_profile_end(mm3d_ctx* ctx, char** json);
 /* kernels launched through this context so far */
 long long mm3d_kernel_launches(mm3d_ctx* ctx);
 

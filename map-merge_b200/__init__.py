@@ -39,7 +39,7 @@ SYMBOLS = [
     "mm3d_keypoints", "mm3d_descriptors", "mm3d_match", "mm3d_ransac", "mm3d_icp", "mm3d_score", "mm3d_global_transforms",
     "mm3d_maps_upload", "mm3d_maps_free", "mm3d_features_compute", "mm3d_features_count", "mm3d_features_sizes",
     "mm3d_features_export_dev", "mm3d_features_import_dev", "mm3d_features_export_host", "mm3d_features_free",
-    "mm3d_register_pairs", "mm3d_estimate_resident",
+    "mm3d_register_pairs", "mm3d_estimate_resident", "mm3d_profile_begin", "mm3d_profile_end",
 ]
 
 
@@ -154,6 +154,16 @@ class Context:
     @property
     def launches(self) -> int:
         return int(self.L.mm3d_kernel_launches(self.h))
+
+    def profile_begin(self):
+        self._check(self.L.mm3d_profile_begin(self.h))
+
+    def profile_end(self):
+        import json
+        s = C.c_char_p()
+        self._check(self.L.mm3d_profile_end(self.h, C.byref(s)))
+        out = json.loads(s.value.decode())
+        return out
 
     # ---- low-level interface ------------------------------------------------
     def downsample(self, pts, resolution):

@@ -2,6 +2,7 @@
 // stage-major per-map loops and the all-pairs loop of
 // map_merge_3d/src/map_merging.cpp:188-275, each stage one batched launch set.
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -628,6 +629,53 @@ int mm3d_global_transforms(int n_pairs, const int32_t* st, const float* transfor
     return MM3D_ERR;
   }
   return MM3D_OK;
+}
+
+int mm3d_profile_begin(mm3d_ctx* ctx)
+{
+  MM_TRY(ctx)
+  c.sync();
+  for (KernelSample& s : c.samples) { c.event_pool.push_back(s.e0); c.event_pool.push_back(s.e1); }
+  c.samples.clear();
+  c.profiling = true;
+  MM_CATCH
+}
+
+int mm3d_profile_end(mm3d_ctx* ctx, char** json)
+{
+  if (!json) return MM3D_ERR_ARG;
+  *json = nullptr;
+  MM_TRY(ctx)
+  c.sync();
+  c.profiling = false;
+  struct Agg { std::string name; long long n = 0; double ms = 0, bytes = 0, ms_annotated = 0; };
+  std::vector<Agg> agg;
+  for (KernelSample& s : c.samples) {
+    float ms = 0.f;
+    MM_CUDA(cudaEventElapsedTime(&ms, s.e0, s.e1));
+    size_t k = 0;
+    for (; k < agg.size(); ++k)
+      if (agg[k].name == s.name) break;
+    if (k == agg.size()) { agg.emplace_back(); agg.back().name = s.name; }
+    agg[k].n += 1;
+    agg[k].ms += ms;
+    agg[k].bytes += s.bytes;
+    if (s.bytes > 0) agg[k].ms_annotated += ms;
+    c.event_pool.push_back(s.e0);
+    c.event_pool.push_back(s.e1);
+  }
+  c.samples.clear();
+  std::string out = "[";
+  for (size_t k = 0; k < agg.size(); ++k) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s{\"kernel\": \"%s\", \"launches\": %lld, \"ms\": %.6f, \"algorithmic_bytes\": %.1f, \"ms_annotated\": %.6f}",
+             k ? ", " : "", agg[k].name.c_str(), agg[k].n, agg[k].ms, agg[k].bytes, agg[k].ms_annotated);
+    out += buf;
+  }
+  out += "]";
+  *json = (char*)malloc(out.size() + 1);
+  memcpy(*json, out.c_str(), out.size() + 1);
+  MM_CATCH
 }
 
 // ---- resident interface -----------------------------------------------------

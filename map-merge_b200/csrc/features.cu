@@ -435,6 +435,7 @@ void remove_outliers_batch(Ctx& c, const std::vector<CloudView>& clouds, const s
   const float r2 = (float)(radius * radius);
   const int rv = radius_voxels(radius, idx[0].v.leaf);
   const int mx = max_n(clouds);
+  { double b = 0; for (int m = 0; m < M; ++m) b += 20.0 * ns[m]; MM_BYTES(c, b); }
   MM_LAUNCH(c, outlier_kernel, dim3((mx + FB - 1) / FB, M), FB, 0, dj.p, r2, rv, min_nb);
   std::vector<int> totals;
   scan_flags_batch(c, flags.p, pos.p, segs, totals);
@@ -466,6 +467,7 @@ void normals_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vect
   DBuf<NormalJob> dj = to_device(c, jobs);
   const float r2 = (float)(radius * radius);
   const int rv = radius_voxels(radius, idx[0].v.leaf);
+  { double b = 0; for (int m = 0; m < M; ++m) b += 32.0 * clouds[m].n; MM_BYTES(c, b); }
   MM_LAUNCH(c, normals_kernel, dim3((mx + FB - 1) / FB, M), FB, 0, dj.p, r2, rv);
 }
 
@@ -528,7 +530,9 @@ void sift_batch(Ctx& c, const std::vector<CloudView>& clouds, float min_scale, i
     DBuf<SiftJob> dj = to_device(c, jobs);
     const int mx = max_n(ov);
     const dim3 grid((mx + FB - 1) / FB, M);
+    { double b = 0; for (int m = 0; m < M; ++m) b += 36.0 * ns[m]; MM_BYTES(c, b); }
     MM_LAUNCH(c, sift_scale_space_kernel, grid, FB, 0, dj.p, sc, r2, rv);
+    { double b = 0; for (int m = 0; m < M; ++m) b += 48.0 * ns[m]; MM_BYTES(c, b); }
     MM_LAUNCH(c, sift_extrema_kernel, grid, FB, 0, dj.p, min_contrast);
     std::vector<int> totals;
     scan_flags_batch(c, flags.p, pos.p, segs3, totals);
@@ -600,7 +604,9 @@ void fpfh_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<
   const float r2 = (float)(radius * radius);
   const int rv = radius_voxels(radius, idx[0].v.leaf);
   MM_LAUNCH(c, fpfh_mark_kernel, dim3((mxk + FB - 1) / FB, M), FB, 0, dj.p, r2, rv);
+  { double b = 0; for (int m = 0; m < M; ++m) b += (32.0 + 132.0 + 4.0) * clouds[m].n; MM_BYTES(c, b); }
   MM_LAUNCH(c, spfh_kernel, dim3((mx + FB - 1) / FB, M), FB, 0, dj.p, r2, rv);
+  { double b = 0; for (int m = 0; m < M; ++m) b += (16.0 + 132.0) * clouds[m].n + (16.0 + 132.0) * nks[m]; MM_BYTES(c, b); }
   MM_LAUNCH(c, fpfh_weight_kernel, dim3((mxk * 3 + FB - 1) / FB, M), FB, 0, dj.p, r2, rv);
   DBuf<uint32_t> flags(c, totalk), pos(c, totalk);
   std::vector<FpfhFlagJob> fj(M);

@@ -291,6 +291,7 @@ void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<D
   const dim3 grid(std::max(1, (mx + IB - 1) / IB), A);
   int it = 0;
   while (n_active > 0 && it < std::max(max_it, 1)) {
+    { double b = 0; for (int a = 0; a < A; ++a) b += 16.0 * ((double)ij[a].ns * (it > 0 ? 2 : 1) + ij[a].tgt.n); MM_BYTES(c, b * ((double)n_active / A)); }
     MM_LAUNCH(c, icp_accumulate_kernel, grid, IB, 0, dij.p, max_dist_sqr, rv, it > 0 ? 1 : 0);
     MM_LAUNCH(c, icp_solve_kernel, (A + 31) / 32, 32, 0, dij.p, A, max_it, 1.0 - eps, eps, max_log, dn_active.p);
     dn_active.download(c, &n_active, 1);
@@ -348,6 +349,7 @@ void score_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector
   DBuf<ScoreJob> dsj = to_device(c, sj);
   const float leaf = idx[jobs[0].b].v.leaf;
   const int rv = (int)std::ceil(std::sqrt(std::max(max_range, 0.0)) / (double)leaf) + 1;
+  { double b = 0; for (int p = 0; p < P; ++p) b += 16.0 * ((double)sj[p].ns + sj[p].tgt.n); MM_BYTES(c, b); }
   MM_LAUNCH(c, score_kernel, dim3((mx + IB - 1) / IB, P), IB, 0, dsj.p, max_range, rv);
   std::vector<long long> h((size_t)P * 2);
   sums.download(c, h.data(), h.size());

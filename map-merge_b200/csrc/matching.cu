@@ -482,8 +482,10 @@ void match_batch(Ctx& c, const std::vector<const float*>& desc, const std::vecto
   DBuf<KnnJob> dkj = to_device(c, kj);
   if (max_rows > 0) {
     if (dim == 33) {
+      { double b = 0; for (const KnnJob& q : kj) b += 4.0 * dim * ((double)q.na + q.nb) + 8.0 * q.k * q.na; MM_BYTES(c, b); }
       MM_LAUNCH(c, knn_small_kernel<33>, dim3((max_rows + 127) / 128, 2 * P), 128, 0, dkj.p);
     } else {
+      { double b = 0; for (const KnnJob& q : kj) b += 4.0 * dim * ((double)q.na + q.nb) + 8.0 * q.k * q.na; MM_BYTES(c, b); }
       MM_LAUNCH(c, knn_generic_kernel, dim3((max_rows + 63) / 64, 2 * P), 128, 0, dkj.p, dim);
     }
   }

@@ -28,21 +28,66 @@ namespace mm3d {
                                std::to_string(__LINE__) + " (" #expr ")");                              \
   } while (0)
 
+// Optional per-kernel timing: one CUDA event pair around every launch, recorded on
+// the launching stream and resolved when profiling ends (no extra synchronisation).
+struct KernelSample {
+  const char* name;
+  double bytes;  // algorithmic bytes of this launch (inputs read once + outputs written once), 0 = not annotated
+  cudaEvent_t e0, e1;
+};
+
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::string err;
   long long launches = 0;  // kernels launched through this context (bench.py's gpu_launches)
+  bool profiling = false;
+  double next_bytes = 0.0;
+  std::vector<KernelSample> samples;
+  std::vector<cudaEvent_t> event_pool;
   void sync() { MM_CUDA(cudaStreamSynchronize(stream)); }
+  cudaEvent_t get_event()
+  {
+    cudaEvent_t e;
+    if (!event_pool.empty()) {
+      e = event_pool.back();
+      event_pool.pop_back();
+    } else {
+      MM_CUDA(cudaEventCreate(&e));
+    }
+    return e;
+  }
+  void before_launch(const char* name)
+  {
+    ++launches;
+    if (!profiling) return;
+    KernelSample s;
+    s.name = name;
+    s.bytes = next_bytes;
+    s.e0 = get_event();
+    s.e1 = get_event();
+    MM_CUDA(cudaEventRecord(s.e0, stream));
+    samples.push_back(s);
+  }
+  void after_launch()
+  {
+    next_bytes = 0.0;
+    if (!profiling) return;
+    MM_CUDA(cudaEventRecord(samples.back().e1, stream));
+  }
 };
 
 #define MM_LAUNCH(ctx, kernel, grid, block, smem, ...)                 \
   do {                                                                 \
+    (ctx).before_launch(#kernel);                                      \
     kernel<<<(grid), (block), (smem), (ctx).stream>>>(__VA_ARGS__);    \
-    (ctx).launches++;                                                  \
+    (ctx).after_launch();                                              \
     MM_CUDA(cudaGetLastError());                                       \
   } while (0)
+
+// annotate the next launch with its algorithmic byte count
+#define MM_BYTES(ctx, b) ((ctx).next_bytes = (double)(b))
 
 // Stream-ordered device buffer.
 template <typename T>

@@ -235,8 +235,12 @@ void radix_sort_pairs_batch(Ctx& c, uint32_t* keys, uint32_t* vals, uint32_t* ke
   const dim3 grid(tiles_max, (unsigned)segs.size());
   uint32_t *kin = keys, *vin = vals, *kout = keys_tmp, *vout = vals_tmp;
   for (int shift = 0; shift < nbits; shift += 8) {
+    double tot_n = 0;
+    for (const Seg& s : segs) tot_n += s.n;
+    MM_BYTES(c, 4.0 * tot_n);
     MM_LAUNCH(c, rs_hist_kernel, grid, RS_THREADS, 0, kin, dsegs.p, shift, hist.p, tiles_max);
     MM_LAUNCH(c, rs_scan_kernel, (unsigned)segs.size(), 1024, 0, hist.p, dsegs.p, tiles_max);
+    MM_BYTES(c, 16.0 * tot_n);
     MM_LAUNCH(c, rs_scatter_kernel, grid, RS_THREADS, 0, kin, vin, kout, vout, dsegs.p, shift, hist.p, tiles_max);
     std::swap(kin, kout);
     std::swap(vin, vout);

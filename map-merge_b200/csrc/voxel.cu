@@ -328,6 +328,7 @@ void voxel_downsample_batch(Ctx& c, const std::vector<CloudView>& in, float leaf
   DBuf<uint32_t> keys(c, total), vals(c, total), keys2(c, total), vals2(c, total);
   const int mx = max_n(in);
   const dim3 grid((mx + 255) / 256, M);
+  MM_BYTES(c, 24.0 * total);
   MM_LAUNCH(c, voxel_key_kernel, grid, 256, 0, dviews.p, dgeom.p, dsegs.p, leaf, keys.p, vals.p);
   uint32_t *ks, *vs;
   radix_sort_pairs_batch(c, keys.p, vals.p, keys2.p, vals2.p, segs, nbits, &ks, &vs);
@@ -343,6 +344,7 @@ void voxel_downsample_batch(Ctx& c, const std::vector<CloudView>& in, float leaf
     outs[m].pts = out[m].pts.p;
   }
   DBuf<CentroidOut> douts = to_device(c, outs);
+  { double b = 28.0 * total; for (int m = 0; m < M; ++m) b += 16.0 * totals[m]; MM_BYTES(c, b); }
   MM_LAUNCH(c, centroid_kernel, grid, 256, 0, dviews.p, dsegs.p, ks, vs, flags, pos.p, dgeom.p, douts.p);
 }
 
