@@ -209,17 +209,6 @@ def cpu_baseline_sample(maps, M, P):
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
-def lpt_assign(costs, n_bins):
-    order = np.argsort(-np.asarray(costs), kind="stable")
-    load = np.zeros(n_bins)
-    owner = np.zeros(len(costs), np.int64)
-    for k in order:
-        b = int(np.argmin(load))
-        owner[k] = b
-        load[b] += costs[k]
-    return owner
-
-
 class Job:
     """One rank's share of the sharded path."""
 
@@ -229,6 +218,8 @@ class Job:
         import mm3d_pkg
         self.torch, self.dist = torch, dist
         self.mm = mm3d_pkg.load()
+        import importlib
+        self.sh = importlib.import_module("map_merge_b200.sharding")
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.rank = int(os.environ.get("RANK", "0"))
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -241,10 +232,8 @@ class Job:
         self.M = len(maps)
         self.P = n_pairs_of(self.M)
         # contiguous block of maps per rank
-        per = -(-self.M // self.world)
-        self.first = min(self.rank * per, self.M)
-        self.count = max(0, min(per, self.M - self.first))
-        self.owner_of_map = [min(m // per, self.world - 1) for m in range(self.M)]
+        self.first, self.count, per = self.sh.map_block(self.rank, self.world, self.M)
+        self.owner_of_map = [self.sh.owner_of_map(m, self.world, self.M) for m in range(self.M)]
         # pinned host copies of this rank's maps (e2e path) and resident device copies (value path)
         self.host = []
         for m in range(self.first, self.first + self.count):
@@ -292,18 +281,12 @@ class Job:
             pp.append(base); kp.append(base + max_pt * 16); dp.append(base + (max_pt + max_kp) * 16)
         torch.cuda.current_stream().synchronize()
         allf = self.ctx.features_import_dev(n_points, pp, n_kp, kp, dp, dim)
-        ij = [(i, j) for i in range(self.M - 1) for j in range(i + 1, self.M) if n_kp[i] > 0 and n_kp[j] > 0]
-        costs = [float(n_kp[i]) * n_kp[j] * dim * 2e-3 + 4.0 * n_points[i] + n_points[j] for i, j in ij]
-        owner = lpt_assign(costs, self.world) if ij else np.zeros(0, np.int64)
+        ij = self.sh.pair_list(n_kp)
+        owner = self.sh.lpt_assign(self.sh.pair_costs(ij, n_points, n_kp, dim), self.world) if ij else np.zeros(0, np.int64)
         mine = [k for k in range(len(ij)) if owner[k] == self.rank]
         T, conf, stats = self.ctx.register_pairs(allf, [ij[k] for k in mine], self.p)
-        # fixed-size result exchange: every rank fills its own slots of the row-major pair list
-        res = torch.zeros((len(ij), 18), dtype=torch.float64, device=self.dev)
-        if mine:
-            block = np.concatenate([T.reshape(len(mine), 16).astype(np.float64), conf.reshape(-1, 1), np.ones((len(mine), 1))], axis=1)
-            res[torch.tensor(mine, device=self.dev)] = torch.from_numpy(block).to(self.dev)
-        if len(ij):
-            dist.all_reduce(res)  # disjoint slots: the sum is a gather that keeps the reference's pair order
+        # every rank fills its own slots of the row-major pair list (keeps the reference's pair order)
+        res = self.sh.gather_pair_results(dist, torch, self.dev, len(ij), mine, T, conf)
         out = None
         if self.rank == 0 and len(ij):
             h = res.cpu().numpy()

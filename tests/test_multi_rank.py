@@ -1,0 +1,117 @@
+"""The N > 1 host logic on CPU: two gloo ranks shard maps and pairs, exchange results, rank 0 builds the pose graph.
+The per-pair registration itself is GPU work (covered by the -m gpu tests); here each rank looks its pairs up in a
+precomputed table so that sharding, ordering and the result exchange are what is under test."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _poses(n, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        q, _r = np.linalg.qr(rng.normal(size=(3, 3)))
+        if np.linalg.det(q) < 0:
+            q[:, 0] *= -1
+        P = np.eye(4)
+        P[:3, :3] = q
+        P[:3, 3] = rng.normal(size=3) * 4
+        out.append(P)
+    return out
+
+
+def _table(n_maps, seed):
+    poses = _poses(n_maps, seed)
+    rng = np.random.default_rng(seed + 1)
+    n_kp = rng.integers(0, 5000, n_maps)
+    n_kp[rng.integers(0, n_maps)] = 0  # one map without keypoints drops out of the pair list
+    n_pts = rng.integers(50_000, 150_000, n_maps)
+    tab = {}
+    for i in range(n_maps - 1):
+        for j in range(i + 1, n_maps):
+            tab[(i, j)] = ((np.linalg.inv(poses[j]) @ poses[i]).astype(np.float32), float(np.round(rng.uniform(0.5, 20.0), 1)))
+    return n_kp, n_pts, tab
+
+
+def _worker(rank, world, port, n_maps, seed, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import mm3d_pkg
+    import importlib
+    mm = mm3d_pkg.load()
+    sh = importlib.import_module("map_merge_b200.sharding")
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        n_kp, n_pts, tab = _table(n_maps, seed)
+        first, count, per = sh.map_block(rank, world, n_maps)
+        # stage A exchange: every rank contributes the sizes of its block of maps
+        sizes = torch.zeros((per, 2), dtype=torch.int32)
+        for m in range(count):
+            sizes[m, 0] = int(n_pts[first + m]); sizes[m, 1] = int(n_kp[first + m])
+        allsz = [torch.zeros_like(sizes) for _ in range(world)]
+        dist.all_gather(allsz, sizes)
+        allsz = torch.stack(allsz).numpy()
+        g_pts = [int(allsz[sh.owner_of_map(m, world, n_maps), m - sh.owner_of_map(m, world, n_maps) * per, 0]) for m in range(n_maps)]
+        g_kp = [int(allsz[sh.owner_of_map(m, world, n_maps), m - sh.owner_of_map(m, world, n_maps) * per, 1]) for m in range(n_maps)]
+        assert g_pts == [int(x) for x in n_pts] and g_kp == [int(x) for x in n_kp]
+        # stage B: shard the pair list, "register" the local share, exchange
+        ij = sh.pair_list(g_kp)
+        owner = sh.lpt_assign(sh.pair_costs(ij, g_pts, g_kp, 33), world)
+        mine = [k for k in range(len(ij)) if owner[k] == rank]
+        T = np.stack([tab[ij[k]][0] for k in mine]) if mine else np.zeros((0, 4, 4), np.float32)
+        conf = np.array([tab[ij[k]][1] for k in mine])
+        res = sh.gather_pair_results(dist, torch, torch.device("cpu"), len(ij), mine, T.transpose(0, 2, 1), conf).numpy()
+        if rank == 0:
+            G, ref = mm.global_transforms(np.array(ij, np.int32), res[:, :16].reshape(-1, 4, 4).transpose(0, 2, 1).astype(np.float32), res[:, 16], 0.0)
+            q.put(dict(ij=ij, res=res, G=G, ref=ref, mine=len(mine)))
+        else:
+            q.put(dict(mine=len(mine)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_maps,world", [(8, 2), (5, 2), (3, 2)])
+def test_sharded_path_matches_single_process(mm, n_maps, world):
+    import torch.multiprocessing as mp
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_maps, 7, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    r0 = [o for o in outs if "G" in o][0]
+    import importlib
+    sh = importlib.import_module("map_merge_b200.sharding")
+    n_kp, n_pts, tab = _table(n_maps, 7)
+    ij = sh.pair_list([int(x) for x in n_kp])
+    assert r0["ij"] == ij
+    assert sum(o["mine"] for o in outs) == len(ij)
+    assert (r0["res"][:, 17] == 1).all()  # every pair registered by exactly one rank
+    T = np.stack([tab[p][0] for p in ij]); conf = [tab[p][1] for p in ij]
+    np.testing.assert_array_equal(r0["res"][:, :16].reshape(-1, 4, 4).transpose(0, 2, 1).astype(np.float32), T)
+    G, ref = mm.global_transforms(np.array(ij, np.int32), T, conf, 0.0)
+    assert ref == r0["ref"]
+    np.testing.assert_array_equal(G, r0["G"])
+
+
+def test_lpt_is_balanced_and_deterministic(mm):
+    import importlib
+    sh = importlib.import_module("map_merge_b200.sharding")
+    rng = np.random.default_rng(0)
+    costs = rng.uniform(1, 10, 496)
+    a = sh.lpt_assign(costs, 8)
+    assert np.array_equal(a, sh.lpt_assign(costs, 8))
+    loads = np.array([costs[a == b].sum() for b in range(8)])
+    assert loads.max() / loads.mean() < 1.02
+    assert sh.map_block(0, 8, 32) == (0, 4, 4) and sh.map_block(7, 8, 32) == (28, 4, 4)
+    assert sh.map_block(2, 4, 5) == (4, 1, 2) and sh.map_block(3, 4, 5)[1] == 0
