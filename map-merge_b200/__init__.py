@@ -196,7 +196,7 @@ class Context:
                                           C.byref(dog) if debug else None, C.byref(nd) if debug else None))
         r = self._take(kp, nk.value * 4, np.float32, (-1, 4))
         if debug:
-            return r, self._take(dog, nd.value, np.float32, (-1, 5))
+            return r, self._take(dog, nd.value, np.float32, (-1, 5) if type == "SIFT" else None)  # SIFT: octave-0 DoG; HARRIS: response
         return r
 
     def descriptors(self, pts, normals, kp, type="FPFH", radius=0.8, index_leaf=0.0, debug=False):

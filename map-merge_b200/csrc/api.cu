@@ -101,7 +101,7 @@ double auto_leaf(double index_leaf, double radius, double ratio)
 
 void check_supported(const mm3d_params& p)
 {
-  if (p.keypoint_type != MM3D_KP_SIFT) throw std::runtime_error("unsupported: keypoint_type HARRIS is not built yet (SURVEY.md 8f)");
+  if (p.keypoint_type != MM3D_KP_SIFT && p.keypoint_type != MM3D_KP_HARRIS) throw std::runtime_error("unsupported: unknown keypoint_type");
   if (p.descriptor_type != MM3D_DESC_FPFH) throw std::runtime_error("unsupported: only descriptor_type FPFH is built in this round");
   if (p.estimation_method != MM3D_EST_MATCHING) throw std::runtime_error("unsupported: estimation_method SAC_IA is not built yet (SURVEY.md 8f)");
 }
@@ -143,12 +143,15 @@ void compute_features(Ctx& c, const std::vector<CloudView>& raw, const mm3d_para
 
   tm.begin();
   std::vector<DCloud> kps;
-  sift_batch(c, fv, (float)p.resolution, 3, 3, (float)p.keypoint_threshold, kps, nullptr);
+  std::vector<const float4*> np(M);
+  for (int m = 0; m < M; ++m) np[m] = normals[m].p;
+  if (p.keypoint_type == MM3D_KP_HARRIS)  // detectKeypoints(..., threshold, normal_radius, resolution)  (map_merging.cpp:230-235)
+    harris_batch(c, fv, idx, np, (float)p.keypoint_threshold, (float)p.normal_radius, kps, nullptr, nullptr);
+  else
+    sift_batch(c, fv, (float)p.resolution, 3, 3, (float)p.keypoint_threshold, kps, nullptr);
   tm.end(3);
 
   tm.begin();
-  std::vector<const float4*> np(M);
-  for (int m = 0; m < M; ++m) np[m] = normals[m].p;
   std::vector<DBuf<float>> desc;
   fpfh_batch(c, fv, idx, np, kps, p.descriptor_radius, desc, nullptr);
   tm.end(4);
@@ -466,14 +469,29 @@ int mm3d_normals(mm3d_ctx* ctx, const float* pts, uint64_t n, double radius, dou
 int mm3d_keypoints(mm3d_ctx* ctx, const float* pts, uint64_t n, const float* normals, int type, double threshold, double radius,
                    double resolution, float** keypoints, uint64_t* n_keypoints, float** dog0, uint64_t* n_dog0)
 {
-  (void)normals;
-  (void)radius;
   if (!keypoints || !n_keypoints) return MM3D_ERR_ARG;
   MM_TRY(ctx)
-  if (type != MM3D_KP_SIFT) throw std::runtime_error("unsupported: keypoint_type HARRIS is not built yet (SURVEY.md 8f)");
+  if (type != MM3D_KP_SIFT && type != MM3D_KP_HARRIS) throw std::runtime_error("unsupported: unknown keypoint_type");
   DCloud d = upload_cloud(c, pts, n);
   std::vector<DCloud> kp;
   std::vector<DBuf<float>> dog;
+  if (type == MM3D_KP_HARRIS) {
+    // detectKeypointsHarris(points, normals, threshold, radius)  (features.cpp:94); dog0 receives the Harris response
+    if (!normals) throw std::runtime_error("detectKeypoints(HARRIS) needs normals");
+    DBuf<float4> nm(c, d.n);
+    if (d.n) MM_CUDA(cudaMemcpyAsync(nm.p, normals, (size_t)d.n * sizeof(float4), cudaMemcpyHostToDevice, c.stream));
+    std::vector<DIndex> idx;
+    build_index_batch(c, {d.view()}, (float)resolution, 2, 0, 0, idx);
+    harris_batch(c, {d.view()}, idx, {nm.p}, (float)threshold, (float)radius, kp, dog0 ? &dog : nullptr, nullptr);
+    *keypoints = (float*)host_copy(c, kp[0].pts.p, (size_t)kp[0].n);
+    *n_keypoints = (uint64_t)kp[0].n;
+    if (dog0) {
+      *dog0 = host_copy(c, dog[0].p, dog[0].n);
+      *n_dog0 = dog[0].n;
+    }
+    c.sync();
+    return MM3D_OK;
+  }
   // detectKeypointsSIFT(points, resolution, 3, 3, threshold)  (features.cpp:92)
   sift_batch(c, {d.view()}, (float)resolution, 3, 3, (float)threshold, kp, dog0 ? &dog : nullptr);
   *keypoints = (float*)host_copy(c, kp[0].pts.p, (size_t)kp[0].n);

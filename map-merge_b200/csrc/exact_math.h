@@ -37,73 +37,82 @@ MM_HD double bits_to_double(uint64_t u)
   return d;
 }
 
-// exp(x) for float x, evaluated in double and rounded once.
+MM_HD float bits_to_float(uint32_t u)
+{
+  float f;
+  memcpy(&f, &u, sizeof(f));
+  return f;
+}
+
+// exp(x) in float only: Cody-Waite reduction x = n ln2 + r, |r| <= ln2/2, degree-7 polynomial,
+// exact power-of-two scaling.  Within 1 ulp of the correctly rounded result (tests pin it against libm).
 MM_HD float expf_(float x)
 {
   if (x != x) return x;
   if (x < -104.0f) return 0.0f;
-  if (x > 88.8f) return INFINITY;
-  const double xd = (double)x;
-  const double n = rint(xd * 1.4426950408889634074);
-  const double r = xd - n * 0.69314718055994530942;
-  // Taylor, |r| <= 0.347: r^12/12! < 7e-15
-  double p = 1.0 / 39916800.0;
-  p = p * r + 1.0 / 3628800.0;
-  p = p * r + 1.0 / 362880.0;
-  p = p * r + 1.0 / 40320.0;
-  p = p * r + 1.0 / 5040.0;
-  p = p * r + 1.0 / 720.0;
-  p = p * r + 1.0 / 120.0;
-  p = p * r + 1.0 / 24.0;
-  p = p * r + 1.0 / 6.0;
-  p = p * r + 0.5;
-  p = p * r + 1.0;
-  p = p * r + 1.0;
-  const int ni = (int)n;  // in [-151, 129]
-  const double s = bits_to_double((uint64_t)(1023 + ni) << 52);
-  return (float)(p * s);
+  if (x > 88.72f) return INFINITY;
+  const float n = rintf(x * 1.44269504088896341f);
+  // ln2 split: the high part has 9 significant bits, so n * hi is exact for |n| < 2^15
+  float r = x - n * 0.693359375f;
+  r = r - n * -2.12194440e-4f;
+  float p = 1.9875691500e-4f;
+  p = p * r + 1.3981999507e-3f;
+  p = p * r + 8.3334519073e-3f;
+  p = p * r + 4.1665795894e-2f;
+  p = p * r + 1.6666665459e-1f;
+  p = p * r + 5.0000001201e-1f;
+  const float y = (p * (r * r) + r) + 1.0f;
+  int ni = (int)n;  // in [-151, 128]
+  // 2^ni in two exact factors so that sub-normal results and ni = 128 are handled
+  const int h = ni / 2;
+  const float s1 = bits_to_float((uint32_t)(127 + h) << 23);
+  const float s2 = bits_to_float((uint32_t)(127 + (ni - h)) << 23);
+  return (y * s1) * s2;
 }
 
-// atan(z) for z in [0, 1], double.
-MM_HD double atan01_(double z)
+// atan on [0, inf) in float: three-interval reduction, odd degree-9 polynomial, the constants pi/2 and
+// pi/4 carried as hi + lo pairs.  <= 2 ulp from the correctly rounded value (tests pin it against libm).
+MM_HD float atanf_pos_(float x, float* lo)
 {
-  z = z / (1.0 + sqrt(1.0 + z * z));
-  z = z / (1.0 + sqrt(1.0 + z * z));  // now z <= 0.1990
-  const double z2 = z * z;
-  double s = 1.0 / 23.0;
-  s = 1.0 / 21.0 - z2 * s;
-  s = 1.0 / 19.0 - z2 * s;
-  s = 1.0 / 17.0 - z2 * s;
-  s = 1.0 / 15.0 - z2 * s;
-  s = 1.0 / 13.0 - z2 * s;
-  s = 1.0 / 11.0 - z2 * s;
-  s = 1.0 / 9.0 - z2 * s;
-  s = 1.0 / 7.0 - z2 * s;
-  s = 1.0 / 5.0 - z2 * s;
-  s = 1.0 / 3.0 - z2 * s;
-  s = 1.0 - z2 * s;
-  return 4.0 * (z * s);
-}
-
-MM_HD double atan2d_(double y, double x)
-{
-  const double kPi = 3.14159265358979323846;
-  if (x != x || y != y) return x + y;
-  const double ax = fabs(x), ay = fabs(y);
-  double a;
-  if (ax == 0.0 && ay == 0.0)
-    a = 0.0;
-  else if (ay <= ax)
-    a = atan01_(ay / ax);
-  else
-    a = 0.5 * kPi - atan01_(ax / ay);
-  if (signbit(x)) a = kPi - a;
-  return signbit(y) ? -a : a;
+  float y0, y0lo;
+  if (x > 2.414213562373095f) {  // tan(3 pi / 8)
+    y0 = 1.57079637050628662109375f;
+    y0lo = -4.37113900018624283e-8f;
+    x = -(1.0f / x);
+  } else if (x > 0.4142135623730950f) {  // tan(pi / 8)
+    y0 = 0.785398185253143310546875f;
+    y0lo = -2.18556950009312142e-8f;
+    x = (x - 1.0f) / (x + 1.0f);
+  } else {
+    y0 = 0.0f;
+    y0lo = 0.0f;
+  }
+  const float z = x * x;
+  float p = 8.05374449538e-2f;
+  p = p * z - 1.38776856032e-1f;
+  p = p * z + 1.99777106478e-1f;
+  p = p * z - 3.33329491539e-1f;
+  const float corr = p * z * x + y0lo;  // small terms first
+  const float hi = y0 + x;              // exact or nearly so: x is small against y0 or y0 is 0
+  *lo = ((y0 - hi) + x) + corr;         // rounding error of hi + the small terms
+  return hi;
 }
 
 MM_HD float atan2f_(float y, float x)
 {
-  return (float)atan2d_((double)y, (double)x);
+  if (x != x || y != y) return x + y;
+  const float ax = fabsf(x), ay = fabsf(y);
+  float hi = 0.0f, lo = 0.0f;
+  if (!(ax == 0.0f && ay == 0.0f)) hi = atanf_pos_(ay / ax, &lo);  // ay / 0 = inf -> pi/2
+  float a;
+  if (signbit(x)) {
+    // pi - (hi + lo) with pi = pi_hi + pi_lo
+    const float d = 3.1415927410125732421875f - hi;
+    a = d + (-8.74227800037248566e-8f - lo);
+  } else {
+    a = hi + lo;
+  }
+  return signbit(y) ? -a : a;
 }
 
 // sin/cos for |t| <= ~1.2 (the eigen-solver only needs [0, pi/3]).
@@ -405,6 +414,101 @@ MM_HD void eigen33_smallest(const float* mat, float* eigenvalue, float* vec)
   vec[0] = v[0] / inv;
   vec[1] = v[1] / inv;
   vec[2] = v[2] / inv;
+}
+
+// Symmetric 3x3 eigen-decomposition in double by cyclic Jacobi rotations (stands in for
+// Eigen::SelfAdjointEigenSolver<Matrix3d> in the SHOT local reference frame).  a is row-major symmetric;
+// eigenvalues come out ascending, vec[:, i] (column i, row-major storage) is the matching unit eigenvector.
+MM_HD void eig3_sym_d(const double* a_in, double* val, double* vec)
+{
+  double a[9];
+  for (int i = 0; i < 9; ++i) {
+    a[i] = a_in[i];
+    vec[i] = 0.0;
+  }
+  vec[0] = vec[4] = vec[8] = 1.0;
+  for (int sweep = 0; sweep < 50; ++sweep) {
+    const double off = a[1] * a[1] + a[2] * a[2] + a[5] * a[5];
+    const double diag = a[0] * a[0] + a[4] * a[4] + a[8] * a[8];
+    if (off <= 1e-32 * diag || off == 0.0) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        const double apq = a[p * 3 + q];
+        if (apq == 0.0) continue;
+        const double theta = (a[q * 3 + q] - a[p * 3 + p]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < 3; ++k) {  // A <- A J
+          const double akp = a[k * 3 + p], akq = a[k * 3 + q];
+          a[k * 3 + p] = c * akp - sn * akq;
+          a[k * 3 + q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < 3; ++k) {  // A <- J^T A
+          const double apk = a[p * 3 + k], aqk = a[q * 3 + k];
+          a[p * 3 + k] = c * apk - sn * aqk;
+          a[q * 3 + k] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; ++k) {  // V <- V J
+          const double vkp = vec[k * 3 + p], vkq = vec[k * 3 + q];
+          vec[k * 3 + p] = c * vkp - sn * vkq;
+          vec[k * 3 + q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+  val[0] = a[0];
+  val[1] = a[4];
+  val[2] = a[8];
+  // ascending order (selection sort on three values, columns follow)
+  for (int i = 0; i < 2; ++i)
+    for (int j = i + 1; j < 3; ++j)
+      if (val[j] < val[i]) {
+        const double tv = val[i];
+        val[i] = val[j];
+        val[j] = tv;
+        for (int k = 0; k < 3; ++k) {
+          const double tt = vec[k * 3 + i];
+          vec[k * 3 + i] = vec[k * 3 + j];
+          vec[k * 3 + j] = tt;
+        }
+      }
+}
+
+// acos / atan2 in double for SHOT's inclination and azimuth interpolation (IEEE ops only).
+MM_HD double atan01_d_(double z)
+{
+  z = z / (1.0 + sqrt(1.0 + z * z));
+  z = z / (1.0 + sqrt(1.0 + z * z));
+  const double z2 = z * z;
+  double s = 1.0 / 23.0;
+  s = 1.0 / 21.0 - z2 * s;
+  s = 1.0 / 19.0 - z2 * s;
+  s = 1.0 / 17.0 - z2 * s;
+  s = 1.0 / 15.0 - z2 * s;
+  s = 1.0 / 13.0 - z2 * s;
+  s = 1.0 / 11.0 - z2 * s;
+  s = 1.0 / 9.0 - z2 * s;
+  s = 1.0 / 7.0 - z2 * s;
+  s = 1.0 / 5.0 - z2 * s;
+  s = 1.0 / 3.0 - z2 * s;
+  s = 1.0 - z2 * s;
+  return 4.0 * (z * s);
+}
+MM_HD double atan2_d_(double y, double x)
+{
+  const double kPi = 3.14159265358979323846;
+  if (x != x || y != y) return x + y;
+  const double ax = fabs(x), ay = fabs(y);
+  double a;
+  if (ax == 0.0 && ay == 0.0) a = 0.0;
+  else if (ay <= ax) a = atan01_d_(ay / ax);
+  else a = 0.5 * kPi - atan01_d_(ax / ay);
+  if (signbit(x)) a = kPi - a;
+  return signbit(y) ? -a : a;
+}
+// acos(c) for c in [-1, 1]: atan2(sqrt((1 - c)(1 + c)), c)
+MM_HD double acos_d_(double c)
+{
+  return atan2_d_(sqrt((1.0 - c) * (1.0 + c)), c);
 }
 
 // FLANN L2_Simple in 3-D: sequential float accumulation, no contraction.

@@ -7,6 +7,7 @@
 // point index, so every float accumulation happens in the canonical order.
 #include <algorithm>
 #include <cmath>
+#include <limits>
 
 #include "mm3d_internal.cuh"
 
@@ -297,9 +298,28 @@ __device__ __forceinline__ int clampbin(int h)
   return h < 0 ? 0 : (h > 10 ? 10 : h);
 }
 
-__global__ void __launch_bounds__(FB) spfh_kernel(const FpfhJob* __restrict__ jobs, float r2, int rv)
+// FPFH bins are floor(11 * ((f + pi) / 2pi)) resp. floor(11 * ((f + 1) / 2)) evaluated in DOUBLE from a float feature
+// (pcl/features/impl/fpfh.hpp).  Both are monotone in f, so the bin is fully described by 10 float thresholds:
+// thr[b] = smallest float whose double formula reaches bin b.  The host derives the thresholds from the literal double
+// expressions; the kernel only compares floats.
+struct BinTable {
+  float t[3][12];  // t[feature][b], b = 1..10 used; t[.][0] = -inf, t[.][11] = +inf
+};
+
+__device__ __forceinline__ int lookup_bin(const float* thr, float f, float scale, float shift)
+{
+  int g = clampbin((int)((f + shift) * scale));  // float guess, at most one bin off
+  while (g < 10 && f >= thr[g + 1]) ++g;
+  while (g > 0 && f < thr[g]) --g;
+  return g;
+}
+
+__global__ void __launch_bounds__(FB) spfh_kernel(const FpfhJob* __restrict__ jobs, float r2, int rv, BinTable bins)
 {
   __shared__ unsigned short cnt[33 * FB];
+  __shared__ float thr[3][12];
+  if (threadIdx.x < 36) (&thr[0][0])[threadIdx.x] = (&bins.t[0][0])[threadIdx.x];
+  __syncthreads();
   const FpfhJob& j = jobs[blockIdx.y];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= j.g.n) return;
@@ -307,7 +327,6 @@ __global__ void __launch_bounds__(FB) spfh_kernel(const FpfhJob* __restrict__ jo
   for (int b = 0; b < 33; ++b) cnt[b * FB + threadIdx.x] = 0;
   const float4 p = j.g.pts[k];
   const float4 np = j.normals[j.g.orig ? j.g.orig[k] : k];
-  const float d_pi = 1.0f / (2.0f * 3.14159265358979323846f);
   int n = 0;
   for_each_in_radius(j.g, p.x, p.y, p.z, r2, rv, [&](int q, const float4& pq, float) {
     ++n;
@@ -315,9 +334,9 @@ __global__ void __launch_bounds__(FB) spfh_kernel(const FpfhJob* __restrict__ jo
     const float4 nq = j.normals[j.g.orig ? j.g.orig[q] : q];
     float f1, f2, f3;
     pair_features(p, np, pq, nq, &f1, &f2, &f3);
-    const int h1 = clampbin((int)floor(11 * (((double)f1 + 3.14159265358979323846) * (double)d_pi)));
-    const int h2 = clampbin((int)floor(11 * (((double)f2 + 1.0) * 0.5)));
-    const int h3 = clampbin((int)floor(11 * (((double)f3 + 1.0) * 0.5)));
+    const int h1 = lookup_bin(thr[0], f1, 11.0f * 0.15915494f, 3.14159274f);
+    const int h2 = lookup_bin(thr[1], f2, 5.5f, 1.0f);
+    const int h3 = lookup_bin(thr[2], f3, 5.5f, 1.0f);
     cnt[h1 * FB + threadIdx.x]++;
     cnt[(11 + h2) * FB + threadIdx.x]++;
     cnt[(22 + h3) * FB + threadIdx.x]++;
@@ -404,9 +423,206 @@ __global__ void __launch_bounds__(256) fpfh_emit_kernel(const FpfhEmitJob* __res
   if (b == 0) j.kp_out[o] = j.kp[kp];
 }
 
+// ---------------------------------------------------------------- K6 Harris3D
+struct HarrisJob {
+  GridView g;
+  const float4* normals;  // per original point
+  float* response;        // per slot
+  uint32_t* flags;        // per original point
+  const float4* cloud;    // original order
+  float4* corners;
+  int n_corners;
+};
+
+// responseHarris + calculateNormalCovar (SSE branch: sums divided by the count)
+__global__ void __launch_bounds__(FB) harris_response_kernel(const HarrisJob* __restrict__ jobs, float r2, int rv)
+{
+  const HarrisJob& j = jobs[blockIdx.y];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= j.g.n) return;
+  const float4 q = j.g.pts[k];
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f, c5 = 0.f, c6 = 0.f, c7 = 0.f;
+  unsigned count = 0;
+  for_each_in_radius(j.g, q.x, q.y, q.z, r2, rv, [&](int s, const float4&, float) {
+    const float4 nq = j.normals[j.g.orig ? j.g.orig[s] : s];
+    if (!isfinite(nq.x)) return;
+    c0 += nq.x * nq.x; c1 += nq.x * nq.y; c2 += nq.x * nq.z;
+    c5 += nq.y * nq.y; c6 += nq.y * nq.z;
+    c7 += nq.z * nq.z;
+    ++count;
+  });
+  if (count > 0) {
+    const float cn = (float)count;
+    c0 /= cn; c1 /= cn; c2 /= cn; c5 /= cn; c6 /= cn; c7 /= cn;
+  } else {
+    c0 = c1 = c2 = c5 = c6 = c7 = 0.f;
+  }
+  float resp = 0.0f;
+  const float trace = c0 + c5 + c7;
+  if (trace != 0.f) {
+    const float det = c0 * c5 * c7 + 2.0f * c1 * c2 * c6 - c2 * c2 * c5 - c1 * c1 * c7 - c6 * c6 * c0;
+    resp = 0.04f + det - 0.04f * trace * trace;
+  }
+  j.response[k] = resp;
+}
+
+// non-maximum suppression: keep a point unless a radius neighbour has a strictly larger response
+__global__ void __launch_bounds__(FB) harris_nms_kernel(const HarrisJob* __restrict__ jobs, float r2, int rv, float threshold)
+{
+  const HarrisJob& j = jobs[blockIdx.y];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= j.g.n) return;
+  const float resp = j.response[k];
+  uint32_t keep = 0;
+  if (isfinite(resp) && !(resp < threshold)) {
+    const float4 q = j.g.pts[k];
+    bool is_max = true;
+    for_each_in_radius(j.g, q.x, q.y, q.z, r2, rv, [&](int s, const float4&, float) {
+      if (resp < j.response[s]) is_max = false;
+    });
+    keep = is_max ? 1u : 0u;
+  }
+  j.flags[j.g.orig ? j.g.orig[k] : k] = keep;
+}
+
+struct HarrisEmitJob {
+  const float4* cloud;
+  const uint32_t* flags;
+  const uint32_t* pos;
+  float4* dst;
+  int n;
+};
+__global__ void __launch_bounds__(256) harris_emit_kernel(const HarrisEmitJob* __restrict__ jobs)
+{
+  const HarrisEmitJob& j = jobs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= j.n) return;
+  if (!j.flags[i]) return;
+  const float4 p = j.cloud[i];
+  j.dst[j.pos[i]] = make_float4(p.x, p.y, p.z, __uint_as_float(0xff000000u));
+}
+
+// refineCorners: c <- (sum n n^T)^-1 sum n n^T p over the radius neighbours of c, at most 10 times
+__global__ void __launch_bounds__(FB) harris_refine_kernel(const HarrisJob* __restrict__ jobs, float r2, int rv)
+{
+  const HarrisJob& j = jobs[blockIdx.y];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= j.n_corners) return;
+  float4 corner = j.corners[t];
+  unsigned iterations = 0;
+  float diff;
+  do {
+    float N[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, Np[3] = {0.f, 0.f, 0.f};
+    const float cx = corner.x, cy = corner.y, cz = corner.z;
+    for_each_in_radius(j.g, cx, cy, cz, r2, rv, [&](int s, const float4& p, float) {
+      const float4 nq = j.normals[j.g.orig ? j.g.orig[s] : s];
+      if (!isfinite(nq.x)) return;
+      const float nv[3] = {nq.x, nq.y, nq.z};
+      float nnT[9];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) nnT[r * 3 + c] = nv[r] * nv[c];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) N[e] += nnT[e];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) Np[r] += (nnT[r * 3 + 0] * p.x + nnT[r * 3 + 1] * p.y) + nnT[r * 3 + 2] * p.z;
+    });
+    // pcl::invert3x3SymMatrix
+    const float fd_ee = N[4] * N[8] - N[7] * N[5];
+    const float ce_bf = N[2] * N[5] - N[1] * N[8];
+    const float be_cd = N[1] * N[5] - N[2] * N[4];
+    const float det = N[0] * fd_ee + N[1] * ce_bf + N[2] * be_cd;
+    if (det != 0.f) {
+      float inv[9];
+      inv[0] = fd_ee;
+      inv[1] = inv[3] = ce_bf;
+      inv[2] = inv[6] = be_cd;
+      inv[4] = (N[0] * N[8] - N[2] * N[2]);
+      inv[5] = inv[7] = (N[1] * N[2] - N[0] * N[5]);
+      inv[8] = (N[0] * N[4] - N[1] * N[1]);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) inv[e] /= det;
+      corner.x = (inv[0] * Np[0] + inv[1] * Np[1]) + inv[2] * Np[2];
+      corner.y = (inv[3] * Np[0] + inv[4] * Np[1]) + inv[5] * Np[2];
+      corner.z = (inv[6] * Np[0] + inv[7] * Np[1]) + inv[8] * Np[2];
+    }
+    const float dx = corner.x - cx, dy = corner.y - cy, dz = corner.z - cz;
+    diff = (dx * dx + dy * dy) + dz * dz;
+  } while ((double)diff > 1e-6 && ++iterations < 10);
+  j.corners[t] = corner;
+}
+
 }  // namespace
 
 // ===========================================================================
+void harris_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<const float4*>& normals,
+                  float threshold, float radius_f, std::vector<DCloud>& keypoints, std::vector<DBuf<float>>* response_dbg,
+                  std::vector<DCloud>* unrefined_dbg)
+{
+  const int M = (int)clouds.size();
+  keypoints.clear();
+  keypoints.resize(M);
+  if (response_dbg) { response_dbg->clear(); response_dbg->resize(M); }
+  if (unrefined_dbg) { unrefined_dbg->clear(); unrefined_dbg->resize(M); }
+  if (M == 0) return;
+  std::vector<int> ns(M);
+  for (int m = 0; m < M; ++m) ns[m] = clouds[m].n;
+  int total = 0;
+  std::vector<Seg> segs = make_segs(ns, &total);
+  const int mx = max_n(clouds);
+  if (total == 0) return;
+  // search_radius_ is the float radius widened to double (HarrisKeypoint3D::setRadius(float))
+  const double rd = (double)radius_f;
+  const float r2 = (float)(rd * rd);
+  const int rv = radius_voxels(rd, idx[0].v.leaf);
+  DBuf<uint32_t> flags(c, total), pos(c, total);
+  std::vector<DBuf<float>> resp(M);
+  std::vector<HarrisJob> jobs(M);
+  for (int m = 0; m < M; ++m) {
+    resp[m].alloc(c, ns[m]);
+    jobs[m].g = idx[m].v;
+    jobs[m].normals = normals[m];
+    jobs[m].response = resp[m].p;
+    jobs[m].flags = flags.p + segs[m].off;
+    jobs[m].cloud = clouds[m].pts;
+    jobs[m].corners = nullptr;
+    jobs[m].n_corners = 0;
+  }
+  DBuf<HarrisJob> dj = to_device(c, jobs);
+  const dim3 grid((mx + FB - 1) / FB, M);
+  { double b = 0; for (int m = 0; m < M; ++m) b += 36.0 * ns[m]; MM_BYTES(c, b); }
+  MM_LAUNCH(c, harris_response_kernel, grid, FB, 0, dj.p, r2, rv);
+  { double b = 0; for (int m = 0; m < M; ++m) b += 24.0 * ns[m]; MM_BYTES(c, b); }
+  MM_LAUNCH(c, harris_nms_kernel, grid, FB, 0, dj.p, r2, rv, threshold);
+  std::vector<int> totals;
+  scan_flags_batch(c, flags.p, pos.p, segs, totals);
+  std::vector<HarrisEmitJob> ej(M);
+  int mxc = 0;
+  for (int m = 0; m < M; ++m) {
+    keypoints[m].n = totals[m];
+    keypoints[m].pts.alloc(c, totals[m]);
+    ej[m] = HarrisEmitJob{clouds[m].pts, flags.p + segs[m].off, pos.p + segs[m].off, keypoints[m].pts.p, ns[m]};
+    jobs[m].corners = keypoints[m].pts.p;
+    jobs[m].n_corners = totals[m];
+    mxc = std::max(mxc, totals[m]);
+  }
+  DBuf<HarrisEmitJob> dej = to_device(c, ej);
+  MM_LAUNCH(c, harris_emit_kernel, dim3((mx + 255) / 256, M), 256, 0, dej.p);
+  if (unrefined_dbg)
+    for (int m = 0; m < M; ++m) {
+      (*unrefined_dbg)[m].n = totals[m];
+      (*unrefined_dbg)[m].pts.alloc(c, totals[m]);
+      if (totals[m]) MM_CUDA(cudaMemcpyAsync((*unrefined_dbg)[m].pts.p, keypoints[m].pts.p, (size_t)totals[m] * sizeof(float4), cudaMemcpyDeviceToDevice, c.stream));
+    }
+  if (mxc > 0) {
+    DBuf<HarrisJob> dj2 = to_device(c, jobs);
+    MM_LAUNCH(c, harris_refine_kernel, dim3((mxc + FB - 1) / FB, M), FB, 0, dj2.p, r2, rv);
+  }
+  if (response_dbg)
+    for (int m = 0; m < M; ++m) (*response_dbg)[m] = std::move(resp[m]);
+}
+
 void remove_outliers_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, double radius, int min_nb,
                            std::vector<DCloud>& out, std::vector<DBuf<int>>* counts)
 {
@@ -563,6 +779,42 @@ void sift_batch(Ctx& c, const std::vector<CloudView>& clouds, float min_scale, i
   }
 }
 
+static int fpfh_bin_f1(float f)
+{
+  const float d_pi = 1.0f / (2.0f * (float)M_PI);
+  int h = (int)std::floor(11 * (((double)f + M_PI) * (double)d_pi));
+  return h < 0 ? 0 : (h > 10 ? 10 : h);
+}
+static int fpfh_bin_f23(float f)
+{
+  int h = (int)std::floor(11 * (((double)f + 1.0) * 0.5));
+  return h < 0 ? 0 : (h > 10 ? 10 : h);
+}
+static float next_up(float f) { return std::nextafter(f, std::numeric_limits<float>::infinity()); }
+
+static BinTable make_bin_table()
+{
+  BinTable bt;
+  for (int feat = 0; feat < 3; ++feat) {
+    int (*fn)(float) = feat == 0 ? fpfh_bin_f1 : fpfh_bin_f23;
+    bt.t[feat][0] = -std::numeric_limits<float>::infinity();
+    bt.t[feat][11] = std::numeric_limits<float>::infinity();
+    for (int b = 1; b <= 10; ++b) {
+      // smallest float with fn(f) >= b: bisection over the ordered float line in [-8, 8]
+      float lo = -8.0f, hi = 8.0f;  // fn(lo) = 0 < b <= fn(hi) = 10
+      while (next_up(lo) < hi) {
+        const float mid = lo + (hi - lo) * 0.5f;
+        const float m = (mid <= lo) ? next_up(lo) : (mid >= hi ? lo : mid);
+        if (m <= lo || m >= hi) break;
+        if (fn(m) >= b) hi = m;
+        else lo = m;
+      }
+      bt.t[feat][b] = hi;
+    }
+  }
+  return bt;
+}
+
 void fpfh_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<const float4*>& normals,
                 std::vector<DCloud>& keypoints, double radius, std::vector<DBuf<float>>& desc, std::vector<DBuf<float>>* spfh_dbg)
 {
@@ -605,7 +857,8 @@ void fpfh_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<
   const int rv = radius_voxels(radius, idx[0].v.leaf);
   MM_LAUNCH(c, fpfh_mark_kernel, dim3((mxk + FB - 1) / FB, M), FB, 0, dj.p, r2, rv);
   { double b = 0; for (int m = 0; m < M; ++m) b += (32.0 + 132.0 + 4.0) * clouds[m].n; MM_BYTES(c, b); }
-  MM_LAUNCH(c, spfh_kernel, dim3((mx + FB - 1) / FB, M), FB, 0, dj.p, r2, rv);
+  static const BinTable bins = make_bin_table();
+  MM_LAUNCH(c, spfh_kernel, dim3((mx + FB - 1) / FB, M), FB, 0, dj.p, r2, rv, bins);
   { double b = 0; for (int m = 0; m < M; ++m) b += (16.0 + 132.0) * clouds[m].n + (16.0 + 132.0) * nks[m]; MM_BYTES(c, b); }
   MM_LAUNCH(c, fpfh_weight_kernel, dim3((mxk * 3 + FB - 1) / FB, M), FB, 0, dj.p, r2, rv);
   DBuf<uint32_t> flags(c, totalk), pos(c, totalk);

@@ -24,15 +24,16 @@ struct KnnJob {
   float* dist;  // na x k
 };
 
-// Exact FP32 k-NN of every row of A among the rows of B.  One thread owns one
-// query row (registers); B streams through shared memory, every thread reads the
-// same B element at a time (broadcast).  Distances accumulate dimension by
-// dimension without contraction, like flann::L2_Simple; ties keep the lower index.
-template <int D>
+// Exact FP32 k-NN of every row of A among the rows of B.  One thread owns one query row (registers); B
+// streams through shared memory stored dimension-major, so one 128-bit broadcast load feeds the same
+// dimension of four B rows.  Distances accumulate dimension by dimension without contraction, like
+// flann::L2_Simple; ties keep the lower index.  The running top-K lives in registers (K is a template
+// parameter, insertion is a fully unrolled compare/select chain).
+template <int D, int K>
 __global__ void __launch_bounds__(128) knn_small_kernel(const KnnJob* __restrict__ jobs)
 {
   constexpr int TB = 64;
-  __shared__ float sb[TB * D];
+  __shared__ __align__(16) float sb[D * TB];
   const KnnJob j = jobs[blockIdx.y];
   if (blockIdx.x * blockDim.x >= j.na) return;
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -40,41 +41,61 @@ __global__ void __launch_bounds__(128) knn_small_kernel(const KnnJob* __restrict
   float a[D];
 #pragma unroll
   for (int t = 0; t < D; ++t) a[t] = live ? j.A[(size_t)row * D + t] : 0.f;
-  float bd[KMAX];
-  int bi[KMAX];
-  int cnt = 0;
-  const int k = j.k;
+  float bd[K];
+  int bi[K];
+#pragma unroll
+  for (int t = 0; t < K; ++t) {
+    bd[t] = __int_as_float(0x7f800000);  // +inf
+    bi[t] = -1;
+  }
   for (int base = 0; base < j.nb; base += TB) {
     const int tb = min(TB, j.nb - base);
     __syncthreads();
-    for (int e = threadIdx.x; e < tb * D; e += blockDim.x) sb[e] = j.B[(size_t)base * D + e];
+    for (int e = threadIdx.x; e < TB * D; e += blockDim.x) {
+      const int r = e / D, t = e - r * D;  // coalesced global read, transposed shared write
+      sb[t * TB + r] = (r < tb) ? j.B[(size_t)(base + r) * D + t] : 0.f;
+    }
     __syncthreads();
     if (!live) continue;
-    for (int r = 0; r < tb; ++r) {
-      const float* b = sb + r * D;
-      float acc = 0.f;
+    for (int r0 = 0; r0 < tb; r0 += 4) {
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll
       for (int t = 0; t < D; ++t) {
-        const float diff = a[t] - b[t];
-        acc += diff * diff;
+        const float4 b = *reinterpret_cast<const float4*>(&sb[t * TB + r0]);
+        const float d0 = a[t] - b.x, d1 = a[t] - b.y, d2 = a[t] - b.z, d3 = a[t] - b.w;
+        acc0 += d0 * d0;
+        acc1 += d1 * d1;
+        acc2 += d2 * d2;
+        acc3 += d3 * d3;
       }
-      if (cnt == k && !(acc < bd[k - 1])) continue;
-      int pos = (cnt < k) ? cnt : k - 1;
-      while (pos > 0 && acc < bd[pos - 1]) {
-        bd[pos] = bd[pos - 1];
-        bi[pos] = bi[pos - 1];
-        --pos;
+      const float accs[4] = {acc0, acc1, acc2, acc3};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float acc = accs[u];
+        if (r0 + u < tb && acc < bd[K - 1]) {
+          const int id = base + r0 + u;
+#pragma unroll
+          for (int t = K - 1; t >= 1; --t) {
+            const bool up = acc < bd[t - 1];
+            const bool here = !up && acc < bd[t];
+            bd[t] = up ? bd[t - 1] : (here ? acc : bd[t]);
+            bi[t] = up ? bi[t - 1] : (here ? id : bi[t]);
+          }
+          if (acc < bd[0]) {
+            bd[0] = acc;
+            bi[0] = id;
+          }
+        }
       }
-      bd[pos] = acc;
-      bi[pos] = base + r;
-      if (cnt < k) ++cnt;
     }
   }
-  if (live)
-    for (int t = 0; t < k; ++t) {
-      j.idx[(size_t)row * k + t] = t < cnt ? bi[t] : -1;
-      j.dist[(size_t)row * k + t] = t < cnt ? bd[t] : 0.f;
+  if (live) {
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+      j.idx[(size_t)row * K + t] = bi[t];
+      j.dist[(size_t)row * K + t] = bi[t] >= 0 ? bd[t] : 0.f;
     }
+  }
 }
 
 // Any dimension (PFH 125 ... SHOT 1344): a block owns 64 query rows and a tile of
@@ -481,9 +502,16 @@ void match_batch(Ctx& c, const std::vector<const float*>& desc, const std::vecto
   }
   DBuf<KnnJob> dkj = to_device(c, kj);
   if (max_rows > 0) {
-    if (dim == 33) {
+    // the register kernel needs one k for the whole batch (k is clamped per job only when a set is smaller than k)
+    bool uniform_k = true;
+    for (const KnnJob& q : kj)
+      if (q.na > 0 && q.k != (int)k_in) uniform_k = false;
+    if (dim == 33 && uniform_k && (k_in == 5 || k_in == 1 || k_in == 8)) {
       { double b = 0; for (const KnnJob& q : kj) b += 4.0 * dim * ((double)q.na + q.nb) + 8.0 * q.k * q.na; MM_BYTES(c, b); }
-      MM_LAUNCH(c, knn_small_kernel<33>, dim3((max_rows + 127) / 128, 2 * P), 128, 0, dkj.p);
+      const dim3 grid((max_rows + 127) / 128, 2 * P);
+      if (k_in == 5) MM_LAUNCH(c, (knn_small_kernel<33, 5>), grid, 128, 0, dkj.p);
+      else if (k_in == 1) MM_LAUNCH(c, (knn_small_kernel<33, 1>), grid, 128, 0, dkj.p);
+      else MM_LAUNCH(c, (knn_small_kernel<33, 8>), grid, 128, 0, dkj.p);
     } else {
       { double b = 0; for (const KnnJob& q : kj) b += 4.0 * dim * ((double)q.na + q.nb) + 8.0 * q.k * q.na; MM_BYTES(c, b); }
       MM_LAUNCH(c, knn_generic_kernel, dim3((max_rows + 63) / 64, 2 * P), 128, 0, dkj.p, dim);

@@ -323,6 +323,9 @@ void remove_outliers_batch(Ctx& c, const std::vector<CloudView>& clouds, const s
 void normals_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, double radius, std::vector<DBuf<float4>>& normals);
 void sift_batch(Ctx& c, const std::vector<CloudView>& clouds, float min_scale, int n_octaves, int n_scales, float min_contrast,
                 std::vector<DCloud>& keypoints, std::vector<DBuf<float>>* dog0);
+void harris_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<const float4*>& normals,
+                  float threshold, float radius, std::vector<DCloud>& keypoints, std::vector<DBuf<float>>* response_dbg,
+                  std::vector<DCloud>* unrefined_dbg);
 // keypoints are filtered in place; desc[m] = K' x 33
 void fpfh_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<const float4*>& normals,
                 std::vector<DCloud>& keypoints, double radius, std::vector<DBuf<float>>& desc, std::vector<DBuf<float>>* spfh_dbg);

@@ -701,6 +701,108 @@ static Cloud sift_keypoints(const Cloud& input, float min_scale, int nr_octaves,
 }
 
 // ===========================================================================
+// a7  detectKeypoints(HARRIS) -> pcl::HarrisKeypoint3D<PointXYZRGB, PointXYZI>
+// [REF src/features.cpp:64-83: setNonMaxSupression(true), setRefine(true), setThreshold(float), setRadius(float)]
+// [PCL-recall pcl/keypoints/impl/harris_3d.hpp (SSE branch of calculateNormalCovar), pcl/common/impl/eigen.hpp
+//  invert3x3SymMatrix].  PCL's OpenMP loops make the output order nondeterministic; canonical = ascending index.
+// ===========================================================================
+static Cloud harris_keypoints(const Cloud& input, const Normals& normals, float threshold, float radius_f,
+                              std::vector<float>* response_dbg = nullptr, Cloud* unrefined_dbg = nullptr)
+{
+  const double search_radius = (double)radius_f;  // search_radius_ = float radius (setRadius(float))
+  Grid tree;
+  tree.build(input, radius_f);
+  const size_t n = input.size();
+  std::vector<float> response(n, 0.0f);
+  std::vector<int> nn_idx;
+  std::vector<float> nn_dist;
+  // responseHarris
+  for (size_t p = 0; p < n; ++p) {
+    tree.radius_sorted(input[p].x, input[p].y, input[p].z, search_radius, nn_idx, nn_dist);
+    // calculateNormalCovar: xx xy xz | yy yz | zz
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c5 = 0.f, c6 = 0.f, c7 = 0.f;
+    unsigned count = 0;
+    for (int q : nn_idx) {
+      const N4& nq = normals[q];
+      if (!std::isfinite(nq.nx)) continue;
+      c0 += nq.nx * nq.nx; c1 += nq.nx * nq.ny; c2 += nq.nx * nq.nz;
+      c5 += nq.ny * nq.ny; c6 += nq.ny * nq.nz;
+      c7 += nq.nz * nq.nz;
+      ++count;
+    }
+    if (count > 0) {
+      const float cn = (float)count;
+      c0 /= cn; c1 /= cn; c2 /= cn; c5 /= cn; c6 /= cn; c7 /= cn;
+    } else {
+      c0 = c1 = c2 = c5 = c6 = c7 = 0.f;
+    }
+    const float trace = c0 + c5 + c7;
+    if (trace != 0) {
+      const float det = c0 * c5 * c7 + 2.0f * c1 * c2 * c6 - c2 * c2 * c5 - c1 * c1 * c7 - c6 * c6 * c0;
+      response[p] = 0.04f + det - 0.04f * trace * trace;
+    }
+  }
+  if (response_dbg) *response_dbg = response;
+  // non-maximum suppression
+  Cloud corners;
+  for (size_t p = 0; p < n; ++p) {
+    if (!std::isfinite(response[p]) || response[p] < threshold) continue;
+    tree.radius_sorted(input[p].x, input[p].y, input[p].z, search_radius, nn_idx, nn_dist);
+    bool is_maxima = true;
+    for (int q : nn_idx)
+      if (response[p] < response[q]) { is_maxima = false; break; }
+    if (is_maxima) {
+      P4 c = input[p];
+      c.rgba = 0xff000000u;
+      corners.push_back(c);
+    }
+  }
+  if (unrefined_dbg) *unrefined_dbg = corners;
+  // refineCorners
+  for (P4& corner_out : corners) {
+    unsigned iterations = 0;
+    float diff;
+    do {
+      float NNT[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, NNTp[3] = {0, 0, 0};
+      const float cx = corner_out.x, cy = corner_out.y, cz = corner_out.z;
+      tree.radius_sorted(cx, cy, cz, search_radius, nn_idx, nn_dist);
+      for (int q : nn_idx) {
+        const N4& nq = normals[q];
+        if (!std::isfinite(nq.nx)) continue;
+        const float nv[3] = {nq.nx, nq.ny, nq.nz};
+        float nnT[9];
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c) nnT[r * 3 + c] = nv[r] * nv[c];
+        for (int k = 0; k < 9; ++k) NNT[k] += nnT[k];
+        const float pv[3] = {input[q].x, input[q].y, input[q].z};
+        for (int r = 0; r < 3; ++r) NNTp[r] += (nnT[r * 3 + 0] * pv[0] + nnT[r * 3 + 1] * pv[1]) + nnT[r * 3 + 2] * pv[2];
+      }
+      // invert3x3SymMatrix (column-major coeff(i) of a symmetric matrix == row-major)
+      const float fd_ee = NNT[4] * NNT[8] - NNT[7] * NNT[5];
+      const float ce_bf = NNT[2] * NNT[5] - NNT[1] * NNT[8];
+      const float be_cd = NNT[1] * NNT[5] - NNT[2] * NNT[4];
+      const float det = NNT[0] * fd_ee + NNT[1] * ce_bf + NNT[2] * be_cd;
+      if (det != 0) {
+        float inv[9];
+        inv[0] = fd_ee;
+        inv[1] = inv[3] = ce_bf;
+        inv[2] = inv[6] = be_cd;
+        inv[4] = (NNT[0] * NNT[8] - NNT[2] * NNT[2]);
+        inv[5] = inv[7] = (NNT[1] * NNT[2] - NNT[0] * NNT[5]);
+        inv[8] = (NNT[0] * NNT[4] - NNT[1] * NNT[1]);
+        for (int k = 0; k < 9; ++k) inv[k] /= det;
+        corner_out.x = (inv[0] * NNTp[0] + inv[1] * NNTp[1]) + inv[2] * NNTp[2];
+        corner_out.y = (inv[3] * NNTp[0] + inv[4] * NNTp[1]) + inv[5] * NNTp[2];
+        corner_out.z = (inv[6] * NNTp[0] + inv[7] * NNTp[1]) + inv[8] * NNTp[2];
+      }
+      const float dx = corner_out.x - cx, dy = corner_out.y - cy, dz = corner_out.z - cz;
+      diff = (dx * dx + dy * dy) + dz * dz;
+    } while (diff > 1e-6 && ++iterations < 10);
+  }
+  return corners;
+}
+
+// ===========================================================================
 // a8-FPFH  computeLocalDescriptors(FPFH) -> pcl::FPFHEstimation
 // [REF src/features.cpp:99-150, src/dispatch_descriptors.h:40]
 // [PCL-recall pcl/features/impl/fpfh.hpp, pcl/features/impl/pfh.hpp computePairFeatures]
@@ -812,6 +914,299 @@ static std::vector<float> fpfh_descriptors(const Cloud& surface, const Normals& 
     if (!finite) continue;  // DefaultPointRepresentation::isValid
     desc.insert(desc.end(), f, f + 33);
     kept.push_back(keypoints[k]);
+  }
+  keypoints.swap(kept);
+  return desc;
+}
+
+// ===========================================================================
+// a8-SHOT  computeLocalDescriptors(SHOT) -> pcl::SHOTColorEstimation<PointXYZRGB, Normal, SHOT1344>
+// [REF src/dispatch_descriptors.h:46, src/features.cpp:99-150]
+// [PCL-recall pcl/features/impl/shot.hpp (computeFeature, computePointSHOT, createBinDistanceShape,
+//  interpolateDoubleChannel, normalizeHistogram, RGB2CIELAB), pcl/features/impl/shot_lrf.hpp (getLocalRF)]
+// 32 spatial sectors x (10+1 shape bins, 30+1 colour bins) = 1344.  The keypoint cloud is what the reference
+// passes as input_: after copyPointCloud its colour is the default (0,0,0), so the colour reference is black.
+// ===========================================================================
+static const double PST_PI = 3.1415926535897932384626433832795;
+static const double PST_RAD_45 = 0.78539816339744830961566084581988;
+static const double PST_RAD_90 = 1.5707963267948966192313216916398;
+static const double PST_RAD_135 = 2.3561944901923449288469825374596;
+static const double PST_RAD_PI_7_8 = 2.7488935718910690836548129603691;
+
+struct LabLut {
+  float srgb[256];
+  float xyz[4000];
+  LabLut()
+  {
+    for (int i = 0; i < 256; i++) {
+      const float f = (float)i / 255.0f;
+      if (f > 0.04045) srgb[i] = powf((f + 0.055f) / 1.055f, 2.4f);
+      else srgb[i] = f / 12.92f;
+    }
+    for (int i = 0; i < 4000; i++) {
+      const float f = (float)i / 4000.0f;
+      if (f > 0.008856) xyz[i] = (float)powf(f, 0.3333f);
+      else xyz[i] = (float)((7.787 * f) + (16.0 / 116.0));
+    }
+  }
+};
+static const LabLut& lab_lut()
+{
+  static LabLut l;
+  return l;
+}
+
+static void rgb2cielab(unsigned char R, unsigned char G, unsigned char B, float& L, float& A, float& B2)
+{
+  const LabLut& lut = lab_lut();
+  const float fr = lut.srgb[R], fg = lut.srgb[G], fb = lut.srgb[B];
+  const float x = fr * 0.412453f + fg * 0.357580f + fb * 0.180423f;
+  const float y = fr * 0.212671f + fg * 0.715160f + fb * 0.072169f;
+  const float z = fr * 0.019334f + fg * 0.119193f + fb * 0.950227f;
+  float vx = x / 0.95047f;
+  float vy = y;
+  float vz = z / 1.08883f;
+  vx = lut.xyz[int(vx * 4000)];
+  vy = lut.xyz[int(vy * 4000)];
+  vz = lut.xyz[int(vz * 4000)];
+  L = 116.0f * vy - 16.0f;
+  if (L > 100) L = 100.0f;
+  A = 500.0f * (vx - vy);
+  if (A > 120) A = 120.0f;
+  else if (A < -120) A = -120.0f;
+  B2 = 200.0f * (vy - vz);
+  if (B2 > 120) B2 = 120.0f;
+  else if (B2 < -120) B2 = -120.0f;
+}
+
+// SHOTLocalReferenceFrameEstimation::getLocalRF; rf row-major (x axis, y axis, z axis); false = NaN frame
+static bool shot_lrf(const Cloud& surface, const P4& center, double radius, const std::vector<int>& idx, const std::vector<float>& sqd, float* rf)
+{
+  std::vector<double> vij;
+  vij.reserve(idx.size() * 3);
+  double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double sum = 0.0;
+  int valid = 0;
+  for (size_t i = 0; i < idx.size(); ++i) {
+    const P4& pt = surface[idx[i]];
+    if (pt.x == center.x && pt.y == center.y && pt.z == center.z) continue;
+    const double v[3] = {(double)(pt.x - center.x), (double)(pt.y - center.y), (double)(pt.z - center.z)};
+    const double distance = radius - std::sqrt((double)sqd[i]);
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) cov[r * 3 + c] += distance * (v[r] * v[c]);
+    sum += distance;
+    vij.push_back(v[0]); vij.push_back(v[1]); vij.push_back(v[2]);
+    ++valid;
+  }
+  if (valid < 5) return false;
+  for (int k = 0; k < 9; ++k) cov[k] /= sum;
+  double val[3], vec[9];
+  em::eig3_sym_d(cov, val, vec);
+  if (!std::isfinite(val[0]) || !std::isfinite(val[1]) || !std::isfinite(val[2])) return false;
+  double v1[3] = {vec[0 * 3 + 2], vec[1 * 3 + 2], vec[2 * 3 + 2]};  // largest eigenvalue
+  double v3[3] = {vec[0 * 3 + 0], vec[1 * 3 + 0], vec[2 * 3 + 0]};  // smallest
+  int plusNormal = 0, plusTangent = 0;
+  for (int ne = 0; ne < valid; ++ne) {
+    const double* r = &vij[ne * 3];
+    if ((r[0] * v1[0] + r[1] * v1[1]) + r[2] * v1[2] >= 0) ++plusTangent;
+    if ((r[0] * v3[0] + r[1] * v3[1]) + r[2] * v3[2] >= 0) ++plusNormal;
+  }
+  plusTangent = 2 * plusTangent - valid;
+  if (plusTangent == 0) {
+    const int points = 5, median = valid / 2;
+    for (int i = -points / 2; i <= points / 2; ++i) {
+      const double* r = &vij[(median - i) * 3];
+      if ((r[0] * v1[0] + r[1] * v1[1]) + r[2] * v1[2] > 0) ++plusTangent;
+    }
+    if (plusTangent < points / 2 + 1) for (double& c : v1) c *= -1;
+  } else if (plusTangent < 0) {
+    for (double& c : v1) c *= -1;
+  }
+  plusNormal = 2 * plusNormal - valid;
+  if (plusNormal == 0) {
+    const int points = 5, median = valid / 2;
+    for (int i = -points / 2; i <= points / 2; ++i) {
+      const double* r = &vij[(median - i) * 3];
+      if ((r[0] * v3[0] + r[1] * v3[1]) + r[2] * v3[2] > 0) ++plusNormal;
+    }
+    if (plusNormal < points / 2 + 1) for (double& c : v3) c *= -1;
+  } else if (plusNormal < 0) {
+    for (double& c : v3) c *= -1;
+  }
+  for (int k = 0; k < 3; ++k) { rf[k] = (float)v1[k]; rf[6 + k] = (float)v3[k]; }
+  // rf.row(1) = rf.row(2).cross(rf.row(0))
+  rf[3] = rf[7] * rf[2] - rf[8] * rf[1];
+  rf[4] = rf[8] * rf[0] - rf[6] * rf[2];
+  rf[5] = rf[6] * rf[1] - rf[7] * rf[0];
+  return true;
+}
+
+static std::vector<float> shot_descriptors(const Cloud& surface, const Normals& normals, Cloud& keypoints, double radius,
+                                           std::vector<float>* rf_dbg = nullptr)
+{
+  const int nr_shape = 10, nr_color = 30, sectors = 32, D = 1344;
+  const int shapeToColorStride = sectors * (nr_shape + 1);
+  Grid tree;
+  tree.build(surface, (float)radius);
+  const double radius3_4 = (radius * 3) / 4, radius1_4 = radius / 4, radius1_2 = radius / 2;
+  std::vector<float> desc;
+  Cloud kept;
+  std::vector<int> idx;
+  std::vector<float> sqd;
+  std::vector<float> shot(D);
+  for (size_t k = 0; k < keypoints.size(); ++k) {
+    const P4& c = keypoints[k];
+    tree.radius_sorted(c.x, c.y, c.z, radius, idx, sqd);
+    float rf[9];
+    if (!shot_lrf(surface, c, radius, idx, sqd, rf)) continue;  // NaN frame -> NaN descriptor -> dropped
+    if (idx.empty() || idx.size() < 5) continue;                // "not sufficient for its description" -> NaN -> dropped
+    for (float& v : shot) v = 0.f;
+    // reference colour = the keypoint's own colour
+    float LRef, aRef, bRef;
+    rgb2cielab((c.rgba >> 16) & 0xff, (c.rgba >> 8) & 0xff, c.rgba & 0xff, LRef, aRef, bRef);
+    LRef /= 100.0f; aRef /= 120.0f; bRef /= 120.0f;
+    for (size_t i = 0; i < idx.size(); ++i) {
+      const N4& nq = normals[idx[i]];
+      // createBinDistanceShape
+      if (!std::isfinite(nq.nx) || !std::isfinite(nq.ny) || !std::isfinite(nq.nz)) continue;
+      double cosineDesc = (double)(((nq.nx * rf[6] + nq.ny * rf[7]) + nq.nz * rf[8]) + 0.0f);
+      if (cosineDesc > 1.0) cosineDesc = 1.0;
+      if (cosineDesc < -1.0) cosineDesc = -1.0;
+      double binDistanceShape = ((1.0 + cosineDesc) * nr_shape) / 2;
+      // colour
+      const P4& sp = surface[idx[i]];
+      float L, a, b;
+      rgb2cielab((sp.rgba >> 16) & 0xff, (sp.rgba >> 8) & 0xff, sp.rgba & 0xff, L, a, b);
+      L /= 100.0f; a /= 120.0f; b /= 120.0f;
+      double colorDistance = (std::fabs(LRef - L) + ((std::fabs(aRef - a) + std::fabs(bRef - b)) / 2)) / 3;
+      if (colorDistance > 1.0) colorDistance = 1.0;
+      if (colorDistance < 0.0) colorDistance = 0.0;
+      double binDistanceColor = colorDistance * nr_color;
+      // interpolateDoubleChannel
+      const float dl[3] = {sp.x - c.x, sp.y - c.y, sp.z - c.z};
+      const double distance = std::sqrt((double)sqd[i]);
+      if (std::fabs(distance - 0.0) < 1E-15) continue;
+      double xInFeatRef = (double)((dl[0] * rf[0] + dl[1] * rf[1]) + dl[2] * rf[2]);
+      double yInFeatRef = (double)((dl[0] * rf[3] + dl[1] * rf[4]) + dl[2] * rf[5]);
+      double zInFeatRef = (double)((dl[0] * rf[6] + dl[1] * rf[7]) + dl[2] * rf[8]);
+      if (std::fabs(yInFeatRef) < 1E-30) yInFeatRef = 0;
+      if (std::fabs(xInFeatRef) < 1E-30) xInFeatRef = 0;
+      if (std::fabs(zInFeatRef) < 1E-30) zInFeatRef = 0;
+      const unsigned char bit4 = ((yInFeatRef > 0) || ((yInFeatRef == 0.0) && (xInFeatRef < 0))) ? 1 : 0;
+      const unsigned char bit3 = (unsigned char)(((xInFeatRef > 0) || ((xInFeatRef == 0.0) && (yInFeatRef > 0))) ? !bit4 : bit4);
+      int desc_index = (bit4 << 3) + (bit3 << 2);
+      desc_index = desc_index << 1;
+      if ((xInFeatRef * yInFeatRef > 0) || (xInFeatRef == 0.0)) desc_index += (std::fabs(xInFeatRef) >= std::fabs(yInFeatRef)) ? 0 : 4;
+      else desc_index += (std::fabs(xInFeatRef) > std::fabs(yInFeatRef)) ? 4 : 0;
+      desc_index += zInFeatRef > 0 ? 1 : 0;
+      desc_index += (distance > radius1_2) ? 2 : 0;
+      const int step_index_shape = (int)std::floor(binDistanceShape + 0.5);
+      const int step_index_color = (int)std::floor(binDistanceColor + 0.5);
+      const int volume_index_shape = desc_index * (nr_shape + 1);
+      const int volume_index_color = shapeToColorStride + desc_index * (nr_color + 1);
+      binDistanceShape -= step_index_shape;
+      binDistanceColor -= step_index_color;
+      double intWeightShape = (1 - std::fabs(binDistanceShape));
+      double intWeightColor = (1 - std::fabs(binDistanceColor));
+      if (binDistanceShape > 0) shot[volume_index_shape + ((step_index_shape + 1) % nr_shape)] += (float)binDistanceShape;
+      else shot[volume_index_shape + ((step_index_shape - 1 + nr_shape) % nr_shape)] -= (float)binDistanceShape;
+      if (binDistanceColor > 0) shot[volume_index_color + ((step_index_color + 1) % nr_color)] += (float)binDistanceColor;
+      else shot[volume_index_color + ((step_index_color - 1 + nr_color) % nr_color)] -= (float)binDistanceColor;
+      if (distance > radius1_2) {
+        const double radiusDistance = (distance - radius3_4) / radius1_2;
+        if (distance > radius3_4) {
+          intWeightShape += 1 - radiusDistance;
+          intWeightColor += 1 - radiusDistance;
+        } else {
+          intWeightShape += 1 + radiusDistance;
+          intWeightColor += 1 + radiusDistance;
+          shot[(desc_index - 2) * (nr_shape + 1) + step_index_shape] -= (float)radiusDistance;
+          shot[shapeToColorStride + (desc_index - 2) * (nr_color + 1) + step_index_color] -= (float)radiusDistance;
+        }
+      } else {
+        const double radiusDistance = (distance - radius1_4) / radius1_2;
+        if (distance < radius1_4) {
+          intWeightShape += 1 + radiusDistance;
+          intWeightColor += 1 + radiusDistance;
+        } else {
+          intWeightShape += 1 - radiusDistance;
+          intWeightColor += 1 - radiusDistance;
+          shot[(desc_index + 2) * (nr_shape + 1) + step_index_shape] += (float)radiusDistance;
+          shot[shapeToColorStride + (desc_index + 2) * (nr_color + 1) + step_index_color] += (float)radiusDistance;
+        }
+      }
+      double inclinationCosine = zInFeatRef / distance;
+      if (inclinationCosine < -1.0) inclinationCosine = -1.0;
+      if (inclinationCosine > 1.0) inclinationCosine = 1.0;
+#ifdef ORACLE_LIBM
+      const double inclination = std::acos(inclinationCosine);
+#else
+      const double inclination = em::acos_d_(inclinationCosine);
+#endif
+      if (inclination > PST_RAD_90 || (std::fabs(inclination - PST_RAD_90) < 1e-30 && zInFeatRef <= 0)) {
+        const double inclinationDistance = (inclination - PST_RAD_135) / PST_RAD_90;
+        if (inclination > PST_RAD_135) {
+          intWeightShape += 1 - inclinationDistance;
+          intWeightColor += 1 - inclinationDistance;
+        } else {
+          intWeightShape += 1 + inclinationDistance;
+          intWeightColor += 1 + inclinationDistance;
+          shot[(desc_index + 1) * (nr_shape + 1) + step_index_shape] -= (float)inclinationDistance;
+          shot[shapeToColorStride + (desc_index + 1) * (nr_color + 1) + step_index_color] -= (float)inclinationDistance;
+        }
+      } else {
+        const double inclinationDistance = (inclination - PST_RAD_45) / PST_RAD_90;
+        if (inclination < PST_RAD_45) {
+          intWeightShape += 1 + inclinationDistance;
+          intWeightColor += 1 + inclinationDistance;
+        } else {
+          intWeightShape += 1 - inclinationDistance;
+          intWeightColor += 1 - inclinationDistance;
+          shot[(desc_index - 1) * (nr_shape + 1) + step_index_shape] += (float)inclinationDistance;
+          shot[shapeToColorStride + (desc_index - 1) * (nr_color + 1) + step_index_color] += (float)inclinationDistance;
+        }
+      }
+      if (yInFeatRef != 0.0 || xInFeatRef != 0.0) {
+#ifdef ORACLE_LIBM
+        const double azimuth = std::atan2(yInFeatRef, xInFeatRef);
+#else
+        const double azimuth = em::atan2_d_(yInFeatRef, xInFeatRef);
+#endif
+        const int sel = desc_index >> 2;
+        const double angularSectorSpan = PST_RAD_45;
+        const double angularSectorStart = -PST_RAD_PI_7_8;
+        double azimuthDistance = (azimuth - (angularSectorStart + angularSectorSpan * sel)) / angularSectorSpan;
+        azimuthDistance = std::max(-0.5, std::min(azimuthDistance, 0.5));
+        if (azimuthDistance > 0) {
+          intWeightShape += 1 - azimuthDistance;
+          intWeightColor += 1 - azimuthDistance;
+          const int interp_index = (desc_index + 4) % sectors;
+          shot[interp_index * (nr_shape + 1) + step_index_shape] += (float)azimuthDistance;
+          shot[shapeToColorStride + interp_index * (nr_color + 1) + step_index_color] += (float)azimuthDistance;
+        } else {
+          const int interp_index = (desc_index - 4 + sectors) % sectors;
+          intWeightShape += 1 + azimuthDistance;
+          intWeightColor += 1 + azimuthDistance;
+          shot[interp_index * (nr_shape + 1) + step_index_shape] -= (float)azimuthDistance;
+          shot[shapeToColorStride + interp_index * (nr_color + 1) + step_index_color] -= (float)azimuthDistance;
+        }
+      }
+      shot[volume_index_shape + step_index_shape] += (float)intWeightShape;
+      shot[volume_index_color + step_index_color] += (float)intWeightColor;
+    }
+    // normalizeHistogram
+    double acc_norm = 0.0;
+    for (int j = 0; j < D; ++j) acc_norm += shot[j] * shot[j];
+    acc_norm = std::sqrt(acc_norm);
+    bool finite = true;
+    for (int j = 0; j < D; ++j) {
+      shot[j] /= (float)acc_norm;
+      if (!std::isfinite(shot[j])) finite = false;
+    }
+    if (!finite) continue;
+    desc.insert(desc.end(), shot.begin(), shot.end());
+    kept.push_back(c);
+    if (rf_dbg) rf_dbg->insert(rf_dbg->end(), rf, rf + 9);
   }
   keypoints.swap(kept);
   return desc;
@@ -1381,6 +1776,7 @@ struct MapFeatures {
   Normals normals;
   Cloud keypoints;
   std::vector<float> desc;
+  int dim = 33;
 };
 
 static void map_features(const Cloud& in, const Params& p, MapFeatures& f, StageTimes* st)
@@ -1392,10 +1788,14 @@ static void map_features(const Cloud& in, const Params& p, MapFeatures& f, Stage
   double t2 = now_s();
   f.normals = surface_normals(f.cloud, p.normal_radius);
   double t3 = now_s();
-  // Keypoint::SIFT only (HARRIS is a later row of SURVEY §8)
-  f.keypoints = sift_keypoints(f.cloud, (float)p.resolution, 3, 3, (float)p.keypoint_threshold, 0);
+  if (p.keypoint_type == 1)  // Keypoint::HARRIS: radius = normal_radius (map_merging.cpp:233)
+    f.keypoints = harris_keypoints(f.cloud, f.normals, (float)p.keypoint_threshold, (float)p.normal_radius);
+  else
+    f.keypoints = sift_keypoints(f.cloud, (float)p.resolution, 3, 3, (float)p.keypoint_threshold, 0);
   double t4 = now_s();
-  f.desc = fpfh_descriptors(f.cloud, f.normals, f.keypoints, p.descriptor_radius);
+  if (p.descriptor_type == 4) f.desc = shot_descriptors(f.cloud, f.normals, f.keypoints, p.descriptor_radius);
+  else f.desc = fpfh_descriptors(f.cloud, f.normals, f.keypoints, p.descriptor_radius);
+  f.dim = p.descriptor_type == 4 ? 1344 : 33;
   double t5 = now_s();
   if (st) {
     st->t[0] += t1 - t0; st->t[1] += t2 - t1; st->t[2] += t3 - t2; st->t[3] += t4 - t3; st->t[4] += t5 - t4;
@@ -1407,7 +1807,7 @@ static PairResult register_pair(const MapFeatures& a, const MapFeatures& b, int 
   PairResult r;
   r.i = i; r.j = j;
   double t0 = now_s();
-  std::vector<Corr> corr = find_correspondences(a.desc.data(), a.keypoints.size(), b.desc.data(), b.keypoints.size(), 33, p.matching_k);
+  std::vector<Corr> corr = find_correspondences(a.desc.data(), a.keypoints.size(), b.desc.data(), b.keypoints.size(), a.dim, p.matching_k);
   double t1 = now_s();
   std::vector<int> inl;
   Mat4 t = ransac_transform(a.keypoints, b.keypoints, corr, p.inlier_threshold, inl);
@@ -1516,6 +1916,21 @@ int orc_sift(const float* pts, uint64_t n, double min_scale, int n_octaves, int 
   return 0;
 }
 
+int orc_harris(const float* pts, uint64_t n, const float* normals, double threshold, double radius, float** kp, uint64_t* nk, float** response,
+               float** unrefined, uint64_t* n_unrefined)
+{
+  Normals nm(n);
+  if (n) memcpy(nm.data(), normals, n * sizeof(N4));
+  std::vector<float> resp;
+  Cloud unref;
+  Cloud o = harris_keypoints(to_cloud(pts, n), nm, (float)threshold, (float)radius, response ? &resp : nullptr, unrefined ? &unref : nullptr);
+  *kp = dup_f(o.data(), o.size() * sizeof(P4));
+  *nk = o.size();
+  if (response) *response = dup_f(resp.data(), resp.size() * 4);
+  if (unrefined) { *unrefined = dup_f(unref.data(), unref.size() * sizeof(P4)); *n_unrefined = unref.size(); }
+  return 0;
+}
+
 int orc_fpfh(const float* pts, uint64_t n, const float* normals, const float* kp_in, uint64_t nk_in, double radius, float** kp_out,
              uint64_t* nk_out, float** desc, float** spfh)
 {
@@ -1529,6 +1944,22 @@ int orc_fpfh(const float* pts, uint64_t n, const float* normals, const float* kp
   *nk_out = kp.size();
   *desc = dup_f(d.data(), d.size() * 4);
   if (spfh) *spfh = dup_f(sp.data(), sp.size() * 4);
+  return 0;
+}
+
+int orc_shot(const float* pts, uint64_t n, const float* normals, const float* kp_in, uint64_t nk_in, double radius, float** kp_out,
+             uint64_t* nk_out, float** desc, float** rf)
+{
+  Cloud surf = to_cloud(pts, n);
+  Normals nm(n);
+  if (n) memcpy(nm.data(), normals, n * sizeof(N4));
+  Cloud kp = to_cloud(kp_in, nk_in);
+  std::vector<float> rfv;
+  std::vector<float> d = shot_descriptors(surf, nm, kp, radius, rf ? &rfv : nullptr);
+  *kp_out = dup_f(kp.data(), kp.size() * sizeof(P4));
+  *nk_out = kp.size();
+  *desc = dup_f(d.data(), d.size() * 4);
+  if (rf) *rf = dup_f(rfv.data(), rfv.size() * 4);
   return 0;
 }
 

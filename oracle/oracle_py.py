@@ -120,6 +120,16 @@ class Oracle:
         s = _take(sc, nk.value, np.float32); self._free(sc)
         return (r, d, s) if debug else r
 
+    def harris(self, pts, normals, threshold, radius, debug=False):
+        a, ap = _f(pts); nm, nmp = _f(normals)
+        kp = f32p(); nk = C.c_uint64(); resp = f32p(); un = f32p(); nun = C.c_uint64()
+        self.lib.orc_harris(ap, C.c_uint64(len(a)), nmp, C.c_double(threshold), C.c_double(radius), C.byref(kp), C.byref(nk), C.byref(resp),
+                            C.byref(un), C.byref(nun))
+        r = _take(kp, nk.value * 4, np.float32, (-1, 4)); self._free(kp)
+        rs = _take(resp, len(a), np.float32); self._free(resp)
+        u = _take(un, nun.value * 4, np.float32, (-1, 4)); self._free(un)
+        return (r, rs, u) if debug else r
+
     def fpfh(self, pts, normals, kp, radius, debug=False):
         a, ap = _f(pts); nm, nmp = _f(normals); k, kpp = _f(kp)
         ko = f32p(); nko = C.c_uint64(); desc = f32p(); spfh = f32p()
@@ -131,6 +141,16 @@ class Oracle:
             s = _take(spfh, len(a) * 33, np.float32, (-1, 33)); self._free(spfh)
             return kout, d, s
         return kout, d
+
+    def shot(self, pts, normals, kp, radius, debug=False):
+        a, ap = _f(pts); nm, nmp = _f(normals); k, kpp = _f(kp)
+        ko = f32p(); nko = C.c_uint64(); desc = f32p(); rf = f32p()
+        self.lib.orc_shot(ap, C.c_uint64(len(a)), nmp, kpp, C.c_uint64(len(k)), C.c_double(radius), C.byref(ko), C.byref(nko),
+                          C.byref(desc), C.byref(rf))
+        kout = _take(ko, nko.value * 4, np.float32, (-1, 4)); self._free(ko)
+        d = _take(desc, nko.value * 1344, np.float32, (-1, 1344)); self._free(desc)
+        r = _take(rf, nko.value * 9, np.float32, (-1, 9)); self._free(rf)
+        return (kout, d, r) if debug else (kout, d)
 
     def match(self, ds, dt, k=5):
         a, ap = _f(ds); b, bp = _f(dt)

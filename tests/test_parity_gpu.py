@@ -120,6 +120,31 @@ def test_sift_bit_exact(ctx, tiny_stages):
         assert len(kp) > 50
 
 
+# ---------------------------------------------------------------- K6 Harris3D
+def test_harris_bit_exact(ctx, oracle, tiny_stages):
+    for st in tiny_stages:
+        for thr in (0.0, 0.01):
+            wk, wresp, wun = oracle.harris(st["filtered"], st["normals"], thr, 0.6, debug=True)
+            gk, gresp = ctx.keypoints(st["filtered"], normals=st["normals"], type="HARRIS", threshold=thr, radius=0.6, resolution=0.1, debug=True)
+            assert_same_bits(gresp, wresp, "Harris response")
+            assert_same_bits(gk, wk, f"refined Harris corners (threshold {thr})")
+            assert len(wk) >= 5
+
+
+def test_harris_pipeline_matches_oracle(ctx, mm, oracle, small_maps):
+    """Keypoint::HARRIS through the whole path (BASELINE config 4 uses it with SHOT; here with FPFH)."""
+    import oracle_py
+    maps, truth = small_maps
+    want = oracle.estimate_maps_transforms(maps, oracle_py.default_params(descriptor_type=2, keypoint_type=1, keypoint_threshold=0.0))
+    dm = ctx.maps_upload(maps)
+    p = mm.default_params(descriptor_type="FPFH", keypoint_type="HARRIS", keypoint_threshold=0.0)
+    f = ctx.features_compute(dm, 0, len(maps), p)
+    T, conf, stats = ctx.register_pairs(f, want["pairs"][:, :2], p)
+    np.testing.assert_array_equal(stats[:, :2], want["pairs"][:, 2:4])
+    np.testing.assert_array_equal(T, want["pair_T"])
+    np.testing.assert_array_equal(conf, want["pair_conf"])
+
+
 # ---------------------------------------------------------------- K7 FPFH
 def test_fpfh_bit_exact(ctx, tiny_stages):
     for st in tiny_stages:
