@@ -207,7 +207,9 @@ class Context:
                                             C.byref(sp) if debug else None))
         kout = self._take(ko, nko.value * 4, np.float32, (-1, 4))
         d = self._take(desc, nko.value * dim.value, np.float32, (-1, dim.value))
-        if debug:
+        if debug:  # FPFH: SPFH signatures (n x 33); SHOT: local reference frames (K' x 9)
+            if type == "SHOT":
+                return kout, d, self._take(sp, nko.value * 9, np.float32, (-1, 9))
             return kout, d, self._take(sp, len(a) * 33, np.float32, (-1, 33))
         return kout, d
 

@@ -102,7 +102,8 @@ double auto_leaf(double index_leaf, double radius, double ratio)
 void check_supported(const mm3d_params& p)
 {
   if (p.keypoint_type != MM3D_KP_SIFT && p.keypoint_type != MM3D_KP_HARRIS) throw std::runtime_error("unsupported: unknown keypoint_type");
-  if (p.descriptor_type != MM3D_DESC_FPFH) throw std::runtime_error("unsupported: only descriptor_type FPFH is built in this round");
+  if (p.descriptor_type != MM3D_DESC_FPFH && p.descriptor_type != MM3D_DESC_SHOT && p.descriptor_type != MM3D_DESC_PFH)
+    throw std::runtime_error("unsupported: descriptor_type PFHRGB / RSD / SC3D are not built yet (SURVEY.md 8f rank 3)");
   if (p.estimation_method != MM3D_EST_MATCHING) throw std::runtime_error("unsupported: estimation_method SAC_IA is not built yet (SURVEY.md 8f)");
 }
 
@@ -153,7 +154,9 @@ void compute_features(Ctx& c, const std::vector<CloudView>& raw, const mm3d_para
 
   tm.begin();
   std::vector<DBuf<float>> desc;
-  fpfh_batch(c, fv, idx, np, kps, p.descriptor_radius, desc, nullptr);
+  if (p.descriptor_type == MM3D_DESC_SHOT) shot_batch(c, fv, idx, np, kps, p.descriptor_radius, desc, nullptr);
+  else if (p.descriptor_type == MM3D_DESC_PFH) pfh_batch(c, fv, idx, np, kps, p.descriptor_radius, desc);
+  else fpfh_batch(c, fv, idx, np, kps, p.descriptor_radius, desc, nullptr);
   tm.end(4);
 
   for (int m = 0; m < M; ++m) {
@@ -238,6 +241,11 @@ void register_pairs(Ctx& c, const std::vector<MapFeat>& f, int dim, const std::v
 }
 
 // returns number of transforms written
+int desc_dim(const mm3d_params& p)
+{
+  return p.descriptor_type == MM3D_DESC_SHOT ? 1344 : (p.descriptor_type == MM3D_DESC_PFH ? 125 : 33);
+}
+
 int estimate_from_views(Ctx& c, const std::vector<CloudView>& raw, const mm3d_params& p, float* out_transforms, float* stage_ms)
 {
   const int M = (int)raw.size();
@@ -254,7 +262,7 @@ int estimate_from_views(Ctx& c, const std::vector<CloudView>& raw, const mm3d_pa
     for (int j = i + 1; j < M; ++j)
       if (f[i].keypoints.n > 0 && f[j].keypoints.n > 0) jobs.push_back(PairJob{i, j});
   std::vector<PairOut> po;
-  register_pairs(c, f, 33, jobs, p, po, stage_ms);
+  register_pairs(c, f, desc_dim(p), jobs, p, po, stage_ms);
   std::vector<HostEstimate> est(jobs.size());
   for (size_t k = 0; k < jobs.size(); ++k) {
     est[k].source_idx = (size_t)jobs[k].a;
@@ -510,7 +518,8 @@ int mm3d_descriptors(mm3d_ctx* ctx, const float* pts, uint64_t n, const float* n
 {
   if (!keypoints_out || !n_out || !descriptors) return MM3D_ERR_ARG;
   MM_TRY(ctx)
-  if (type != MM3D_DESC_FPFH) throw std::runtime_error("unsupported: only descriptor_type FPFH is built in this round");
+  if (type != MM3D_DESC_FPFH && type != MM3D_DESC_SHOT && type != MM3D_DESC_PFH)
+    throw std::runtime_error("unsupported: descriptor_type PFHRGB / RSD / SC3D are not built yet (SURVEY.md 8f rank 3)");
   DCloud d = upload_cloud(c, pts, n);
   DBuf<float4> nm(c, d.n);
   if (d.n) MM_CUDA(cudaMemcpyAsync(nm.p, normals, (size_t)d.n * sizeof(float4), cudaMemcpyHostToDevice, c.stream));
@@ -519,11 +528,16 @@ int mm3d_descriptors(mm3d_ctx* ctx, const float* pts, uint64_t n, const float* n
   std::vector<DIndex> idx;
   build_index_batch(c, {d.view()}, (float)auto_leaf(index_leaf, radius, 8.0), 2, 0, 0, idx);
   std::vector<DBuf<float>> desc, sp;
-  fpfh_batch(c, {d.view()}, idx, {nm.p}, kp, radius, desc, spfh ? &sp : nullptr);
+  const int D = type == MM3D_DESC_SHOT ? 1344 : (type == MM3D_DESC_PFH ? 125 : 33);
+  if (type == MM3D_DESC_PFH) {
+    pfh_batch(c, {d.view()}, idx, {nm.p}, kp, radius, desc);
+    if (spfh) { sp.resize(1); }
+  } else if (type == MM3D_DESC_SHOT) shot_batch(c, {d.view()}, idx, {nm.p}, kp, radius, desc, spfh ? &sp : nullptr);  // spfh <- reference frames (K' x 9)
+  else fpfh_batch(c, {d.view()}, idx, {nm.p}, kp, radius, desc, spfh ? &sp : nullptr);
   *keypoints_out = (float*)host_copy(c, kp[0].pts.p, (size_t)kp[0].n);
   *n_out = (uint64_t)kp[0].n;
-  *descriptors = host_copy(c, desc[0].p, (size_t)kp[0].n * 33);
-  if (dim) *dim = 33;
+  *descriptors = host_copy(c, desc[0].p, (size_t)kp[0].n * D);
+  if (dim) *dim = D;
   if (spfh) *spfh = host_copy(c, sp[0].p, sp[0].n);
   c.sync();
   MM_CATCH
@@ -722,6 +736,7 @@ int mm3d_features_compute(mm3d_ctx* ctx, const mm3d_maps* maps, int first, int c
   for (int m = 0; m < count; ++m) v[m] = maps->clouds[first + m].view();
   std::unique_ptr<mm3d_features> f(new mm3d_features);
   compute_features(c, v, *params, f->maps, nullptr);
+  f->dim = desc_dim(*params);
   *out = f.release();
   MM_CATCH
 }

@@ -10,6 +10,7 @@
 #include <limits>
 
 #include "mm3d_internal.cuh"
+#include "pair_features.cuh"
 
 namespace mm3d {
 
@@ -50,10 +51,11 @@ __global__ void __launch_bounds__(FB) outlier_kernel(const OutlierJob* __restric
 {
   const OutlierJob& j = jobs[blockIdx.y];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= j.g.n) return;
-  const float4 q = j.g.pts[k];
+  const bool live = k < j.g.n;
+  const float4 q = live ? j.g.pts[k] : make_float4(0.f, 0.f, 0.f, 0.f);
   int cnt = 0;
-  for_each_in_radius(j.g, q.x, q.y, q.z, r2, rv, [&](int, const float4&, float) { ++cnt; });
+  for_each_in_radius(j.g, live, q.x, q.y, q.z, r2, rv, [&](int, const float4&, float) { ++cnt; });
+  if (!live) return;
   const int oi = j.g.orig ? j.g.orig[k] : k;
   j.flags[oi] = cnt > min_nb ? 1u : 0u;  // "k <= min_pts_radius_" is an outlier
   if (j.counts) j.counts[oi] = cnt;
@@ -84,17 +86,18 @@ __global__ void __launch_bounds__(FB) normals_kernel(const NormalJob* __restrict
 {
   const NormalJob& j = jobs[blockIdx.y];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= j.g.n) return;
-  const float4 q = j.g.pts[k];
+  const bool live = k < j.g.n;
+  const float4 q = live ? j.g.pts[k] : make_float4(0.f, 0.f, 0.f, 0.f);
   // pcl::computeMeanAndCovarianceMatrix, single pass, float accumulators
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f, a8 = 0.f;
   int cnt = 0;
-  for_each_in_radius(j.g, q.x, q.y, q.z, r2, rv, [&](int, const float4& p, float) {
+  for_each_in_radius(j.g, live, q.x, q.y, q.z, r2, rv, [&](int, const float4& p, float) {
     a0 += p.x * p.x; a1 += p.x * p.y; a2 += p.x * p.z;
     a3 += p.y * p.y; a4 += p.y * p.z; a5 += p.z * p.z;
     a6 += p.x; a7 += p.y; a8 += p.z;
     ++cnt;
   });
+  if (!live) return;
   const int oi = j.g.orig ? j.g.orig[k] : k;
   if (cnt < 3) {
     const float nanv = __int_as_float(0x7fc00000);
@@ -143,12 +146,12 @@ __global__ void __launch_bounds__(FB) sift_scale_space_kernel(const SiftJob* __r
 {
   const SiftJob& j = jobs[blockIdx.y];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= j.g.n) return;
-  const float4 q = j.g.pts[k];
+  const bool live = k < j.g.n;
+  const float4 q = live ? j.g.pts[k] : make_float4(0.f, 0.f, 0.f, 0.f);
   float num[6], den[6];
 #pragma unroll
   for (int s = 0; s < 6; ++s) { num[s] = 0.f; den[s] = 0.f; }
-  for_each_in_radius(j.g, q.x, q.y, q.z, r2, rv, [&](int, const float4& p, float d2) {
+  for_each_in_radius(j.g, live, q.x, q.y, q.z, r2, rv, [&](int, const float4& p, float d2) {
     const float value = sift_intensity(p.w);
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
@@ -160,6 +163,7 @@ __global__ void __launch_bounds__(FB) sift_scale_space_kernel(const SiftJob* __r
       }
     }
   });
+  if (!live) return;
   float prev = 0.f, resp = 0.f;
 #pragma unroll
   for (int s = 0; s < 6; ++s) {
@@ -173,18 +177,20 @@ __global__ void __launch_bounds__(FB) sift_extrema_kernel(const SiftJob* __restr
 {
   const SiftJob& j = jobs[blockIdx.y];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= j.g.n) return;
-  const float4 q = j.g.pts[k];
+  const bool live = k < j.g.n;
+  const float4 q = live ? j.g.pts[k] : make_float4(0.f, 0.f, 0.f, 0.f);
   constexpr int K = 25;
   float bd[K];
   int bi[K];
   int cnt = 0;
   int rv = 3;
   const int rv_max = max(max(j.g.div_v[0], j.g.div_v[1]), j.g.div_v[2]) + 2;
-  for (;;) {
-    cnt = 0;
+  bool searching = live;
+  // every lane keeps calling the (warp-collective) walk until the whole warp is done
+  while (__any_sync(0xffffffffu, searching)) {
+    if (searching) cnt = 0;
     const float rad = (float)rv * j.g.leaf;
-    for_each_in_radius(j.g, q.x, q.y, q.z, rad * rad, rv + 1, [&](int idx, const float4&, float d2) {
+    for_each_in_radius(j.g, searching, q.x, q.y, q.z, rad * rad, rv + 1, [&](int idx, const float4&, float d2) {
       if (cnt == K && !(d2 < bd[K - 1] || (d2 == bd[K - 1] && idx < bi[K - 1]))) return;
       int pos = (cnt < K) ? cnt : K - 1;
       while (pos > 0 && (d2 < bd[pos - 1] || (d2 == bd[pos - 1] && idx < bi[pos - 1]))) {
@@ -196,9 +202,12 @@ __global__ void __launch_bounds__(FB) sift_extrema_kernel(const SiftJob* __restr
       bi[pos] = idx;
       if (cnt < K) ++cnt;
     });
-    if (cnt == K || rv > rv_max) break;
-    rv *= 2;
+    if (searching) {
+      if (cnt == K || rv > rv_max) searching = false;
+      else rv *= 2;
+    }
   }
+  if (!live) return;
   float mn[5], mx[5];
 #pragma unroll
   for (int s = 0; s < 5; ++s) { mn[s] = 3.402823466e+38f; mx[s] = -3.402823466e+38f; }
@@ -256,62 +265,9 @@ __global__ void __launch_bounds__(FB) fpfh_mark_kernel(const FpfhJob* __restrict
 {
   const FpfhJob& j = jobs[blockIdx.y];
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= j.nk) return;
-  const float4 q = j.kp[t];
-  for_each_in_radius(j.g, q.x, q.y, q.z, r2, rv, [&](int k, const float4&, float) { j.need[k] = 1u; });
-}
-
-// pcl::computePairFeatures [PCL-recall pcl/features/impl/pfh.hpp]; the FPFH member ignores its return
-// value, so degenerate pairs still vote with f1 = f2 = f3 = 0.
-__device__ __forceinline__ void pair_features(const float4& p1, const float4& n1, const float4& p2, const float4& n2, float* f1, float* f2,
-                                              float* f3)
-{
-  float dx = p2.x - p1.x, dy = p2.y - p1.y, dz = p2.z - p1.z;
-  const float f4 = sqrtf((dx * dx + dy * dy) + dz * dz);
-  if (f4 == 0.0f) { *f1 = *f2 = *f3 = 0.0f; return; }
-  float ax = n1.x, ay = n1.y, az = n1.z, bx = n2.x, by = n2.y, bz = n2.z;
-  const float angle1 = ((ax * dx + ay * dy) + az * dz) / f4;
-  const float angle2 = ((bx * dx + by * dy) + bz * dz) / f4;
-  const float fa1 = fabsf(angle1), fa2 = fabsf(angle2);
-  // acos(|a1|) > acos(|a2|)  <=>  |a1| < |a2| with both inside [0, 1] (NaN otherwise)
-  if ((fa1 <= 1.0f) && (fa2 <= 1.0f) && (fa1 < fa2)) {
-    float t;
-    t = ax; ax = bx; bx = t;
-    t = ay; ay = by; by = t;
-    t = az; az = bz; bz = t;
-    dx *= -1.f; dy *= -1.f; dz *= -1.f;
-    *f3 = -angle2;
-  } else {
-    *f3 = angle1;
-  }
-  float vx = dy * az - dz * ay, vy = dz * ax - dx * az, vz = dx * ay - dy * ax;
-  const float v_norm = sqrtf((vx * vx + vy * vy) + vz * vz);
-  if (v_norm == 0.0f) { *f1 = *f2 = *f3 = 0.0f; return; }
-  vx /= v_norm; vy /= v_norm; vz /= v_norm;
-  const float wx = ay * vz - az * vy, wy = az * vx - ax * vz, wz = ax * vy - ay * vx;
-  *f2 = (vx * bx + vy * by) + vz * bz;
-  *f1 = em::atan2f_((wx * bx + wy * by) + wz * bz, (ax * bx + ay * by) + az * bz);
-}
-
-__device__ __forceinline__ int clampbin(int h)
-{
-  return h < 0 ? 0 : (h > 10 ? 10 : h);
-}
-
-// FPFH bins are floor(11 * ((f + pi) / 2pi)) resp. floor(11 * ((f + 1) / 2)) evaluated in DOUBLE from a float feature
-// (pcl/features/impl/fpfh.hpp).  Both are monotone in f, so the bin is fully described by 10 float thresholds:
-// thr[b] = smallest float whose double formula reaches bin b.  The host derives the thresholds from the literal double
-// expressions; the kernel only compares floats.
-struct BinTable {
-  float t[3][12];  // t[feature][b], b = 1..10 used; t[.][0] = -inf, t[.][11] = +inf
-};
-
-__device__ __forceinline__ int lookup_bin(const float* thr, float f, float scale, float shift)
-{
-  int g = clampbin((int)((f + shift) * scale));  // float guess, at most one bin off
-  while (g < 10 && f >= thr[g + 1]) ++g;
-  while (g > 0 && f < thr[g]) --g;
-  return g;
+  const bool live = t < j.nk;
+  const float4 q = live ? j.kp[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+  for_each_in_radius(j.g, live, q.x, q.y, q.z, r2, rv, [&](int k, const float4&, float) { j.need[k] = 1u; });
 }
 
 __global__ void __launch_bounds__(FB) spfh_kernel(const FpfhJob* __restrict__ jobs, float r2, int rv, BinTable bins)
@@ -322,25 +278,25 @@ __global__ void __launch_bounds__(FB) spfh_kernel(const FpfhJob* __restrict__ jo
   __syncthreads();
   const FpfhJob& j = jobs[blockIdx.y];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= j.g.n) return;
-  if (!j.need[k]) return;
+  const bool live = k < j.g.n && j.need[k];
   for (int b = 0; b < 33; ++b) cnt[b * FB + threadIdx.x] = 0;
-  const float4 p = j.g.pts[k];
-  const float4 np = j.normals[j.g.orig ? j.g.orig[k] : k];
+  const float4 p = live ? j.g.pts[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 np = live ? j.normals[j.g.orig ? j.g.orig[k] : k] : make_float4(0.f, 0.f, 0.f, 0.f);
   int n = 0;
-  for_each_in_radius(j.g, p.x, p.y, p.z, r2, rv, [&](int q, const float4& pq, float) {
+  for_each_in_radius(j.g, live, p.x, p.y, p.z, r2, rv, [&](int q, const float4& pq, float) {
     ++n;
     if (q == k) return;
     const float4 nq = j.normals[j.g.orig ? j.g.orig[q] : q];
     float f1, f2, f3;
     pair_features(p, np, pq, nq, &f1, &f2, &f3);
-    const int h1 = lookup_bin(thr[0], f1, 11.0f * 0.15915494f, 3.14159274f);
-    const int h2 = lookup_bin(thr[1], f2, 5.5f, 1.0f);
-    const int h3 = lookup_bin(thr[2], f3, 5.5f, 1.0f);
+    const int h1 = lookup_bin(thr[0], 11, f1, 11.0f * 0.15915494f, 3.14159274f);
+    const int h2 = lookup_bin(thr[1], 11, f2, 5.5f, 1.0f);
+    const int h3 = lookup_bin(thr[2], 11, f3, 5.5f, 1.0f);
     cnt[h1 * FB + threadIdx.x]++;
     cnt[(11 + h2) * FB + threadIdx.x]++;
     cnt[(22 + h3) * FB + threadIdx.x]++;
   });
+  if (!live) return;
   // every increment of one histogram is the same float, so a bin's value depends
   // only on its vote count: replay the additions.
   const float hist_incr = 100.0f / (float)(n - 1);
@@ -358,15 +314,15 @@ __global__ void __launch_bounds__(FB) fpfh_weight_kernel(const FpfhJob* __restri
 {
   const FpfhJob& j = jobs[blockIdx.y];
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= j.nk * 3) return;
-  const int kp = t / 3, f = t - kp * 3;
-  const float4 q = j.kp[kp];
+  const bool live = t < j.nk * 3;
+  const int kp = live ? t / 3 : 0, f = live ? t - kp * 3 : 0;
+  const float4 q = live ? j.kp[kp] : make_float4(0.f, 0.f, 0.f, 0.f);
   float acc[11];
 #pragma unroll
   for (int i = 0; i < 11; ++i) acc[i] = 0.f;
   double sum = 0.0;
   int found = 0;
-  for_each_in_radius(j.g, q.x, q.y, q.z, r2, rv, [&](int k, const float4&, float d2) {
+  for_each_in_radius(j.g, live, q.x, q.y, q.z, r2, rv, [&](int k, const float4&, float d2) {
     ++found;
     if (d2 == 0.f) return;
     const float weight = 1.0f / d2;
@@ -378,6 +334,7 @@ __global__ void __launch_bounds__(FB) fpfh_weight_kernel(const FpfhJob* __restri
       acc[i] += val;
     }
   });
+  if (!live) return;
   if (sum != 0.0) sum = 100.0 / sum;
   bool ok = found > 0;
 #pragma unroll
@@ -439,11 +396,11 @@ __global__ void __launch_bounds__(FB) harris_response_kernel(const HarrisJob* __
 {
   const HarrisJob& j = jobs[blockIdx.y];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= j.g.n) return;
-  const float4 q = j.g.pts[k];
+  const bool live = k < j.g.n;
+  const float4 q = live ? j.g.pts[k] : make_float4(0.f, 0.f, 0.f, 0.f);
   float c0 = 0.f, c1 = 0.f, c2 = 0.f, c5 = 0.f, c6 = 0.f, c7 = 0.f;
   unsigned count = 0;
-  for_each_in_radius(j.g, q.x, q.y, q.z, r2, rv, [&](int s, const float4&, float) {
+  for_each_in_radius(j.g, live, q.x, q.y, q.z, r2, rv, [&](int s, const float4&, float) {
     const float4 nq = j.normals[j.g.orig ? j.g.orig[s] : s];
     if (!isfinite(nq.x)) return;
     c0 += nq.x * nq.x; c1 += nq.x * nq.y; c2 += nq.x * nq.z;
@@ -451,6 +408,7 @@ __global__ void __launch_bounds__(FB) harris_response_kernel(const HarrisJob* __
     c7 += nq.z * nq.z;
     ++count;
   });
+  if (!live) return;
   if (count > 0) {
     const float cn = (float)count;
     c0 /= cn; c1 /= cn; c2 /= cn; c5 /= cn; c6 /= cn; c7 /= cn;
@@ -471,18 +429,16 @@ __global__ void __launch_bounds__(FB) harris_nms_kernel(const HarrisJob* __restr
 {
   const HarrisJob& j = jobs[blockIdx.y];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= j.g.n) return;
-  const float resp = j.response[k];
-  uint32_t keep = 0;
-  if (isfinite(resp) && !(resp < threshold)) {
-    const float4 q = j.g.pts[k];
-    bool is_max = true;
-    for_each_in_radius(j.g, q.x, q.y, q.z, r2, rv, [&](int s, const float4&, float) {
-      if (resp < j.response[s]) is_max = false;
-    });
-    keep = is_max ? 1u : 0u;
-  }
-  j.flags[j.g.orig ? j.g.orig[k] : k] = keep;
+  const bool live = k < j.g.n;
+  const float resp = live ? j.response[k] : 0.f;
+  const bool cand = live && isfinite(resp) && !(resp < threshold);
+  const float4 q = cand ? j.g.pts[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+  bool is_max = true;
+  for_each_in_radius(j.g, cand, q.x, q.y, q.z, r2, rv, [&](int s, const float4&, float) {
+    if (resp < j.response[s]) is_max = false;
+  });
+  if (!live) return;
+  j.flags[j.g.orig ? j.g.orig[k] : k] = (cand && is_max) ? 1u : 0u;
 }
 
 struct HarrisEmitJob {
@@ -507,14 +463,15 @@ __global__ void __launch_bounds__(FB) harris_refine_kernel(const HarrisJob* __re
 {
   const HarrisJob& j = jobs[blockIdx.y];
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= j.n_corners) return;
-  float4 corner = j.corners[t];
+  const bool live = t < j.n_corners;
+  float4 corner = live ? j.corners[t] : make_float4(0.f, 0.f, 0.f, 0.f);
   unsigned iterations = 0;
   float diff;
-  do {
+  bool working = live;
+  while (__any_sync(0xffffffffu, working)) {
     float N[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, Np[3] = {0.f, 0.f, 0.f};
     const float cx = corner.x, cy = corner.y, cz = corner.z;
-    for_each_in_radius(j.g, cx, cy, cz, r2, rv, [&](int s, const float4& p, float) {
+    for_each_in_radius(j.g, working, cx, cy, cz, r2, rv, [&](int s, const float4& p, float) {
       const float4 nq = j.normals[j.g.orig ? j.g.orig[s] : s];
       if (!isfinite(nq.x)) return;
       const float nv[3] = {nq.x, nq.y, nq.z};
@@ -528,6 +485,7 @@ __global__ void __launch_bounds__(FB) harris_refine_kernel(const HarrisJob* __re
 #pragma unroll
       for (int r = 0; r < 3; ++r) Np[r] += (nnT[r * 3 + 0] * p.x + nnT[r * 3 + 1] * p.y) + nnT[r * 3 + 2] * p.z;
     });
+    if (!working) continue;
     // pcl::invert3x3SymMatrix
     const float fd_ee = N[4] * N[8] - N[7] * N[5];
     const float ce_bf = N[2] * N[5] - N[1] * N[8];
@@ -549,8 +507,9 @@ __global__ void __launch_bounds__(FB) harris_refine_kernel(const HarrisJob* __re
     }
     const float dx = corner.x - cx, dy = corner.y - cy, dz = corner.z - cz;
     diff = (dx * dx + dy * dy) + dz * dz;
-  } while ((double)diff > 1e-6 && ++iterations < 10);
-  j.corners[t] = corner;
+    if (!((double)diff > 1e-6 && ++iterations < 10)) working = false;
+  }
+  if (live) j.corners[t] = corner;
 }
 
 }  // namespace
@@ -779,42 +738,6 @@ void sift_batch(Ctx& c, const std::vector<CloudView>& clouds, float min_scale, i
   }
 }
 
-static int fpfh_bin_f1(float f)
-{
-  const float d_pi = 1.0f / (2.0f * (float)M_PI);
-  int h = (int)std::floor(11 * (((double)f + M_PI) * (double)d_pi));
-  return h < 0 ? 0 : (h > 10 ? 10 : h);
-}
-static int fpfh_bin_f23(float f)
-{
-  int h = (int)std::floor(11 * (((double)f + 1.0) * 0.5));
-  return h < 0 ? 0 : (h > 10 ? 10 : h);
-}
-static float next_up(float f) { return std::nextafter(f, std::numeric_limits<float>::infinity()); }
-
-static BinTable make_bin_table()
-{
-  BinTable bt;
-  for (int feat = 0; feat < 3; ++feat) {
-    int (*fn)(float) = feat == 0 ? fpfh_bin_f1 : fpfh_bin_f23;
-    bt.t[feat][0] = -std::numeric_limits<float>::infinity();
-    bt.t[feat][11] = std::numeric_limits<float>::infinity();
-    for (int b = 1; b <= 10; ++b) {
-      // smallest float with fn(f) >= b: bisection over the ordered float line in [-8, 8]
-      float lo = -8.0f, hi = 8.0f;  // fn(lo) = 0 < b <= fn(hi) = 10
-      while (next_up(lo) < hi) {
-        const float mid = lo + (hi - lo) * 0.5f;
-        const float m = (mid <= lo) ? next_up(lo) : (mid >= hi ? lo : mid);
-        if (m <= lo || m >= hi) break;
-        if (fn(m) >= b) hi = m;
-        else lo = m;
-      }
-      bt.t[feat][b] = hi;
-    }
-  }
-  return bt;
-}
-
 void fpfh_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<const float4*>& normals,
                 std::vector<DCloud>& keypoints, double radius, std::vector<DBuf<float>>& desc, std::vector<DBuf<float>>* spfh_dbg)
 {
@@ -857,7 +780,7 @@ void fpfh_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<
   const int rv = radius_voxels(radius, idx[0].v.leaf);
   MM_LAUNCH(c, fpfh_mark_kernel, dim3((mxk + FB - 1) / FB, M), FB, 0, dj.p, r2, rv);
   { double b = 0; for (int m = 0; m < M; ++m) b += (32.0 + 132.0 + 4.0) * clouds[m].n; MM_BYTES(c, b); }
-  static const BinTable bins = make_bin_table();
+  static const BinTable bins = make_bin_table(11);
   MM_LAUNCH(c, spfh_kernel, dim3((mx + FB - 1) / FB, M), FB, 0, dj.p, r2, rv, bins);
   { double b = 0; for (int m = 0; m < M; ++m) b += (16.0 + 132.0) * clouds[m].n + (16.0 + 132.0) * nks[m]; MM_BYTES(c, b); }
   MM_LAUNCH(c, fpfh_weight_kernel, dim3((mxk * 3 + FB - 1) / FB, M), FB, 0, dj.p, r2, rv);

@@ -920,6 +920,54 @@ static std::vector<float> fpfh_descriptors(const Cloud& surface, const Normals& 
 }
 
 // ===========================================================================
+// a8-PFH  computeLocalDescriptors(PFH) -> pcl::PFHEstimation<PointXYZRGB, Normal, PFHSignature125>
+// (the DEFAULT descriptor_type, map_merging.h:35) [REF src/dispatch_descriptors.h:38]
+// [PCL-recall pcl/features/impl/pfh.hpp computePointPFHSignature: all pairs (i, j < i) of the neighbourhood,
+//  5 x 5 x 5 bins over (f1, f2, f3), every pair adds 100 / (n (n-1) / 2)]
+// ===========================================================================
+static std::vector<float> pfh_descriptors(const Cloud& surface, const Normals& normals, Cloud& keypoints, double radius)
+{
+  const int nr_split = 5;
+  Grid tree;
+  tree.build(surface, (float)radius);
+  const float d_pi = 1.0f / (2.0f * (float)M_PI);
+  std::vector<int> idx;
+  std::vector<float> sqd;
+  std::vector<float> desc;
+  Cloud kept;
+  for (size_t k = 0; k < keypoints.size(); ++k) {
+    tree.radius_sorted(keypoints[k].x, keypoints[k].y, keypoints[k].z, radius, idx, sqd);
+    if (idx.empty()) continue;  // NaN histogram -> dropped
+    float h[125];
+    for (float& v : h) v = 0.f;
+    const float hist_incr = 100.0f / (float)(idx.size() * (idx.size() - 1) / 2);
+    for (size_t i = 0; i < idx.size(); ++i)
+      for (size_t j = 0; j < i; ++j) {
+        float f1, f2, f3, f4;
+        pair_features(surface[idx[i]], normals[idx[i]], surface[idx[j]], normals[idx[j]], f1, f2, f3, f4);
+        int fi[3];
+        fi[0] = (int)std::floor(nr_split * ((f1 + M_PI) * d_pi));
+        fi[1] = (int)std::floor(nr_split * ((f2 + 1.0) * 0.5));
+        fi[2] = (int)std::floor(nr_split * ((f3 + 1.0) * 0.5));
+        int h_index = 0, h_p = 1;
+        for (int d = 0; d < 3; ++d) {
+          h_index += h_p * clampbin(fi[d], nr_split);
+          h_p *= nr_split;
+        }
+        h[h_index] += hist_incr;
+      }
+    bool finite = true;
+    for (float v : h)
+      if (!std::isfinite(v)) finite = false;
+    if (!finite) continue;
+    desc.insert(desc.end(), h, h + 125);
+    kept.push_back(keypoints[k]);
+  }
+  keypoints.swap(kept);
+  return desc;
+}
+
+// ===========================================================================
 // a8-SHOT  computeLocalDescriptors(SHOT) -> pcl::SHOTColorEstimation<PointXYZRGB, Normal, SHOT1344>
 // [REF src/dispatch_descriptors.h:46, src/features.cpp:99-150]
 // [PCL-recall pcl/features/impl/shot.hpp (computeFeature, computePointSHOT, createBinDistanceShape,
@@ -1794,8 +1842,9 @@ static void map_features(const Cloud& in, const Params& p, MapFeatures& f, Stage
     f.keypoints = sift_keypoints(f.cloud, (float)p.resolution, 3, 3, (float)p.keypoint_threshold, 0);
   double t4 = now_s();
   if (p.descriptor_type == 4) f.desc = shot_descriptors(f.cloud, f.normals, f.keypoints, p.descriptor_radius);
+  else if (p.descriptor_type == 0) f.desc = pfh_descriptors(f.cloud, f.normals, f.keypoints, p.descriptor_radius);
   else f.desc = fpfh_descriptors(f.cloud, f.normals, f.keypoints, p.descriptor_radius);
-  f.dim = p.descriptor_type == 4 ? 1344 : 33;
+  f.dim = p.descriptor_type == 4 ? 1344 : (p.descriptor_type == 0 ? 125 : 33);
   double t5 = now_s();
   if (st) {
     st->t[0] += t1 - t0; st->t[1] += t2 - t1; st->t[2] += t3 - t2; st->t[3] += t4 - t3; st->t[4] += t5 - t4;
@@ -1944,6 +1993,20 @@ int orc_fpfh(const float* pts, uint64_t n, const float* normals, const float* kp
   *nk_out = kp.size();
   *desc = dup_f(d.data(), d.size() * 4);
   if (spfh) *spfh = dup_f(sp.data(), sp.size() * 4);
+  return 0;
+}
+
+int orc_pfh(const float* pts, uint64_t n, const float* normals, const float* kp_in, uint64_t nk_in, double radius, float** kp_out,
+            uint64_t* nk_out, float** desc)
+{
+  Cloud surf = to_cloud(pts, n);
+  Normals nm(n);
+  if (n) memcpy(nm.data(), normals, n * sizeof(N4));
+  Cloud kp = to_cloud(kp_in, nk_in);
+  std::vector<float> d = pfh_descriptors(surf, nm, kp, radius);
+  *kp_out = dup_f(kp.data(), kp.size() * sizeof(P4));
+  *nk_out = kp.size();
+  *desc = dup_f(d.data(), d.size() * 4);
   return 0;
 }
 

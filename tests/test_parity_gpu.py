@@ -165,6 +165,74 @@ def test_fpfh_drops_isolated_keypoints(ctx, oracle, tiny_stages):
     assert_same_bits(gd, wd, "descriptors")
 
 
+# ---------------------------------------------------------------- PFH (default descriptor_type)
+def test_pfh_bit_exact(ctx, mm, oracle, tiny_stages):
+    for st in tiny_stages:
+        kp_in = np.concatenate([st["kp_sift"][:60], np.array([[70, 70, 70, 0]], np.float32)])
+        wk, wd = oracle.pfh(st["filtered"], st["normals"], kp_in, 0.8)
+        gk, gd = ctx.descriptors(st["filtered"], st["normals"], kp_in, type="PFH", radius=0.8, index_leaf=0.1)
+        assert len(wk) == 60
+        assert_same_bits(gk, wk, "kept keypoints")
+        assert_same_bits(gd, wd, "PFH descriptors")
+        np.testing.assert_allclose(gd.sum(1), 100.0, rtol=1e-3)
+    # more neighbours than the shared-memory staging holds -> global path, same result
+    st = tiny_stages[0]
+    wk, wd = oracle.pfh(st["filtered"], st["normals"], st["kp_sift"][:3], 1.5)
+    gk, gd = ctx.descriptors(st["filtered"], st["normals"], st["kp_sift"][:3], type="PFH", radius=1.5, index_leaf=0.1)
+    assert_same_bits(gd, wd, "PFH descriptors (large neighbourhood)")
+
+
+def test_default_params_pipeline_matches_oracle(ctx, mm, oracle, tiny_maps):
+    """MapMergingParams() as shipped: SIFT + PFH + MATCHING + ICP (map_merging.h:29-44)."""
+    import oracle_py
+    maps, truth = tiny_maps
+    sub = [m[:12000] for m in maps]  # keep the O(K n^2) CPU reference affordable
+    want = oracle.estimate_maps_transforms(sub, oracle_py.default_params(descriptor_type=0))
+    got = ctx.estimate_maps_transforms(sub, mm.default_params())
+    np.testing.assert_allclose(got, want["transforms"], rtol=0, atol=1e-5)
+
+
+# ---------------------------------------------------------------- K8 SHOT
+def test_shot_bit_exact(ctx, oracle, tiny_stages):
+    for st in tiny_stages:
+        kp_in = st["kp_sift"][:300]
+        wk, wd, wrf = oracle.shot(st["filtered"], st["normals"], kp_in, 0.8, debug=True)
+        gk, gd, grf = ctx.descriptors(st["filtered"], st["normals"], kp_in, type="SHOT", radius=0.8, index_leaf=0.1, debug=True)
+        assert_same_bits(gk, wk, "kept keypoints")
+        assert_same_bits(grf, wrf, "SHOT local reference frames")
+        assert_same_bits(gd, wd, "SHOT descriptors")
+        assert gd.shape[1] == 1344 and len(gd) > 100
+        np.testing.assert_allclose(np.linalg.norm(gd, axis=1), 1.0, atol=1e-5)
+    # isolated / off-surface keypoints are dropped like in the reference
+    st = tiny_stages[0]
+    kp = np.concatenate([st["kp_sift"][:5], np.array([[50, 50, 50, 0]], np.float32), st["kp_sift"][5:10]])
+    wk, wd = oracle.shot(st["filtered"], st["normals"], kp, 0.8)
+    gk, gd = ctx.descriptors(st["filtered"], st["normals"], kp, type="SHOT", radius=0.8, index_leaf=0.1)
+    assert len(wk) == 10
+    assert_same_bits(gk, wk, "kept keypoints")
+    assert_same_bits(gd, wd, "SHOT descriptors")
+
+
+def test_harris_shot_pipeline_matches_oracle(ctx, mm, oracle, small_maps):
+    """BASELINE config 4 in miniature: Harris3D + SHOT, tight inlier_threshold."""
+    import oracle_py
+    maps, truth = small_maps
+    kw = dict(keypoint_type=1, keypoint_threshold=0.0, inlier_threshold=0.2)
+    want = oracle.estimate_maps_transforms(maps, oracle_py.default_params(descriptor_type=4, **kw))
+    dm = ctx.maps_upload(maps)
+    p = mm.default_params(descriptor_type="SHOT", **kw)
+    f = ctx.features_compute(dm, 0, len(maps), p)
+    T, conf, stats = ctx.register_pairs(f, want["pairs"][:, :2], p)
+    np.testing.assert_array_equal(stats[:, :2], want["pairs"][:, 2:4])
+    np.testing.assert_array_equal(T, want["pair_T"])
+    np.testing.assert_array_equal(conf, want["pair_conf"])
+    # SIFT + SHOT on two maps
+    want = oracle.estimate_maps_transforms(maps[:2], oracle_py.default_params(descriptor_type=4))
+    got = ctx.estimate_maps_transforms(maps[:2], mm.default_params(descriptor_type="SHOT"))
+    np.testing.assert_allclose(got, want["transforms"], rtol=0, atol=1e-5)
+    assert want["pairs"][0][3] > 20
+
+
 # ---------------------------------------------------------------- K9 matching
 def test_match_bit_exact(ctx, oracle, tiny_stages):
     a, b = tiny_stages[0]["desc"], tiny_stages[1]["desc"]
