@@ -116,6 +116,12 @@ int mm3d_match(mm3d_ctx* ctx, const float* desc_src, uint64_t n_src, const float
 int mm3d_ransac(mm3d_ctx* ctx, const float* kp_src, uint64_t n_src, const float* kp_tgt, uint64_t n_tgt, const int32_t* pairs,
                 uint64_t n_corr, double inlier_threshold, float* transform, int32_t** inliers, uint64_t* n_inliers, int32_t* dbg,
                 double* dbg_d, float* best_model);
+/* estimateTransformFromDescriptorsSets (src/matching.cpp:176-194, pcl::SampleConsensusInitialAlignment).
+ * rand_calls (optional, in/out): how many C rand() calls the process has made before / after this call — the reference
+ * draws from the never-seeded global rand() stream, so the n-th call of a process differs from the first. */
+int mm3d_sac_ia(mm3d_ctx* ctx, const float* kp_src, uint64_t n_src, const float* desc_src, const float* kp_tgt, uint64_t n_tgt,
+                const float* desc_tgt, int dim, double min_sample_distance, double max_correspondence_distance, int max_iterations,
+                uint64_t* rand_calls, float* transform, float** errors, uint64_t* n_errors);
 /* estimateTransformICP (src/matching.cpp:196-221); dbg (optional, 2 ints) = iterations, converged;
  * sums (optional) = per-iteration fixed-point reductions, n_sums x 17 int64 */
 int mm3d_icp(mm3d_ctx* ctx, const float* src, uint64_t n_src, const float* tgt, uint64_t n_tgt, const float* initial_guess,

@@ -39,7 +39,7 @@ SYMBOLS = [
     "mm3d_keypoints", "mm3d_descriptors", "mm3d_match", "mm3d_ransac", "mm3d_icp", "mm3d_score", "mm3d_global_transforms",
     "mm3d_maps_upload", "mm3d_maps_free", "mm3d_features_compute", "mm3d_features_count", "mm3d_features_sizes",
     "mm3d_features_export_dev", "mm3d_features_import_dev", "mm3d_features_export_host", "mm3d_features_free",
-    "mm3d_register_pairs", "mm3d_estimate_resident", "mm3d_profile_begin", "mm3d_profile_end",
+    "mm3d_register_pairs", "mm3d_estimate_resident", "mm3d_profile_begin", "mm3d_profile_end", "mm3d_sac_ia",
 ]
 
 
@@ -230,6 +230,16 @@ class Context:
                                        bm.ctypes.data_as(f32p)))
         i = self._take(inl, ni.value, np.int32)
         return _T_out(T), i, dict(iterations=dbg[0], best_count=dbg[1], sample_dist_thresh=dd.value, best_model=_T_out(bm))
+
+    def sac_ia(self, kps, ds, kpt, dt, min_sample_distance, max_corr_dist, max_iterations, rand_calls=0):
+        s, sp = _f(kps, 4); t, tp = _f(kpt, 4); a, ap = _f(ds); b, bp = _f(dt)
+        dim = a.shape[1] if a.ndim == 2 and a.size else 33
+        T = np.zeros(16, np.float32); rc = C.c_uint64(rand_calls); err = f32p(); ne = C.c_uint64()
+        self._check(self.L.mm3d_sac_ia(self.h, sp, C.c_uint64(len(s)), ap, tp, C.c_uint64(len(t)), bp, dim, C.c_double(min_sample_distance),
+                                       C.c_double(max_corr_dist), int(max_iterations), C.byref(rc), T.ctypes.data_as(f32p), C.byref(err),
+                                       C.byref(ne)))
+        e = self._take(err, ne.value, np.float32)
+        return _T_out(T), dict(rand_calls=rc.value, errors=e)
 
     def icp(self, src, tgt, T0, max_dist, max_it, eps, index_leaf=0.0, outlier_threshold=0.5):
         s, sp = _f(src, 4); t, tp = _f(tgt, 4)

@@ -104,7 +104,7 @@ void check_supported(const mm3d_params& p)
   if (p.keypoint_type != MM3D_KP_SIFT && p.keypoint_type != MM3D_KP_HARRIS) throw std::runtime_error("unsupported: unknown keypoint_type");
   if (p.descriptor_type != MM3D_DESC_FPFH && p.descriptor_type != MM3D_DESC_SHOT && p.descriptor_type != MM3D_DESC_PFH)
     throw std::runtime_error("unsupported: descriptor_type PFHRGB / RSD / SC3D are not built yet (SURVEY.md 8f rank 3)");
-  if (p.estimation_method != MM3D_EST_MATCHING) throw std::runtime_error("unsupported: estimation_method SAC_IA is not built yet (SURVEY.md 8f)");
+  if (p.estimation_method != MM3D_EST_MATCHING && p.estimation_method != MM3D_EST_SAC_IA) throw std::runtime_error("unsupported: unknown estimation_method");
 }
 
 // src/map_merging.cpp:212-242, stage-major over all maps
@@ -192,15 +192,38 @@ void register_pairs(Ctx& c, const std::vector<MapFeat>& f, int dim, const std::v
     desc[m] = f[m].desc.p;
     nk[m] = f[m].keypoints.n;
   }
-  tm.begin();
-  std::vector<DCorr> corr;
-  match_batch(c, desc, nk, dim, jobs, (size_t)p.matching_k, corr);
-  tm.end(5);
+  std::vector<DCorr> corr(P);
+  std::vector<RansacOut> rs(P);
+  if (p.estimation_method == MM3D_EST_SAC_IA) {
+    // estimateTransformFromDescriptorsSets(min_sample_distance = inlier_threshold, max_correspondence_distance, max_iterations)
+    // (matching.cpp:242-247).  The C rand() stream runs through the complete row-major pair list of the feature set.
+    tm.begin();
+    std::vector<PairJob> all_pairs;
+    for (int i = 0; i < M - 1; ++i)
+      for (int j2 = i + 1; j2 < M; ++j2)
+        if (nk[i] > 0 && nk[j2] > 0) all_pairs.push_back(PairJob{i, j2});
+    std::vector<int> wanted(P, -1);
+    for (int k = 0; k < P; ++k)
+      for (size_t a = 0; a < all_pairs.size(); ++a)
+        if (all_pairs[a].a == jobs[k].a && all_pairs[a].b == jobs[k].b) wanted[k] = (int)a;
+    for (int k = 0; k < P; ++k)
+      if (wanted[k] < 0) throw std::runtime_error("register_pairs(SAC_IA): pair is not in the row-major pair list (i < j, both with keypoints)");
+    std::vector<SacOut> so;
+    sac_ia_batch(c, kps, desc, dim, all_pairs, wanted, p.inlier_threshold, p.max_correspondence_distance, p.max_iterations, 0, so);
+    for (int k = 0; k < P; ++k) {
+      memset(&rs[k], 0, sizeof(RansacOut));
+      memcpy(rs[k].T, so[k].T, sizeof(float) * 16);
+    }
+    tm.end(6);
+  } else {
+    tm.begin();
+    match_batch(c, desc, nk, dim, jobs, (size_t)p.matching_k, corr);
+    tm.end(5);
 
-  tm.begin();
-  std::vector<RansacOut> rs;
-  ransac_batch(c, kps, jobs, corr, p.inlier_threshold, rs, nullptr);
-  tm.end(6);
+    tm.begin();
+    ransac_batch(c, kps, jobs, corr, p.inlier_threshold, rs, nullptr);
+    tm.end(6);
+  }
 
   // neighbour index over every map that is a target of some pair
   std::vector<CloudView> tv(M, CloudView{nullptr, 0});
@@ -583,6 +606,29 @@ int mm3d_ransac(mm3d_ctx* ctx, const float* kp_src, uint64_t n_src, const float*
   if (dbg) { dbg[0] = out[0].iterations; dbg[1] = out[0].best_count; }
   if (dbg_d) *dbg_d = out[0].sample_dist_thresh;
   if (best_model) to_colmajor(out[0].best_model, best_model);
+  MM_CATCH
+}
+
+int mm3d_sac_ia(mm3d_ctx* ctx, const float* kp_src, uint64_t n_src, const float* desc_src, const float* kp_tgt, uint64_t n_tgt,
+                const float* desc_tgt, int dim, double min_sample_distance, double max_correspondence_distance, int max_iterations,
+                uint64_t* rand_calls, float* transform, float** errors, uint64_t* n_errors)
+{
+  if (!transform) return MM3D_ERR_ARG;
+  MM_TRY(ctx)
+  DCloud s = upload_cloud(c, kp_src, n_src), t = upload_cloud(c, kp_tgt, n_tgt);
+  DBuf<float> a(c, n_src * dim), b(c, n_tgt * dim);
+  a.upload(c, desc_src, n_src * dim);
+  b.upload(c, desc_tgt, n_tgt * dim);
+  std::vector<SacOut> so;
+  sac_ia_batch(c, {s.view(), t.view()}, {a.p, b.p}, dim, {PairJob{0, 1}}, {0}, min_sample_distance, max_correspondence_distance, max_iterations,
+               rand_calls ? *rand_calls : 0, so);
+  to_colmajor(so[0].T, transform);
+  if (rand_calls) *rand_calls = so[0].rand_calls;
+  if (errors) {
+    *errors = (float*)malloc(std::max<size_t>(so[0].errors.size(), 1) * 4);
+    memcpy(*errors, so[0].errors.data(), so[0].errors.size() * 4);
+    *n_errors = so[0].errors.size();
+  }
   MM_CATCH
 }
 

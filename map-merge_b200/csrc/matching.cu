@@ -5,6 +5,8 @@
 //       (pcl::registration::CorrespondenceRejectorSampleConsensus, pcl::RandomSampleConsensus,
 //        pcl::SampleConsensusModelRegistration, boost::mt19937(12345))
 #include <algorithm>
+#include <cmath>
+#include <cstring>
 
 #include "mm3d_internal.cuh"
 
@@ -270,12 +272,33 @@ struct Mt19937 {
 // One block per pair, thread 0 works: sample-distance threshold, then the whole
 // sample sequence the sequential RANSAC would draw (it depends only on the RNG
 // and on source keypoint coordinates, never on inlier counts).
-__global__ void __launch_bounds__(32) ransac_sample_kernel(const RansacJob* __restrict__ jobs)
+// stage_cap = number of correspondences whose source point (3 floats) and shuffle slot (1 int) fit in the
+// dynamic shared memory of this launch; a pair with more falls back to global memory.
+__global__ void __launch_bounds__(128) ransac_sample_kernel(const RansacJob* __restrict__ jobs, int stage_cap)
 {
-  __shared__ uint32_t mt_state[624];
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  uint32_t* mt_state = reinterpret_cast<uint32_t*>(rs_smem);
+  float* sx = reinterpret_cast<float*>(rs_smem + 624 * 4);
+  float* sy = sx + stage_cap;
+  float* sz = sy + stage_cap;
+  int* sshuf = reinterpret_cast<int*>(sz + stage_cap);
   const RansacJob& j = jobs[blockIdx.x];
-  if (threadIdx.x != 0) return;
   const int nc = j.nc;
+  // all threads: stage the source keypoint of every correspondence (the sequential part only reads these)
+  const bool staged = nc <= stage_cap;
+  int* shuffled = staged ? sshuf : j.shuffled;
+  if (staged)
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+      const float4 p = j.skp[j.corr[i].x];
+      sx[i] = p.x; sy[i] = p.y; sz[i] = p.z;
+    }
+  for (int i = threadIdx.x; i < nc; i += blockDim.x) shuffled[i] = i;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  auto src_pt = [&](int pos, float* x, float* y, float* z) {
+    if (staged) { *x = sx[pos]; *y = sy[pos]; *z = sz[pos]; }
+    else { const float4 p = j.skp[j.corr[pos].x]; *x = p.x; *y = p.y; *z = p.z; }
+  };
   j.out->sample_dist_thresh = 0.0;
   if (nc < 3) {
     *j.n_samples = 0;
@@ -284,10 +307,11 @@ __global__ void __launch_bounds__(32) ransac_sample_kernel(const RansacJob* __re
   // computeSampleDistanceThreshold: PCA of the source correspondences
   float a[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int i = 0; i < nc; ++i) {
-    const float4 p = j.skp[j.corr[i].x];
-    a[0] += p.x * p.x; a[1] += p.x * p.y; a[2] += p.x * p.z;
-    a[3] += p.y * p.y; a[4] += p.y * p.z; a[5] += p.z * p.z;
-    a[6] += p.x; a[7] += p.y; a[8] += p.z;
+    float px, py, pz;
+    src_pt(i, &px, &py, &pz);
+    a[0] += px * px; a[1] += px * py; a[2] += px * pz;
+    a[3] += py * py; a[4] += py * pz; a[5] += pz * pz;
+    a[6] += px; a[7] += py; a[8] += pz;
   }
   const float n = (float)nc;
   for (int k = 0; k < 9; ++k) a[k] /= n;
@@ -308,7 +332,6 @@ __global__ void __launch_bounds__(32) ransac_sample_kernel(const RansacJob* __re
   Mt19937 rng;
   rng.s = mt_state;
   rng.seed(12345u);
-  for (int i = 0; i < nc; ++i) j.shuffled[i] = i;
   int ns = 0;
   for (int h = 0; h < MAX_HYP; ++h) {
     bool good = false;
@@ -316,16 +339,19 @@ __global__ void __launch_bounds__(32) ransac_sample_kernel(const RansacJob* __re
     for (int iter = 0; iter < 1000; ++iter) {
       for (int i = 0; i < 3; ++i) {
         const uint32_t rnd = rng.next() >> 1;  // uniform_int<>(0, INT_MAX) on mt19937
-        const int o = i + (int)((unsigned long long)rnd % (unsigned long long)(nc - i));
-        const int t = j.shuffled[i];
-        j.shuffled[i] = j.shuffled[o];
-        j.shuffled[o] = t;
+        const int o = i + (int)(rnd % (uint32_t)(nc - i));
+        const int t = shuffled[i];
+        shuffled[i] = shuffled[o];
+        shuffled[o] = t;
       }
-      s0 = j.shuffled[0]; s1 = j.shuffled[1]; s2 = j.shuffled[2];
-      const float4 pa = j.skp[j.corr[s0].x], pb = j.skp[j.corr[s1].x], pc = j.skp[j.corr[s2].x];
-      const float ax = pb.x - pa.x, ay = pb.y - pa.y, az = pb.z - pa.z;
-      const float bx = pc.x - pa.x, by = pc.y - pa.y, bz = pc.z - pa.z;
-      const float cx = pc.x - pb.x, cy = pc.y - pb.y, cz = pc.z - pb.z;
+      s0 = shuffled[0]; s1 = shuffled[1]; s2 = shuffled[2];
+      float pax, pay, paz, pbx, pby, pbz, pcx, pcy, pcz;
+      src_pt(s0, &pax, &pay, &paz);
+      src_pt(s1, &pbx, &pby, &pbz);
+      src_pt(s2, &pcx, &pcy, &pcz);
+      const float ax = pbx - pax, ay = pby - pay, az = pbz - paz;
+      const float bx = pcx - pax, by = pcy - pay, bz = pcz - paz;
+      const float cx = pcx - pbx, cy = pcy - pby, cz = pcz - pbz;
       if ((double)(ax * ax + ay * ay + az * az) > thr && (double)(bx * bx + by * by + bz * bz) > thr &&
           (double)(cx * cx + cy * cy + cz * cz) > thr) {
         good = true;
@@ -415,12 +441,10 @@ __device__ bool is_identity4(const float* t)
   return true;
 }
 
-// replay of pcl::RandomSampleConsensus::computeModel's adaptive loop over the
-// pre-scored hypotheses, then inlier selection and the final float SVD.
-__global__ void __launch_bounds__(32) ransac_select_kernel(const RansacJob* __restrict__ jobs, double thresh)
+// replay of pcl::RandomSampleConsensus::computeModel's adaptive loop over the pre-scored hypotheses;
+// fills the debug fields of the output and returns the winning hypothesis (or -1)
+__device__ int ransac_replay(const RansacJob& j)
 {
-  const RansacJob& j = jobs[blockIdx.x];
-  if (threadIdx.x != 0) return;
   RansacOut& o = *j.out;
   for (int i = 0; i < 16; ++i) { o.T[i] = 0.f; o.best_model[i] = (i % 5 == 0) ? 1.f : 0.f; }
   o.iterations = 0;
@@ -428,7 +452,7 @@ __global__ void __launch_bounds__(32) ransac_select_kernel(const RansacJob* __re
   o.n_inliers = 0;
   const int nc = j.nc;
   const int ns = *j.n_samples;
-  if (nc < 3) return;
+  if (nc < 3) return -1;
   int iterations = 0, n_best = -2147483647, best_h = -1;
   double k = 1.0;
   const double log_probability = log(1.0 - 0.99);
@@ -450,26 +474,118 @@ __global__ void __launch_bounds__(32) ransac_select_kernel(const RansacJob* __re
   }
   o.iterations = iterations;
   o.best_count = n_best;
+  return best_h;
+}
+
+// replay of pcl::RandomSampleConsensus::computeModel's adaptive loop over the
+// pre-scored hypotheses, then inlier selection and the final float SVD.
+__global__ void __launch_bounds__(32) ransac_select_kernel(const RansacJob* __restrict__ jobs, double thresh)
+{
+  const RansacJob& j = jobs[blockIdx.x];
+  __shared__ int s_best;
+  if (threadIdx.x == 0) s_best = ransac_replay(j);
+  __syncwarp();
+  const int best_h = s_best;
+  if (best_h >= 0) {
+    // selectWithinDistance with the whole warp: ordered compaction keeps correspondence order
+    float bm[12];
+    for (int i = 0; i < 12; ++i) bm[i] = j.models[best_h * 12 + i];
+    int ni = 0;
+    for (int base = 0; base < j.nc; base += 32) {
+      const int i = base + threadIdx.x;
+      bool in = false;
+      if (i < j.nc) {
+        const int2 cr = j.corr[i];
+        const float4 s = j.skp[cr.x], t = j.tkp[cr.y];
+        float px, py, pz;
+        em::transform_point(bm, s.x, s.y, s.z, &px, &py, &pz);
+        const float ex = px - t.x, ey = py - t.y, ez = pz - t.z;
+        in = (double)((ex * ex + ey * ey) + ez * ez) < thresh;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, in);
+      if (in) j.inliers[ni + __popc(m & ((1u << threadIdx.x) - 1u))] = i;
+      ni += __popc(m);
+    }
+    __syncwarp();
+    if (threadIdx.x == 0) *j.n_samples = ni;
+  }
+  __syncwarp();
+  if (threadIdx.x != 0) return;
+  RansacOut& o = *j.out;
   if (best_h < 0) return;
   float bm[16];
   for (int i = 0; i < 12; ++i) bm[i] = j.models[best_h * 12 + i];
   bm[12] = bm[13] = bm[14] = 0.f;
   bm[15] = 1.f;
   for (int i = 0; i < 16; ++i) o.best_model[i] = bm[i];
-  int ni = 0;
-  for (int i = 0; i < nc; ++i) {
-    const int2 cr = j.corr[i];
-    const float4 s = j.skp[cr.x], t = j.tkp[cr.y];
-    float px, py, pz;
-    em::transform_point(bm, s.x, s.y, s.z, &px, &py, &pz);
-    const float ex = px - t.x, ey = py - t.y, ez = pz - t.z;
-    if ((double)((ex * ex + ey * ey) + ez * ez) < thresh) j.inliers[ni++] = i;
-  }
+  int ni = *j.n_samples;  // inlier count left here by the warp-wide selection below
   if (ni < 3 || is_identity4(bm)) return;  // matching.cpp:128-133 -> zero matrix, inliers cleared
   o.n_inliers = ni;
   umeyama_seq<float>(
       ni, [&](int i, float* v) { const float4 p = j.skp[j.corr[j.inliers[i]].x]; v[0] = p.x; v[1] = p.y; v[2] = p.z; },
       [&](int i, float* v) { const float4 p = j.tkp[j.corr[j.inliers[i]].y]; v[0] = p.x; v[1] = p.y; v[2] = p.z; }, o.T);
+}
+
+// ---------------------------------------------------------------- SAC_IA
+// pcl::SampleConsensusInitialAlignment (map_merge_3d/src/matching.cpp:142-194).  The random choices (C rand(), a
+// process-global stream in the reference) are drawn on the host for ALL pairs in row-major order; the device scores
+// every iteration's hypothesis: float Umeyama on the 3 sampled pairs, then TruncatedError over the transformed source
+// keypoints (nearest target keypoint, squared distance), summed sequentially in float like the reference.
+struct SacJob {
+  const float4* skp;
+  int ns;
+  const float4* tkp;
+  GridView tgt;          // index over the target keypoints
+  const int* knn_idx;    // ns x kk nearest target features per source feature
+  int kk;
+  const int* samples;    // n_it x 3 source keypoint indices
+  const int* choice;     // n_it x 3 index into the k-NN list
+  float* errors;         // n_it
+  float* models;         // n_it x 16 (row-major)
+};
+
+__global__ void __launch_bounds__(128) sac_hypothesis_kernel(const SacJob* __restrict__ jobs, int n_jobs, int n_it, float thr, int rv,
+                                                            float* __restrict__ scratch, int scratch_stride)
+{
+  __shared__ float T[16];
+  float* terms = scratch + (size_t)blockIdx.x * scratch_stride;
+  for (int h = blockIdx.x; h < n_jobs * n_it; h += gridDim.x) {
+    const SacJob& j = jobs[h / n_it];
+    const int it = h % n_it;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int* smp = j.samples + it * 3;
+      const int* ch = j.choice + it * 3;
+      int corr[3];
+      for (int i = 0; i < 3; ++i) corr[i] = j.knn_idx[(size_t)smp[i] * j.kk + min(ch[i], j.kk - 1)];
+      float Rt[16];
+      umeyama_seq<float>(
+          3, [&](int i, float* o) { const float4 p = j.skp[smp[i]]; o[0] = p.x; o[1] = p.y; o[2] = p.z; },
+          [&](int i, float* o) { const float4 p = j.tkp[corr[i]]; o[0] = p.x; o[1] = p.y; o[2] = p.z; }, Rt);
+      for (int i = 0; i < 16; ++i) {
+        T[i] = Rt[i];
+        j.models[(size_t)it * 16 + i] = Rt[i];
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < j.ns; i += blockDim.x) {
+      const float4 p = j.skp[i];
+      float x, y, z;
+      em::transform_point(T, p.x, p.y, p.z, &x, &y, &z);
+      int idx;
+      float d2;
+      float4 q;
+      float term = 1.0f;
+      if (nearest_bounded(j.tgt, x, y, z, (double)thr, rv, &idx, &d2, &q)) term = (d2 <= thr) ? (d2 / thr) : 1.0f;
+      terms[i] = term;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float error = 0.f;
+      for (int i = 0; i < j.ns; ++i) error += terms[i];
+      j.errors[it] = error;
+    }
+  }
 }
 
 }  // namespace
@@ -577,7 +693,16 @@ void ransac_batch(Ctx& c, const std::vector<CloudView>& keypoints, const std::ve
   }
   DBuf<RansacJob> drj = to_device(c, rj);
   const double thresh = inlier_threshold * inlier_threshold;
-  MM_LAUNCH(c, ransac_sample_kernel, P, 32, 0, drj.p);
+  int max_c = 0;
+  for (int p = 0; p < P; ++p) max_c = std::max(max_c, corr[p].n);
+  const int stage_cap = std::min(std::max(max_c, 1), (200 * 1024 - 624 * 4) / 16);
+  const size_t rs_smem = 624 * 4 + (size_t)stage_cap * 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MM_CUDA(cudaFuncSetAttribute(ransac_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  MM_LAUNCH(c, ransac_sample_kernel, P, 128, rs_smem, drj.p, stage_cap);
   MM_LAUNCH(c, ransac_score_kernel, dim3((MAX_HYP + 3) / 4, P), 128, 0, drj.p, thresh);
   MM_LAUNCH(c, ransac_select_kernel, P, 32, 0, drj.p, thresh);
   dout.download(c, out.data(), P);
@@ -593,6 +718,175 @@ void ransac_batch(Ctx& c, const std::vector<CloudView>& keypoints, const std::ve
       (*inliers)[p].assign(hinl.begin() + off, hinl.begin() + off + out[p].n_inliers);
       off += (size_t)corr[p].n;
     }
+  }
+}
+
+// glibc rand(): TYPE_3 additive feedback generator, never seeded in the reference => seed 1
+struct GlibcRand {
+  int32_t r[34];
+  int f, b;
+  unsigned long long calls = 0;
+  GlibcRand()
+  {
+    r[0] = 1;
+    for (int i = 1; i < 31; ++i) {
+      const long hi = r[i - 1] / 127773, lo = r[i - 1] % 127773;
+      long word = 16807 * lo - 2836 * hi;
+      if (word < 0) word += 2147483647;
+      r[i] = (int32_t)word;
+    }
+    f = 3;
+    b = 0;
+    for (int i = 0; i < 310; ++i) step();
+  }
+  int step()
+  {
+    uint32_t* st = (uint32_t*)r;
+    st[f] += st[b];
+    const int result = (int)(st[f] >> 1);
+    if (++f >= 31) f = 0;
+    if (++b >= 31) b = 0;
+    return result;
+  }
+  int next() { ++calls; return step(); }
+  int index(int n) { return (int)(n * (next() / (2147483647 + 1.0))); }  // getRandomIndex
+};
+
+void sac_ia_batch(Ctx& c, const std::vector<CloudView>& keypoints, const std::vector<const float*>& desc, int dim,
+                  const std::vector<PairJob>& all_pairs, const std::vector<int>& wanted, double min_sample_distance, double max_corr_dist,
+                  int max_iterations, unsigned long long rand_skip, std::vector<SacOut>& out)
+{
+  out.assign(wanted.size(), SacOut());
+  for (SacOut& o : out) {
+    for (int k = 0; k < 16; ++k) o.T[k] = (k % 5 == 0) ? 1.f : 0.f;  // align() leaves the identity guess when nothing is scored
+    o.rand_calls = 0;
+  }
+  if (wanted.empty() || max_iterations <= 0) return;
+  const int M = (int)keypoints.size();
+  const int n_it = max_iterations;
+  // host copies of the keypoints: the sample selection is sequential and touches only a few points per draw
+  std::vector<std::vector<float4>> hk(M);
+  std::vector<char> needed(M, 0);
+  for (const PairJob& p : all_pairs) needed[p.a] = 1;
+  for (int m = 0; m < M; ++m)
+    if (needed[m] && keypoints[m].n) {
+      hk[m].resize(keypoints[m].n);
+      MM_CUDA(cudaMemcpyAsync(hk[m].data(), keypoints[m].pts, (size_t)keypoints[m].n * sizeof(float4), cudaMemcpyDeviceToHost, c.stream));
+    }
+  c.sync();
+  std::vector<int> slot_of_pair(all_pairs.size(), -1);
+  for (size_t w = 0; w < wanted.size(); ++w) slot_of_pair[wanted[w]] = (int)w;
+  const int W = (int)wanted.size();
+  std::vector<int> h_samples((size_t)W * n_it * 3, 0), h_choice((size_t)W * n_it * 3, 0);
+  std::vector<char> runnable(W, 0);
+  GlibcRand rng;
+  for (unsigned long long i = 0; i < rand_skip; ++i) rng.next();
+  for (size_t pi = 0; pi < all_pairs.size(); ++pi) {
+    const PairJob& pj = all_pairs[pi];
+    const int ns = keypoints[pj.a].n, nt = keypoints[pj.b].n;
+    const int slot = slot_of_pair[pi];
+    if (ns < 3 || nt == 0) {
+      if (slot >= 0) out[slot].rand_calls = rng.calls;
+      continue;
+    }
+    if (slot >= 0) runnable[slot] = 1;
+    const std::vector<float4>& kp = hk[pj.a];
+    float msd = (float)min_sample_distance;
+    for (int it = 0; it < n_it; ++it) {
+      int sample[3], nsmp = 0, without = 0;
+      const int max_without = 3 * ns;
+      while (nsmp < 3) {
+        const int idx = rng.index(ns);
+        bool valid = true;
+        for (int i = 0; i < nsmp; ++i) {
+          const float dx = kp[idx].x - kp[sample[i]].x, dy = kp[idx].y - kp[sample[i]].y, dz = kp[idx].z - kp[sample[i]].z;
+          const float dist = std::sqrt((dx * dx + dy * dy) + dz * dz);
+          if (idx == sample[i] || dist < msd) { valid = false; break; }
+        }
+        if (valid) { sample[nsmp++] = idx; without = 0; }
+        else ++without;
+        if (without >= max_without) { msd *= 0.5f; without = 0; }
+      }
+      for (int i = 0; i < 3; ++i) {
+        const int rc = rng.index(10);
+        if (slot >= 0) {
+          h_samples[((size_t)slot * n_it + it) * 3 + i] = sample[i];
+          h_choice[((size_t)slot * n_it + it) * 3 + i] = rc;
+        }
+      }
+    }
+    if (slot >= 0) out[slot].rand_calls = rng.calls;
+  }
+  // feature-space 10-NN for the wanted pairs
+  std::vector<KnnJob> kj(W);
+  std::vector<DBuf<int>> kidx(W);
+  std::vector<DBuf<float>> kdist(W);
+  int max_rows = 0, max_ns = 0;
+  bool uniform10 = true;
+  for (int w = 0; w < W; ++w) {
+    const PairJob& pj = all_pairs[wanted[w]];
+    const int ns = runnable[w] ? keypoints[pj.a].n : 0, nt = keypoints[pj.b].n;
+    const int kk = std::min(10, std::max(nt, 1));
+    kidx[w].alloc(c, (size_t)std::max(ns, 1) * kk);
+    kdist[w].alloc(c, (size_t)std::max(ns, 1) * kk);
+    kj[w] = KnnJob{desc[pj.a], ns, desc[pj.b], nt, kk, kidx[w].p, kdist[w].p};
+    max_rows = std::max(max_rows, ns);
+    max_ns = std::max(max_ns, ns);
+    if (ns > 0 && kk != 10) uniform10 = false;
+  }
+  if (max_rows == 0) return;
+  DBuf<KnnJob> dkj = to_device(c, kj);
+  if (dim == 33 && uniform10) MM_LAUNCH(c, (knn_small_kernel<33, 10>), dim3((max_rows + 127) / 128, W), 128, 0, dkj.p);
+  else MM_LAUNCH(c, knn_generic_kernel, dim3((max_rows + 63) / 64, W), 128, 0, dkj.p, dim);
+  // index over the target keypoints (arbitrary positions: the builder re-sorts them)
+  std::vector<CloudView> tv(M, CloudView{nullptr, 0});
+  for (int w = 0; w < W; ++w)
+    if (runnable[w]) tv[all_pairs[wanted[w]].b] = keypoints[all_pairs[wanted[w]].b];
+  const float thr = (float)max_corr_dist;
+  const float leaf = std::max(0.05f, std::sqrt(std::max(thr, 1e-6f)) * 0.25f);
+  std::vector<DIndex> tidx;
+  build_index_batch(c, tv, leaf, 1, 1, 1, tidx);
+  const int rv = (int)std::ceil(std::sqrt((double)thr) / (double)leaf) + 1;
+  DBuf<int> dsamples = to_device(c, h_samples), dchoice = to_device(c, h_choice);
+  DBuf<float> errors(c, (size_t)W * n_it), models(c, (size_t)W * n_it * 16);
+  std::vector<SacJob> sj;
+  std::vector<int> sj_slot;
+  for (int w = 0; w < W; ++w) {
+    if (!runnable[w]) continue;
+    const PairJob& pj = all_pairs[wanted[w]];
+    SacJob j;
+    j.skp = keypoints[pj.a].pts;
+    j.ns = keypoints[pj.a].n;
+    j.tkp = keypoints[pj.b].pts;
+    j.tgt = tidx[pj.b].v;
+    j.knn_idx = kidx[w].p;
+    j.kk = kj[w].k;
+    j.samples = dsamples.p + (size_t)w * n_it * 3;
+    j.choice = dchoice.p + (size_t)w * n_it * 3;
+    j.errors = errors.p + (size_t)w * n_it;
+    j.models = models.p + (size_t)w * n_it * 16;
+    sj.push_back(j);
+    sj_slot.push_back(w);
+  }
+  if (sj.empty()) return;
+  DBuf<SacJob> dsj = to_device(c, sj);
+  const int grid = std::min((int)sj.size() * n_it, 148 * 8);
+  DBuf<float> scratch(c, (size_t)grid * max_ns);
+  MM_LAUNCH(c, sac_hypothesis_kernel, grid, 128, 0, dsj.p, (int)sj.size(), n_it, thr, rv, scratch.p, max_ns);
+  std::vector<float> herr((size_t)W * n_it), hmod((size_t)W * n_it * 16);
+  errors.download(c, herr.data(), herr.size());
+  models.download(c, hmod.data(), hmod.size());
+  c.sync();
+  for (size_t k = 0; k < sj.size(); ++k) {
+    const int w = sj_slot[k];
+    float lowest = 0.f;
+    int best = -1;
+    for (int it = 0; it < n_it; ++it) {
+      const float e = herr[(size_t)w * n_it + it];
+      if (it == 0 || e < lowest) { lowest = e; best = it; }
+    }
+    if (best >= 0) memcpy(out[w].T, &hmod[((size_t)w * n_it + best) * 16], 16 * sizeof(float));
+    out[w].errors.assign(herr.begin() + (size_t)w * n_it, herr.begin() + (size_t)(w + 1) * n_it);
   }
 }
 

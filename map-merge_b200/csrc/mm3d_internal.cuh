@@ -363,6 +363,16 @@ struct RansacOut {
 void ransac_batch(Ctx& c, const std::vector<CloudView>& keypoints, const std::vector<PairJob>& jobs, const std::vector<DCorr>& corr,
                   double inlier_threshold, std::vector<RansacOut>& out, std::vector<std::vector<int>>* inliers);
 
+struct SacOut {
+  float T[16];  // row-major
+  unsigned long long rand_calls;  // rand() calls consumed up to and including this pair
+  std::vector<float> errors;      // per-iteration error metric
+};
+// all_pairs: the complete row-major pair list (the rand() stream runs through all of it); wanted: indices into all_pairs
+void sac_ia_batch(Ctx& c, const std::vector<CloudView>& keypoints, const std::vector<const float*>& desc, int dim,
+                  const std::vector<PairJob>& all_pairs, const std::vector<int>& wanted, double min_sample_distance, double max_corr_dist,
+                  int max_iterations, unsigned long long rand_skip, std::vector<SacOut>& out);
+
 // icp.cu — K11, K12
 struct IcpOut {
   float T[16];  // row-major

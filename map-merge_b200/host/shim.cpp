@@ -283,11 +283,20 @@ Eigen::Matrix4f estimateTransformFromCorrespondences(const PointCloudPtr& source
   return to_matrix(T);
 }
 
-Eigen::Matrix4f estimateTransformFromDescriptorsSets(const PointCloudPtr&, const LocalDescriptorsPtr& source_descriptors, const PointCloudPtr&,
-                                                     const LocalDescriptorsPtr& target_descriptors, double, double, int)
+Eigen::Matrix4f estimateTransformFromDescriptorsSets(const PointCloudPtr& source_keypoints, const LocalDescriptorsPtr& source_descriptors,
+                                                     const PointCloudPtr& target_keypoints, const LocalDescriptorsPtr& target_descriptors,
+                                                     double min_sample_distance, double max_correspondence_distance, int max_iterations)
 {
   assertDescriptorsPair(source_descriptors, target_descriptors);
-  throw std::runtime_error("libmm3d: estimation_method SAC_IA is not built yet (SURVEY.md 8f rank 2)");
+  const DescInfo& d = desc_by_name(source_descriptors->fields[0].name);
+  std::vector<float> s = pack(source_keypoints.get()), t = pack(target_keypoints.get());
+  // the reference draws from the process-global C rand() stream; the shim keeps the running call count per thread
+  static thread_local uint64_t rand_calls = 0;
+  float T[16];
+  check(mm3d_sac_ia(context(), s.data(), s.size() / 4, (const float*)source_descriptors->data.data(), t.data(), t.size() / 4,
+                    (const float*)target_descriptors->data.data(), d.dim, min_sample_distance, max_correspondence_distance, max_iterations,
+                    &rand_calls, T, nullptr, nullptr));
+  return to_matrix(T);
 }
 
 Eigen::Matrix4f estimateTransformICP(const PointCloudPtr& source_points, const PointCloudPtr& target_points, const Eigen::Matrix4f& initial_guess,

@@ -1526,6 +1526,121 @@ static Mat4 ransac_transform(const Cloud& skp, const Cloud& tkp, const std::vect
 }
 
 // ===========================================================================
+// a12-SAC_IA  estimateTransformFromDescriptorsSets -> pcl::SampleConsensusInitialAlignment
+// [REF src/matching.cpp:142-194: setMinSampleDistance(inlier_threshold), setMaxCorrespondenceDistance(max_corr),
+//  setMaximumIterations(max_iterations); inputs are the KEYPOINT clouds and their descriptors]
+// [PCL-recall pcl/registration/impl/ia_ransac.hpp: nr_samples_ = 3, k_correspondences_ = 10, TruncatedError on the
+//  SQUARED nearest-neighbour distance, C rand() (never seeded -> glibc TYPE_3 generator from seed 1)]
+// The rand() stream is process-global in the reference; here it is an explicit state that the caller threads
+// through the pair loop in row-major pair order (a fresh process's first estimateMapsTransforms call).
+// ===========================================================================
+struct GlibcRand {
+  int32_t r[34];
+  int f, b;  // front / rear indices of the additive feedback generator
+  GlibcRand() { seed(1); }
+  void seed(uint32_t s)
+  {
+    // glibc srandom_r, TYPE_3 (degree 31, separation 3)
+    if (s == 0) s = 1;
+    r[0] = (int32_t)s;
+    for (int i = 1; i < 31; ++i) {
+      const long hi = r[i - 1] / 127773, lo = r[i - 1] % 127773;
+      long word = 16807 * lo - 2836 * hi;
+      if (word < 0) word += 2147483647;
+      r[i] = (int32_t)word;
+    }
+    f = 3;
+    b = 0;
+    for (int i = 0; i < 310; ++i) next();
+  }
+  int next()
+  {
+    uint32_t* st = (uint32_t*)r;
+    st[f] += st[b];
+    const int result = (int)(st[f] >> 1);
+    if (++f >= 31) f = 0;
+    if (++b >= 31) b = 0;
+    return result;
+  }
+  uint64_t calls = 0;
+  int rand_() { ++calls; return next(); }
+};
+
+static inline int sac_random_index(GlibcRand& rng, int n)
+{
+  return (int)(n * (rng.rand_() / (2147483647 + 1.0)));  // getRandomIndex: n * (rand() / (RAND_MAX + 1.0))
+}
+
+static Mat4 sac_ia_transform(const Cloud& skp, const std::vector<float>& sdesc, const Cloud& tkp, const std::vector<float>& tdesc, int D,
+                             double min_sample_distance_d, double max_corr_dist, int max_iterations, GlibcRand& rng,
+                             std::vector<float>* errors_dbg = nullptr)
+{
+  const int nr_samples = 3, k_corr = 10;
+  const int ns = (int)skp.size(), nt = (int)tkp.size();
+  Mat4 final_t = Mat4::identity();  // final_transformation_ = guess (identity): what align() leaves when nothing better is found
+  if (ns < nr_samples || nt == 0) return final_t;  // "No. of samples > cloud size": selectSamples bails out; fence for empty target
+  float min_sample_distance = (float)min_sample_distance_d;
+  const float thr = (float)max_corr_dist;  // TruncatedError(corr_dist_threshold_)
+  // feature-space k-NN of every source feature in the target set (exact, sorted)
+  const int kk = std::min(k_corr, nt);
+  std::vector<int> fi;
+  std::vector<float> fd;
+  knn_bruteforce(sdesc.data(), ns, tdesc.data(), nt, D, kk, fi, fd);
+  Grid tree;
+  tree.build(tkp, std::max(thr, 0.05f));
+  float lowest_error = 0.f;
+  std::vector<std::pair<float, int>> nn;
+  for (int it = 0; it < max_iterations; ++it) {
+    // selectSamples
+    std::vector<int> sample;
+    int without = 0;
+    const int max_without = 3 * ns;
+    while ((int)sample.size() < nr_samples) {
+      const int idx = sac_random_index(rng, ns);
+      bool valid = true;
+      for (size_t i = 0; i < sample.size(); ++i) {
+        const P4 &a = skp[idx], &b = skp[sample[i]];
+        const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+        const float dist = std::sqrt((dx * dx + dy * dy) + dz * dz);  // euclideanDistance
+        if (idx == sample[i] || dist < min_sample_distance) { valid = false; break; }
+      }
+      if (valid) { sample.push_back(idx); without = 0; }
+      else ++without;
+      if (without >= max_without) { min_sample_distance *= 0.5f; without = 0; }
+    }
+    // findSimilarFeatures: one of the k nearest target features at random
+    int corr[3];
+    for (int i = 0; i < nr_samples; ++i) {
+      const int rc = sac_random_index(rng, k_corr);
+      corr[i] = fi[(size_t)sample[i] * kk + std::min(rc, kk - 1)];
+    }
+    // TransformationEstimationSVD (float Umeyama) on the three pairs
+    std::vector<float> sv(9), tv(9);
+    for (int i = 0; i < 3; ++i) {
+      sv[i * 3] = skp[sample[i]].x; sv[i * 3 + 1] = skp[sample[i]].y; sv[i * 3 + 2] = skp[sample[i]].z;
+      tv[i * 3] = tkp[corr[i]].x; tv[i * 3 + 1] = tkp[corr[i]].y; tv[i * 3 + 2] = tkp[corr[i]].z;
+    }
+    Mat4 T;
+    umeyama<float>(sv, tv, 3, T.m);
+    // computeErrorMetric over the transformed source keypoints
+    float error = 0.f;
+    for (int i = 0; i < ns; ++i) {
+      float x, y, z;
+      xform(T, skp[i].x, skp[i].y, skp[i].z, x, y, z);
+      tree.knn(x, y, z, 1, nn);
+      const float e = nn[0].first;
+      error += (e <= thr) ? (e / thr) : 1.0f;
+    }
+    if (errors_dbg) errors_dbg->push_back(error);
+    if (it == 0 || error < lowest_error) {
+      lowest_error = error;
+      final_t = T;
+    }
+  }
+  return final_t;
+}
+
+// ===========================================================================
 // a11  estimateTransformICP -> pcl::IterativeClosestPoint  [REF src/matching.cpp:196-221]
 // [PCL-recall pcl/registration/impl/icp.hpp, correspondence_estimation.hpp,
 //  default_convergence_criteria.hpp, transformation_estimation_svd.hpp]
@@ -1851,8 +1966,25 @@ static void map_features(const Cloud& in, const Params& p, MapFeatures& f, Stage
   }
 }
 
+static GlibcRand g_pipeline_rand;
+
 static PairResult register_pair(const MapFeatures& a, const MapFeatures& b, int i, int j, const Params& p, StageTimes* st)
 {
+  if (p.estimation_method == 1) {  // EstimationMethod::SAC_IA (matching.cpp:242-247)
+    PairResult r;
+    r.i = i; r.j = j;
+    double t0 = now_s();
+    Mat4 t = sac_ia_transform(a.keypoints, a.desc, b.keypoints, b.desc, a.dim, p.inlier_threshold, p.max_correspondence_distance,
+                              p.max_iterations, g_pipeline_rand);
+    double t2 = now_s();
+    if (p.refine_transform) t = icp_refine(a.cloud, b.cloud, t, p.max_correspondence_distance, p.max_iterations, p.transform_epsilon);
+    double t3 = now_s();
+    const double score = transform_score(a.cloud, b.cloud, t, p.max_correspondence_distance);
+    double t4 = now_s();
+    r.t = t; r.confidence = 1. / score; r.n_corr = 0; r.n_inliers = 0;
+    if (st) { st->t[6] += t2 - t0; st->t[7] += t3 - t2; st->t[8] += t4 - t3; }
+    return r;
+  }
   PairResult r;
   r.i = i; r.j = j;
   double t0 = now_s();
@@ -2066,6 +2198,30 @@ int orc_ransac(const float* kps, uint64_t ns, const float* kpt, uint64_t nt, con
   return 0;
 }
 
+// rand_calls (in/out): number of rand() calls consumed before / after this pair (0 = fresh process)
+int orc_sac_ia(const float* kps, uint64_t ns, const float* ds, const float* kpt, uint64_t nt, const float* dt, int dim, double min_sample_distance,
+               double max_corr_dist, int max_iterations, uint64_t* rand_calls, float* T, float** errors, uint64_t* n_errors)
+{
+  Cloud s = to_cloud(kps, ns), t = to_cloud(kpt, nt);
+  std::vector<float> sd(ds, ds + ns * dim), td(dt, dt + nt * dim);
+  GlibcRand rng;
+  const uint64_t skip = rand_calls ? *rand_calls : 0;
+  for (uint64_t i = 0; i < skip; ++i) rng.rand_();
+  std::vector<float> err;
+  Mat4 r = sac_ia_transform(s, sd, t, td, dim, min_sample_distance, max_corr_dist, max_iterations, rng, &err);
+  to_colmajor(r, T);
+  if (rand_calls) *rand_calls = rng.calls;
+  if (errors) { *errors = dup_f(err.data(), err.size() * 4); *n_errors = err.size(); }
+  return 0;
+}
+
+int orc_glibc_rand(int n, int32_t* out)
+{
+  GlibcRand rng;
+  for (int i = 0; i < n; ++i) out[i] = rng.rand_();
+  return 0;
+}
+
 int orc_icp(const float* src, uint64_t ns, const float* tgt, uint64_t nt, const float* T0, double max_dist, int max_it, double eps,
             float* T, int32_t* dbg, long long** sums, uint64_t* n_sums)
 {
@@ -2142,6 +2298,7 @@ int orc_estimate_maps_transforms(int n_maps, const float* const* clouds, const u
   }
   StageTimes st;
   memset(&st, 0, sizeof(st));
+  g_pipeline_rand.seed(1);  // a fresh process: rand() has never been called
   std::vector<MapFeatures> f(n_maps);
   for (int i = 0; i < n_maps; ++i) map_features(to_cloud(clouds[i], n_points[i]), *p, f[i], &st);
   std::vector<Estimate> est;

@@ -186,6 +186,19 @@ class Oracle:
         return T.reshape(4, 4).T.copy(), i, dict(iterations=dbg[0], best_count=dbg[1], sample_dist_thresh=dd.value,
                                                  best_model=bm.reshape(4, 4).T.copy())
 
+    def sac_ia(self, kps, ds, kpt, dt, min_sample_distance, max_corr_dist, max_iterations, rand_calls=0):
+        s, sp = _f(kps); t, tp = _f(kpt); a, ap = _f(ds); b, bp = _f(dt)
+        T = np.zeros(16, np.float32); rc = C.c_uint64(rand_calls); err = f32p(); ne = C.c_uint64()
+        self.lib.orc_sac_ia(sp, C.c_uint64(len(s)), ap, tp, C.c_uint64(len(t)), bp, a.shape[1] if a.ndim == 2 else 33, C.c_double(min_sample_distance),
+                            C.c_double(max_corr_dist), int(max_iterations), C.byref(rc), T.ctypes.data_as(f32p), C.byref(err), C.byref(ne))
+        e = _take(err, ne.value, np.float32); self._free(err)
+        return T.reshape(4, 4).T.copy(), dict(rand_calls=rc.value, errors=e)
+
+    def glibc_rand(self, n):
+        out = np.zeros(n, np.int32)
+        self.lib.orc_glibc_rand(int(n), out.ctypes.data_as(i32p))
+        return out
+
     def icp(self, src, tgt, T0, max_dist, max_it, eps):
         s, sp = _f(src); t, tp = _f(tgt)
         T0c = np.ascontiguousarray(np.asarray(T0, np.float32).T)

@@ -303,6 +303,38 @@ def test_ransac_degenerate(ctx, oracle, tiny_stages):
     assert_same_bits(gT, wT, "transform (random correspondences)")
 
 
+# ---------------------------------------------------------------- SAC_IA
+def test_sac_ia_bit_exact(ctx, oracle, tiny_stages):
+    s, t = tiny_stages
+    calls = 0
+    for its in (60, 200):
+        wT, wdbg = oracle.sac_ia(s["kp"], s["desc"], t["kp"], t["desc"], 0.5, 1.0, its, rand_calls=calls)
+        gT, gdbg = ctx.sac_ia(s["kp"], s["desc"], t["kp"], t["desc"], 0.5, 1.0, its, rand_calls=calls)
+        assert gdbg["rand_calls"] == wdbg["rand_calls"]
+        assert_same_bits(gdbg["errors"], wdbg["errors"], "per-iteration error metric")
+        assert_same_bits(gT, wT, "SAC-IA transform")
+        calls = wdbg["rand_calls"]  # the second call continues the rand() stream like a second pair would
+    # degenerate sets: fewer than 3 source keypoints -> the identity guess is returned
+    gT, gdbg = ctx.sac_ia(s["kp"][:2], s["desc"][:2], t["kp"], t["desc"], 0.5, 1.0, 10)
+    assert np.array_equal(gT, np.eye(4, dtype=np.float32))
+
+
+def test_sac_ia_pipeline_matches_oracle(ctx, mm, oracle, small_maps):
+    import oracle_py
+    maps, truth = small_maps
+    want = oracle.estimate_maps_transforms(maps, oracle_py.default_params(descriptor_type=2, estimation_method=1, max_iterations=100))
+    p = mm.default_params(descriptor_type="FPFH", estimation_method="SAC_IA", max_iterations=100)
+    dm = ctx.maps_upload(maps)
+    f = ctx.features_compute(dm, 0, len(maps), p)
+    # a split pair list still sees the single rand() stream of the whole row-major list
+    T1, c1, _ = ctx.register_pairs(f, [[0, 1], [0, 2]], p)
+    T2, c2, _ = ctx.register_pairs(f, [[1, 2]], p)
+    np.testing.assert_array_equal(np.concatenate([T1, T2]), want["pair_T"])
+    np.testing.assert_array_equal(np.concatenate([c1, c2]), want["pair_conf"])
+    got = ctx.estimate_maps_transforms(maps, p)
+    np.testing.assert_allclose(got, want["transforms"], rtol=0, atol=1e-5)
+
+
 # ---------------------------------------------------------------- K11 ICP / K12 score
 def _truth_pair(tiny_maps):
     _, truth = tiny_maps
