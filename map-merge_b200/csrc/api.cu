@@ -119,7 +119,8 @@ void compute_features(Ctx& c, const std::vector<CloudView>& raw, const mm3d_para
 
   tm.begin();
   std::vector<DCloud> resized;
-  voxel_downsample_batch(c, raw, leaf, resized, nullptr);
+  std::vector<VoxGeom> vgeom;
+  voxel_downsample_batch(c, raw, leaf, resized, &vgeom);
   tm.end(0);
 
   tm.begin();
@@ -128,7 +129,7 @@ void compute_features(Ctx& c, const std::vector<CloudView>& raw, const mm3d_para
   std::vector<DCloud> filtered;
   {
     std::vector<DIndex> idx;
-    build_index_batch(c, rv, leaf, 2, 0, 0, idx);
+    build_index_batch(c, rv, leaf, 2, 0, 0, idx, nullptr, &vgeom);
     remove_outliers_batch(c, rv, idx, p.descriptor_radius, p.outliers_min_neighbours, filtered, nullptr);
   }
   tm.end(1);
@@ -137,7 +138,7 @@ void compute_features(Ctx& c, const std::vector<CloudView>& raw, const mm3d_para
   std::vector<CloudView> fv(M);
   for (int m = 0; m < M; ++m) fv[m] = filtered[m].view();
   std::vector<DIndex> idx;
-  build_index_batch(c, fv, leaf, 2, 0, 0, idx);
+  build_index_batch(c, fv, leaf, 2, 0, 0, idx, nullptr, &vgeom);
   std::vector<DBuf<float4>> normals;
   normals_batch(c, fv, idx, p.normal_radius, normals);
   tm.end(2);

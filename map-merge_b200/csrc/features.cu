@@ -47,15 +47,15 @@ struct OutlierJob {
   int* counts;      // optional
 };
 
+// thread per point (a warp-per-point version with the flattened walk was measured: 1.9x slower, the visitor is too cheap)
 __global__ void __launch_bounds__(FB) outlier_kernel(const OutlierJob* __restrict__ jobs, float r2, int rv, int min_nb)
 {
   const OutlierJob& j = jobs[blockIdx.y];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = k < j.g.n;
-  const float4 q = live ? j.g.pts[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (k >= j.g.n) return;
+  const float4 q = j.g.pts[k];
   int cnt = 0;
-  for_each_in_radius(j.g, live, q.x, q.y, q.z, r2, rv, [&](int, const float4&, float) { ++cnt; });
-  if (!live) return;
+  for_each_in_radius(j.g, true, q.x, q.y, q.z, r2, rv, [&](int, const float4&, float) { ++cnt; });
   const int oi = j.g.orig ? j.g.orig[k] : k;
   j.flags[oi] = cnt > min_nb ? 1u : 0u;  // "k <= min_pts_radius_" is an outlier
   if (j.counts) j.counts[oi] = cnt;
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(FB) normals_kernel(const NormalJob* __restrict
 
 // ---------------------------------------------------------------- K5 SIFT
 struct SiftJob {
-  GridView g;
+  GridView g;       // for the scale-space kernel g.pts holds (x, y, z, intensity)
   float* dog;       // n x 5
   uint32_t* flags;  // n x 3 (levels 1..3)
 };
@@ -142,6 +142,22 @@ __device__ __forceinline__ float sift_intensity(float w)
   return (float)(299 * r + 587 * g + 114 * b) / 1000.0f;
 }
 
+// (x, y, z, rgba) -> (x, y, z, intensity): the scale-space walk visits every point ~300 times, so the intensity
+// (integer luma / 1000.0f, pcl::SIFTKeypointFieldSelector<PointXYZRGB>) is computed once per point
+struct SiftPrepJob {
+  const float4* src;
+  float4* dst;
+  int n;
+};
+__global__ void __launch_bounds__(256) sift_prep_kernel(const SiftPrepJob* __restrict__ jobs)
+{
+  const SiftPrepJob& j = jobs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= j.n) return;
+  const float4 p = j.src[i];
+  j.dst[i] = make_float4(p.x, p.y, p.z, sift_intensity(p.w));
+}
+
 __global__ void __launch_bounds__(FB) sift_scale_space_kernel(const SiftJob* __restrict__ jobs, SiftScales sc, float r2, int rv)
 {
   const SiftJob& j = jobs[blockIdx.y];
@@ -151,8 +167,9 @@ __global__ void __launch_bounds__(FB) sift_scale_space_kernel(const SiftJob* __r
   float num[6], den[6];
 #pragma unroll
   for (int s = 0; s < 6; ++s) { num[s] = 0.f; den[s] = 0.f; }
+  // (three nested walks with two scales each were measured: the extra walks cost more than the saved expf blocks)
   for_each_in_radius(j.g, live, q.x, q.y, q.z, r2, rv, [&](int, const float4& p, float d2) {
-    const float value = sift_intensity(p.w);
+    const float value = p.w;  // intensity, see sift_prep_kernel
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
       const float ss = sc.sigma_sqr[s];
@@ -173,62 +190,116 @@ __global__ void __launch_bounds__(FB) sift_scale_space_kernel(const SiftJob* __r
   }
 }
 
+// findScaleSpaceExtrema, warp per point: the warp gathers the candidates of a small sphere into shared memory,
+// ranks them by (d^2, index) with an all-pairs count (m is ~30-100), and reduces the DoG min / max of the 25 nearest
+// with shuffles.  If the sphere holds fewer than 25 points the radius grows and the gather is repeated.
+constexpr int EX_CAP = 384;  // candidates staged per warp
+
 __global__ void __launch_bounds__(FB) sift_extrema_kernel(const SiftJob* __restrict__ jobs, float min_contrast)
 {
+  __shared__ int queues[FB / 32][64];
+  __shared__ float cd[FB / 32][EX_CAP];
+  __shared__ int ci[FB / 32][EX_CAP];
   const SiftJob& j = jobs[blockIdx.y];
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = k < j.g.n;
-  const float4 q = live ? j.g.pts[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.x * (FB / 32) + w;
+  if (k >= j.g.n) return;  // warp-uniform
+  const float4 q = j.g.pts[k];
   constexpr int K = 25;
-  float bd[K];
-  int bi[K];
-  int cnt = 0;
-  int rv = 3;
   const int rv_max = max(max(j.g.div_v[0], j.g.div_v[1]), j.g.div_v[2]) + 2;
-  bool searching = live;
-  // every lane keeps calling the (warp-collective) walk until the whole warp is done
-  while (__any_sync(0xffffffffu, searching)) {
-    if (searching) cnt = 0;
+  int m = 0;
+  bool overflow = false;
+  for (int rv = 3;; rv = rv + max(1, rv / 3)) {
     const float rad = (float)rv * j.g.leaf;
-    for_each_in_radius(j.g, searching, q.x, q.y, q.z, rad * rad, rv + 1, [&](int idx, const float4&, float d2) {
-      if (cnt == K && !(d2 < bd[K - 1] || (d2 == bd[K - 1] && idx < bi[K - 1]))) return;
-      int pos = (cnt < K) ? cnt : K - 1;
-      while (pos > 0 && (d2 < bd[pos - 1] || (d2 == bd[pos - 1] && idx < bi[pos - 1]))) {
-        bd[pos] = bd[pos - 1];
-        bi[pos] = bi[pos - 1];
-        --pos;
+    int fill = 0;  // warp-uniform: passing candidates arrive in dense groups
+    m = warp_radius_query(j.g, q.x, q.y, q.z, rad * rad, rv + 1, queues[w], [&](int slot) {
+      // called with lanes 0..g-1 active; slot order is ascending
+      const int at = fill + lane;
+      if (at < EX_CAP) {
+        const float4 p = j.g.pts[slot];
+        cd[w][at] = em::dist2_3(q.x, q.y, q.z, p.x, p.y, p.z);
+        ci[w][at] = slot;
       }
-      bd[pos] = d2;
-      bi[pos] = idx;
-      if (cnt < K) ++cnt;
+      fill += 32;  // only exact for full groups; the final partial group is the last call
     });
-    if (searching) {
-      if (cnt == K || rv > rv_max) searching = false;
-      else rv *= 2;
-    }
+    __syncwarp();
+    if (m > EX_CAP) { overflow = true; break; }
+    if (m >= K || rv > rv_max) break;
   }
-  if (!live) return;
   float mn[5], mx[5];
 #pragma unroll
   for (int s = 0; s < 5; ++s) { mn[s] = 3.402823466e+38f; mx[s] = -3.402823466e+38f; }
-  for (int t = 0; t < cnt; ++t) {
-    const float* d = j.dog + (size_t)bi[t] * 5;
+  if (!overflow) {
+    // rank = number of candidates that sort before mine; ranks < 25 are the 25 nearest
+    for (int c = lane; c < m; c += 32) {
+      const float d = cd[w][c];
+      const int id = ci[w][c];
+      int rank = 0;
+      for (int o = 0; o < m; ++o) {
+        const float od = cd[w][o];
+        rank += (od < d || (od == d && ci[w][o] < id)) ? 1 : 0;
+      }
+      if (rank < K) {
+        const float* dg = j.dog + (size_t)id * 5;
 #pragma unroll
-    for (int s = 0; s < 5; ++s) {
-      const float v = d[s];
-      mn[s] = fminf(mn[s], v);
-      mx[s] = fmaxf(mx[s], v);
+        for (int s = 0; s < 5; ++s) {
+          const float v = dg[s];
+          mn[s] = fminf(mn[s], v);
+          mx[s] = fmaxf(mx[s], v);
+        }
+      }
+    }
+  } else if (lane == 0) {
+    // rare: a neighbourhood too crowded for the staging buffer -> sequential insertion list on one lane
+    float bd[K];
+    int bi[K];
+    int cnt = 0, rv = 3;
+    for (;;) {
+      cnt = 0;
+      const float rad = (float)rv * j.g.leaf;
+      for_each_in_radius(j.g, true, q.x, q.y, q.z, rad * rad, rv + 1, [&](int idx, const float4&, float d2) {
+        if (cnt == K && !(d2 < bd[K - 1] || (d2 == bd[K - 1] && idx < bi[K - 1]))) return;
+        int pos = (cnt < K) ? cnt : K - 1;
+        while (pos > 0 && (d2 < bd[pos - 1] || (d2 == bd[pos - 1] && idx < bi[pos - 1]))) {
+          bd[pos] = bd[pos - 1];
+          bi[pos] = bi[pos - 1];
+          --pos;
+        }
+        bd[pos] = d2;
+        bi[pos] = idx;
+        if (cnt < K) ++cnt;
+      });
+      if (cnt == K || rv > rv_max) break;
+      rv *= 2;
+    }
+    for (int t = 0; t < cnt; ++t) {
+      const float* dg = j.dog + (size_t)bi[t] * 5;
+#pragma unroll
+      for (int s = 0; s < 5; ++s) {
+        mn[s] = fminf(mn[s], dg[s]);
+        mx[s] = fmaxf(mx[s], dg[s]);
+      }
     }
   }
 #pragma unroll
-  for (int s = 1; s < 4; ++s) {
-    const float val = j.dog[(size_t)k * 5 + s];
-    uint32_t f = 0;
-    if (fabsf(val) >= min_contrast) {
-      if ((val == mn[s]) && (val < mn[s - 1]) && (val < mn[s + 1])) f = 1;
-      else if ((val == mx[s]) && (val > mx[s - 1]) && (val > mx[s + 1])) f = 1;
+  for (int s = 0; s < 5; ++s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[s] = fminf(mn[s], __shfl_xor_sync(0xffffffffu, mn[s], o));
+      mx[s] = fmaxf(mx[s], __shfl_xor_sync(0xffffffffu, mx[s], o));
     }
-    j.flags[(size_t)k * 3 + (s - 1)] = f;
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 1; s < 4; ++s) {
+      const float val = j.dog[(size_t)k * 5 + s];
+      uint32_t f = 0;
+      if (fabsf(val) >= min_contrast) {
+        if ((val == mn[s]) && (val < mn[s - 1]) && (val < mn[s + 1])) f = 1;
+        else if ((val == mx[s]) && (val > mx[s - 1]) && (val > mx[s + 1])) f = 1;
+      }
+      j.flags[(size_t)k * 3 + (s - 1)] = f;
+    }
   }
 }
 
@@ -270,41 +341,44 @@ __global__ void __launch_bounds__(FB) fpfh_mark_kernel(const FpfhJob* __restrict
   for_each_in_radius(j.g, live, q.x, q.y, q.z, r2, rv, [&](int k, const float4&, float) { j.need[k] = 1u; });
 }
 
+// warp per surface point: candidates that pass the radius test are queued so that the pair-feature block always
+// runs with full warps; votes are shared-memory atomics on the warp's 33 counters (every vote of one histogram
+// adds the same float, so a bin's value depends only on its vote count: the additions are replayed at the end).
 __global__ void __launch_bounds__(FB) spfh_kernel(const FpfhJob* __restrict__ jobs, float r2, int rv, BinTable bins)
 {
-  __shared__ unsigned short cnt[33 * FB];
+  __shared__ int queues[FB / 32][64];
+  __shared__ unsigned short cnt[FB / 32][33][32];  // private counters per lane: no atomics, no bank conflicts
   __shared__ float thr[3][12];
   if (threadIdx.x < 36) (&thr[0][0])[threadIdx.x] = (&bins.t[0][0])[threadIdx.x];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = 0; b < 33; ++b) cnt[w][b][lane] = 0;
   __syncthreads();
   const FpfhJob& j = jobs[blockIdx.y];
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = k < j.g.n && j.need[k];
-  for (int b = 0; b < 33; ++b) cnt[b * FB + threadIdx.x] = 0;
-  const float4 p = live ? j.g.pts[k] : make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 np = live ? j.normals[j.g.orig ? j.g.orig[k] : k] : make_float4(0.f, 0.f, 0.f, 0.f);
-  int n = 0;
-  for_each_in_radius(j.g, live, p.x, p.y, p.z, r2, rv, [&](int q, const float4& pq, float) {
-    ++n;
+  const int k = blockIdx.x * (FB / 32) + w;
+  if (k >= j.g.n || !j.need[k]) return;  // warp-uniform
+  const float4 p = j.g.pts[k];
+  const float4 np = j.normals[j.g.orig ? j.g.orig[k] : k];
+  const int n = warp_radius_query(j.g, p.x, p.y, p.z, r2, rv, queues[w], [&](int q) {
     if (q == k) return;
+    const float4 pq = j.g.pts[q];
     const float4 nq = j.normals[j.g.orig ? j.g.orig[q] : q];
     float f1, f2, f3;
     pair_features(p, np, pq, nq, &f1, &f2, &f3);
     const int h1 = lookup_bin(thr[0], 11, f1, 11.0f * 0.15915494f, 3.14159274f);
     const int h2 = lookup_bin(thr[1], 11, f2, 5.5f, 1.0f);
     const int h3 = lookup_bin(thr[2], 11, f3, 5.5f, 1.0f);
-    cnt[h1 * FB + threadIdx.x]++;
-    cnt[(11 + h2) * FB + threadIdx.x]++;
-    cnt[(22 + h3) * FB + threadIdx.x]++;
+    cnt[w][h1][lane]++;
+    cnt[w][11 + h2][lane]++;
+    cnt[w][22 + h3][lane]++;
   });
-  if (!live) return;
-  // every increment of one histogram is the same float, so a bin's value depends
-  // only on its vote count: replay the additions.
+  __syncwarp();
   const float hist_incr = 100.0f / (float)(n - 1);
   float* out = j.spfh + (size_t)k * 33;
-  for (int b = 0; b < 33; ++b) {
-    const int c = cnt[b * FB + threadIdx.x];
+  for (int b = lane; b < 33; b += 32) {
+    unsigned int c = 0;
+    for (int l = 0; l < 32; ++l) c += cnt[w][b][(l + lane) & 31];
     float h = 0.f;
-    for (int t = 0; t < c; ++t) h += hist_incr;
+    for (unsigned int t = 0; t < c; ++t) h += hist_incr;
     out[b] = h;
   }
 }
@@ -667,7 +741,8 @@ void sift_batch(Ctx& c, const std::vector<CloudView>& clouds, float min_scale, i
     for (int m = 0; m < M; ++m) in[m] = active[m] ? cur[m] : CloudView{nullptr, 0};
     keep_alive.emplace_back();
     std::vector<DCloud>& oc = keep_alive.back();
-    voxel_downsample_batch(c, in, s, oc, nullptr);
+    std::vector<VoxGeom> ogeom;
+    voxel_downsample_batch(c, in, s, oc, &ogeom);
     bool any = false;
     std::vector<CloudView> ov(M);
     for (int m = 0; m < M; ++m) {
@@ -678,7 +753,7 @@ void sift_batch(Ctx& c, const std::vector<CloudView>& clouds, float min_scale, i
     }
     if (!any) break;
     std::vector<DIndex> idx;
-    build_index_batch(c, ov, s, 2, 0, 0, idx);
+    build_index_batch(c, ov, s, 2, 0, 0, idx, nullptr, &ogeom);
     // scales[i] = base * 2^((i-1)/3), i = 0..5 ; sigma^2 = powf(scale, 2)
     float scales[6];
     SiftScales sc;
@@ -705,10 +780,23 @@ void sift_batch(Ctx& c, const std::vector<CloudView>& clouds, float min_scale, i
     DBuf<SiftJob> dj = to_device(c, jobs);
     const int mx = max_n(ov);
     const dim3 grid((mx + FB - 1) / FB, M);
+    // intensity-carrying copy of the octave clouds for the scale-space walk (the index must be in identity order)
+    std::vector<DBuf<float4>> pi(M);
+    std::vector<SiftPrepJob> pj(M);
+    std::vector<SiftJob> jobs_ss = jobs;
+    for (int m = 0; m < M; ++m) {
+      if (idx[m].v.orig) throw std::runtime_error("sift_batch: octave cloud is not in voxel order");
+      pi[m].alloc(c, ns[m]);
+      pj[m] = SiftPrepJob{ov[m].pts, pi[m].p, ns[m]};
+      jobs_ss[m].g.pts = pi[m].p;
+    }
+    DBuf<SiftPrepJob> dpj = to_device(c, pj);
+    MM_LAUNCH(c, sift_prep_kernel, dim3((mx + 255) / 256, M), 256, 0, dpj.p);
+    DBuf<SiftJob> djs = to_device(c, jobs_ss);
     { double b = 0; for (int m = 0; m < M; ++m) b += 36.0 * ns[m]; MM_BYTES(c, b); }
-    MM_LAUNCH(c, sift_scale_space_kernel, grid, FB, 0, dj.p, sc, r2, rv);
+    MM_LAUNCH(c, sift_scale_space_kernel, grid, FB, 0, djs.p, sc, r2, rv);
     { double b = 0; for (int m = 0; m < M; ++m) b += 48.0 * ns[m]; MM_BYTES(c, b); }
-    MM_LAUNCH(c, sift_extrema_kernel, grid, FB, 0, dj.p, min_contrast);
+    MM_LAUNCH(c, sift_extrema_kernel, dim3((mx + FB / 32 - 1) / (FB / 32), M), FB, 0, dj.p, min_contrast);
     std::vector<int> totals;
     scan_flags_batch(c, flags.p, pos.p, segs3, totals);
     std::vector<SiftEmitJob> ej(M);
@@ -781,7 +869,7 @@ void fpfh_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<
   MM_LAUNCH(c, fpfh_mark_kernel, dim3((mxk + FB - 1) / FB, M), FB, 0, dj.p, r2, rv);
   { double b = 0; for (int m = 0; m < M; ++m) b += (32.0 + 132.0 + 4.0) * clouds[m].n; MM_BYTES(c, b); }
   static const BinTable bins = make_bin_table(11);
-  MM_LAUNCH(c, spfh_kernel, dim3((mx + FB - 1) / FB, M), FB, 0, dj.p, r2, rv, bins);
+  MM_LAUNCH(c, spfh_kernel, dim3((mx + FB / 32 - 1) / (FB / 32), M), FB, 0, dj.p, r2, rv, bins);
   { double b = 0; for (int m = 0; m < M; ++m) b += (16.0 + 132.0) * clouds[m].n + (16.0 + 132.0) * nks[m]; MM_BYTES(c, b); }
   MM_LAUNCH(c, fpfh_weight_kernel, dim3((mxk * 3 + FB - 1) / FB, M), FB, 0, dj.p, r2, rv);
   DBuf<uint32_t> flags(c, totalk), pos(c, totalk);

@@ -227,6 +227,103 @@ __device__ __forceinline__ void for_each_in_radius(const GridView& g, bool live,
   }
 }
 
+// Warp-cooperative radius query: the 32 lanes of a warp serve ONE query (all lanes pass the same arguments).
+// Lanes look the (z, y) rows of the window up in parallel (32 rows per round), the rows' runs are flattened with a
+// warp scan so that 32 consecutive candidates are tested per step, and the candidates that pass d^2 < r2 are
+// compacted (in ascending index order) through a small shared-memory queue, so `visit` always runs with full warps.
+//   visit(slot)           called by every lane that has a passing candidate `slot` (dense: lanes 0..m-1)
+//   returns the number of candidates that passed
+// queue: 64 ints of shared memory owned by this warp.
+template <typename F>
+__device__ __forceinline__ int warp_radius_query(const GridView& g, float qx, float qy, float qz, float r2, int rv, int* queue, F visit)
+{
+  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  const int vx = floor_to_int(qx * g.inv_leaf) - g.min_b[0];
+  const int vy = floor_to_int(qy * g.inv_leaf) - g.min_b[1];
+  const int vz = floor_to_int(qz * g.inv_leaf) - g.min_b[2];
+  int zlo = vz - rv, zhi = vz + rv, ylo = vy - rv, yhi = vy + rv;
+  if (zhi < 0 || yhi < 0 || vx + rv < 0 || zlo >= g.div_v[2] || ylo >= g.div_v[1] || vx - rv >= g.div_v[0]) return 0;
+  zlo = max(zlo, 0) >> g.shift[2];
+  zhi = min(zhi, g.div_v[2] - 1) >> g.shift[2];
+  ylo = max(ylo, 0) >> g.shift[1];
+  yhi = min(yhi, g.div_v[1] - 1) >> g.shift[1];
+  const int ny = yhi - ylo + 1;
+  const int n_rows = (zhi - zlo + 1) * ny;
+  const float r2v = r2 * g.inv_leaf * g.inv_leaf;
+  int qcount = 0, passed = 0;
+  for (int row0 = 0; row0 < n_rows; row0 += 32) {
+    // each lane resolves one row to its candidate run [s, e)
+    int s = 0, e = 0;
+    const int row = row0 + lane;
+    if (row < n_rows) {
+      const int cz = zlo + row / ny, cy = ylo + row % ny;
+      const int z0 = cz << g.shift[2], z1 = z0 + (1 << g.shift[2]) - 1;
+      const int y0 = cy << g.shift[1], y1 = y0 + (1 << g.shift[1]) - 1;
+      const float fz = (float)max(max(max(z0 - vz, vz - z1), 0) - 1, 0);
+      const float fy = (float)max(max(max(y0 - vy, vy - y1), 0) - 1, 0);
+      const float rem = r2v - fz * fz - fy * fy;
+      if (rem >= 0.0f) {
+        const int rx = (int)sqrtf(rem) + 2;
+        int xlo = vx - rx, xhi = vx + rx;
+        if (xhi >= 0 && xlo < g.div_v[0]) {
+          xlo = max(xlo, 0) >> g.shift[0];
+          xhi = min(xhi, g.div_v[0] - 1) >> g.shift[0];
+          const int base = (cz * g.dim[1] + cy) * g.dim[0];
+          s = g.cell_start[base + xlo];
+          e = g.cell_start[base + xhi + 1];
+        }
+      }
+    }
+    // inclusive scan of the run lengths
+    int incl = e - s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(full, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(full, incl, 31);
+    const int excl = incl - (e - s);
+    for (int t0 = 0; t0 < total; t0 += 32) {
+      const int t = t0 + lane;
+      // owner row of flattened candidate t: smallest L with incl[L] > t
+      int L = 0;
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1) {
+        const int v = __shfl_sync(full, incl, L + step - 1);
+        if (v <= t) L += step;
+      }
+      L = min(L, 31);
+      const int ls = __shfl_sync(full, s, L), le = __shfl_sync(full, excl, L);
+      bool pass = false;
+      int k = 0;
+      if (t < total) {
+        k = ls + (t - le);
+        const float4 p = g.pts[k];
+        pass = em::dist2_3(qx, qy, qz, p.x, p.y, p.z) < r2;
+      }
+      const unsigned m = __ballot_sync(full, pass);
+      if (pass) queue[qcount + __popc(m & ((1u << lane) - 1u))] = k;
+      qcount += __popc(m);
+      passed += __popc(m);
+      __syncwarp();
+      if (qcount >= 32) {
+        visit(queue[lane]);
+        __syncwarp();
+        const int rest = qcount - 32;
+        const int moved = (lane < rest) ? queue[32 + lane] : 0;
+        __syncwarp();
+        if (lane < rest) queue[lane] = moved;
+        qcount = rest;
+        __syncwarp();
+      }
+    }
+  }
+  if (lane < qcount) visit(queue[lane]);
+  __syncwarp();
+  return passed;
+}
+
 // Nearest neighbour among points with (double)d2 <= bound; ties -> lower
 // original index.  Rows are visited outward from the query row so the running
 // best prunes the rest.  rv = ceil(sqrt(bound) / leaf) + 1 voxels.
@@ -316,8 +413,10 @@ void scan_flags_batch(Ctx& c, const uint32_t* flags, uint32_t* pos, const std::v
 
 // voxel.cu — K1
 void voxel_downsample_batch(Ctx& c, const std::vector<CloudView>& in, float leaf, std::vector<DCloud>& out, std::vector<VoxGeom>* geom);
+// geom_hint: voxel geometry (same leaf) of a cloud that contains these points, e.g. the voxel grid they came out of;
+// saves the bounding-box pass and one host synchronisation
 void build_index_batch(Ctx& c, const std::vector<CloudView>& clouds, float leaf, int sx, int sy, int sz, std::vector<DIndex>& out,
-                       std::vector<int>* was_sorted = nullptr);
+                       std::vector<int>* was_sorted = nullptr, const std::vector<VoxGeom>* geom_hint = nullptr);
 void transform_concat(Ctx& c, const std::vector<CloudView>& in, const std::vector<const float*>& transforms_rowmajor_host, DCloud& out);
 
 // features.cu — K3, K4, K5, K7

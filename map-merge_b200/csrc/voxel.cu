@@ -349,7 +349,7 @@ void voxel_downsample_batch(Ctx& c, const std::vector<CloudView>& in, float leaf
 }
 
 void build_index_batch(Ctx& c, const std::vector<CloudView>& clouds, float leaf, int sx, int sy, int sz, std::vector<DIndex>& out,
-                       std::vector<int>* was_sorted)
+                       std::vector<int>* was_sorted, const std::vector<VoxGeom>* geom_hint)
 {
   const int M = (int)clouds.size();
   out.clear();
@@ -378,7 +378,12 @@ void build_index_batch(Ctx& c, const std::vector<CloudView>& clouds, float leaf,
   DBuf<CloudView> dviews = to_device(c, clouds);
   std::vector<VoxGeom> geom;
   DBuf<VoxGeom> dgeom;
-  compute_geom(c, clouds, dviews, leaf, geom, dgeom);
+  bool hinted = geom_hint && (int)geom_hint->size() == M;
+  if (hinted)
+    for (int m = 0; m < M; ++m)
+      if (clouds[m].n > 0 && ((*geom_hint)[m].passthrough || (*geom_hint)[m].div_b[0] <= 0)) hinted = false;
+  if (hinted) geom = *geom_hint;
+  else compute_geom(c, clouds, dviews, leaf, geom, dgeom);
   std::vector<IndexGeom> ig(M);
   for (int m = 0; m < M; ++m) {
     if (geom[m].passthrough && clouds[m].n > 0) throw std::runtime_error("build_index: leaf too small for the cloud extent");
