@@ -36,6 +36,7 @@ struct IcpJob {
   float4* work;      // transformed source (input_transformed)
   long long* sums;   // NSUM
   IcpState* st;
+  int* ticket;       // blocks of this pair that finished the current iteration
   float t0[16];      // initial guess, row-major
   long long* sums_log;  // optional max_log x NSUM
 };
@@ -68,46 +69,6 @@ __device__ __forceinline__ void block_accumulate(long long* vals, int nvals, lon
   }
 }
 
-// the step transform of the previous iteration is applied on the fly
-// (transformCloud(input_transformed, input_transformed, transformation_))
-__global__ void __launch_bounds__(IB) icp_accumulate_kernel(const IcpJob* __restrict__ jobs, double max_dist_sqr, int rv, int apply_step)
-{
-  const IcpJob& j = jobs[blockIdx.y];
-  if (!j.st->active) return;
-  if (blockIdx.x * IB >= j.ns) return;
-  long long v[NSUM];
-#pragma unroll
-  for (int k = 0; k < NSUM; ++k) v[k] = 0;
-  const int i = blockIdx.x * IB + threadIdx.x;
-  if (i < j.ns) {
-    float4 p = j.work[i];
-    if (apply_step) {
-      float4 o;
-      em::transform_point(j.st->step, p.x, p.y, p.z, &o.x, &o.y, &o.z);
-      o.w = p.w;
-      p = o;
-      j.work[i] = p;
-    }
-    int idx;
-    float d2;
-    float4 q;
-    if (nearest_bounded(j.tgt, p.x, p.y, p.z, max_dist_sqr, rv, &idx, &d2, &q)) {
-      const double pp[3] = {(double)p.x, (double)p.y, (double)p.z};
-      const double qq[3] = {(double)q.x, (double)q.y, (double)q.z};
-      v[0] = 1;
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        v[1 + a] = em::to_fix(pp[a], MM3D_FIX1_SCALE);
-        v[4 + a] = em::to_fix(qq[a], MM3D_FIX1_SCALE);
-#pragma unroll
-        for (int b = 0; b < 3; ++b) v[7 + a * 3 + b] = em::to_fix(qq[a] * pp[b], MM3D_FIX2_SCALE);
-      }
-      v[16] = em::to_fix((double)d2, MM3D_FIXD_SCALE);
-    }
-  }
-  block_accumulate(v, NSUM, j.sums);
-}
-
 __device__ void mat4_mul(const float* a, const float* b, float* r)
 {
   for (int i = 0; i < 4; ++i)
@@ -120,18 +81,15 @@ __device__ void mat4_mul(const float* a, const float* b, float* r)
     }
 }
 
-__global__ void __launch_bounds__(32) icp_solve_kernel(const IcpJob* __restrict__ jobs, int n_jobs, int max_iterations, double rotation_threshold,
-                                                      double translation_threshold, int max_log, int* __restrict__ n_active)
+// Umeyama from the finished reductions, transform update and pcl::registration::DefaultConvergenceCriteria for one pair;
+// runs on one thread of the LAST block of that pair to finish (so an ICP iteration is a single kernel)
+__device__ void icp_solve(const IcpJob& j, int max_iterations, double rotation_threshold, double translation_threshold, int max_log,
+                          int* __restrict__ n_active)
 {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_jobs) return;
-  const IcpJob& j = jobs[p];
   IcpState& st = *j.st;
-  if (!st.active) return;
   long long s[NSUM];
   for (int k = 0; k < NSUM; ++k) {
-    s[k] = j.sums[k];
-    j.sums[k] = 0;
+    s[k] = (long long)atomicExch((unsigned long long*)&j.sums[k], 0ull);  // read the other blocks' atomics, reset for the next iteration
   }
   if (j.sums_log && st.iterations < max_log)
     for (int k = 0; k < NSUM; ++k) j.sums_log[(size_t)st.iterations * NSUM + k] = s[k];
@@ -182,6 +140,62 @@ __global__ void __launch_bounds__(32) icp_solve_kernel(const IcpJob* __restrict_
     st.active = 0;
     st.converged = 1;
     atomicSub(n_active, 1);
+  }
+}
+
+// the step transform of the previous iteration is applied on the fly
+// (transformCloud(input_transformed, input_transformed, transformation_))
+__global__ void __launch_bounds__(IB) icp_iteration_kernel(const IcpJob* __restrict__ jobs, double max_dist_sqr, int rv, int apply_step,
+                                                           int max_iterations, double rotation_threshold, double translation_threshold,
+                                                           int max_log, int* __restrict__ n_active)
+{
+  const IcpJob& j = jobs[blockIdx.y];
+  if (!j.st->active) return;
+  if (blockIdx.x * IB >= j.ns) return;
+  long long v[NSUM];
+#pragma unroll
+  for (int k = 0; k < NSUM; ++k) v[k] = 0;
+  const int i = blockIdx.x * IB + threadIdx.x;
+  if (i < j.ns) {
+    float4 p = j.work[i];
+    if (apply_step) {
+      float4 o;
+      em::transform_point(j.st->step, p.x, p.y, p.z, &o.x, &o.y, &o.z);
+      o.w = p.w;
+      p = o;
+      j.work[i] = p;
+    }
+    int idx;
+    float d2;
+    float4 q;
+    if (nearest_bounded(j.tgt, p.x, p.y, p.z, max_dist_sqr, rv, &idx, &d2, &q)) {
+      const double pp[3] = {(double)p.x, (double)p.y, (double)p.z};
+      const double qq[3] = {(double)q.x, (double)q.y, (double)q.z};
+      v[0] = 1;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        v[1 + a] = em::to_fix(pp[a], MM3D_FIX1_SCALE);
+        v[4 + a] = em::to_fix(qq[a], MM3D_FIX1_SCALE);
+#pragma unroll
+        for (int b = 0; b < 3; ++b) v[7 + a * 3 + b] = em::to_fix(qq[a] * pp[b], MM3D_FIX2_SCALE);
+      }
+      v[16] = em::to_fix((double)d2, MM3D_FIXD_SCALE);
+    }
+  }
+  block_accumulate(v, NSUM, j.sums);
+  // last block of this pair: solve + convergence test
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int nblocks = (j.ns + IB - 1) / IB;
+    const int ticket = atomicAdd(j.ticket, 1);
+    s_last = (ticket == nblocks - 1) ? 1 : 0;
+    if (s_last) {
+      *j.ticket = 0;
+      __threadfence();
+      icp_solve(j, max_iterations, rotation_threshold, translation_threshold, max_log, n_active);
+    }
   }
 }
 
@@ -252,6 +266,8 @@ void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<D
   DBuf<float4> work(c, tot + 1);
   DBuf<long long> sums(c, (size_t)A * NSUM);
   sums.zero(c);
+  DBuf<int> tickets(c, A);
+  tickets.zero(c);
   DBuf<long long> slog;
   if (max_log) {
     slog.alloc(c, (size_t)A * max_log * NSUM);
@@ -275,6 +291,7 @@ void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<D
     ij[a].work = work.p + off;
     ij[a].sums = sums.p + (size_t)a * NSUM;
     ij[a].st = dst.p + a;
+    ij[a].ticket = tickets.p + a;
     for (int k = 0; k < 16; ++k) ij[a].t0[k] = T0[act[a]][k];
     ij[a].sums_log = max_log ? slog.p + (size_t)a * max_log * NSUM : nullptr;
     off += (size_t)ij[a].ns;
@@ -292,8 +309,7 @@ void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<D
   int it = 0;
   while (n_active > 0 && it < std::max(max_it, 1)) {
     { double b = 0; for (int a = 0; a < A; ++a) b += 16.0 * ((double)ij[a].ns * (it > 0 ? 2 : 1) + ij[a].tgt.n); MM_BYTES(c, b * ((double)n_active / A)); }
-    MM_LAUNCH(c, icp_accumulate_kernel, grid, IB, 0, dij.p, max_dist_sqr, rv, it > 0 ? 1 : 0);
-    MM_LAUNCH(c, icp_solve_kernel, (A + 31) / 32, 32, 0, dij.p, A, max_it, 1.0 - eps, eps, max_log, dn_active.p);
+    MM_LAUNCH(c, icp_iteration_kernel, grid, IB, 0, dij.p, max_dist_sqr, rv, it > 0 ? 1 : 0, max_it, 1.0 - eps, eps, max_log, dn_active.p);
     dn_active.download(c, &n_active, 1);
     c.sync();
     ++it;
