@@ -72,6 +72,10 @@ void mm3d_free(void* p);
  * launching stream.  *json (mm3d_free) = [{"kernel", "launches", "ms", "algorithmic_bytes", "ms_annotated"}, ...]. */
 int mm3d_profile_begin(mm3d_ctx* ctx);
 int mm3d_profile_end(mm3d_ctx* ctx, char** json);
+/* Tensor-core k-NN bookkeeping since the context was created: out[0] = query rows processed, out[1] = early
+ * flushes (a row's candidate list filled up with ties and was evaluated exactly before the last tile), out[2] = columns that
+ * went through the exact FP32 distance. */
+int mm3d_knn_stats(mm3d_ctx* ctx, uint64_t* out);
 /* kernels launched through this context so far */
 long long mm3d_kernel_launches(mm3d_ctx* ctx);
 
@@ -160,6 +164,26 @@ void mm3d_features_free(mm3d_features* f);
  * stats (optional) = int32[n_pairs][4]: correspondences, RANSAC inliers, ICP iterations, ICP converged. */
 int mm3d_register_pairs(mm3d_ctx* ctx, const mm3d_features* f, int n_pairs, const int32_t* ij, const mm3d_params* params, float* transforms,
                         double* confidences, int32_t* stats);
+
+/* composeMaps (src/map_merging.cpp:277-305) sharded over ranks.  Per rank: begin (transform + concatenate its maps, local
+ * bounding box) -> all-reduce the box -> histogram of global voxel keys over n_buckets key ranges (returns 1 when
+ * pcl::VoxelGrid's overflow guard fires: the result is then the plain concatenation) -> all-reduce, pick splitters
+ * (splitters[r] <= bucket < splitters[r+1] goes to rank r) -> partition (stable; points_dev receives the points grouped by
+ * destination rank) -> all-to-all -> mm3d_downsample_dev on the received points.  Concatenating the ranks' outputs in rank
+ * order gives exactly mm3d_compose_maps' output. */
+typedef struct mm3d_shard mm3d_shard;
+int mm3d_compose_shard_begin(mm3d_ctx* ctx, int n_maps, const float* const* clouds, const uint64_t* n_points, const float* transforms,
+                             float* bbox, mm3d_shard** shard);
+int mm3d_compose_shard_size(const mm3d_shard* shard, uint64_t* n);
+int mm3d_compose_shard_histogram(mm3d_ctx* ctx, const mm3d_shard* shard, const float* global_bbox, double resolution, int n_buckets,
+                                 uint64_t* hist);
+int mm3d_compose_shard_partition(mm3d_ctx* ctx, const mm3d_shard* shard, const float* global_bbox, double resolution, int n_buckets, int n_ranks,
+                                 const int32_t* splitters, uint64_t* send_counts, void* points_dev);
+/* the rank's transformed, concatenated points (what the reference's output holds when the overflow guard fires) */
+int mm3d_compose_shard_points(mm3d_ctx* ctx, const mm3d_shard* shard, float** out, uint64_t* n_out);
+void mm3d_shard_free(mm3d_shard* shard);
+/* downSample of a device-resident cloud (points_dev = n x 4 floats in HBM); the result is returned on the host */
+int mm3d_downsample_dev(mm3d_ctx* ctx, const void* points_dev, uint64_t n, double resolution, float** out, uint64_t* n_out);
 
 /* Whole path on resident clouds; stage_ms (optional, 10 floats) = device time per stage in the order
  * downsampling, removing outliers, normals, keypoints, descriptors, correspondences, initial alignment,

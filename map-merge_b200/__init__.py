@@ -39,7 +39,8 @@ SYMBOLS = [
     "mm3d_keypoints", "mm3d_descriptors", "mm3d_match", "mm3d_ransac", "mm3d_icp", "mm3d_score", "mm3d_global_transforms",
     "mm3d_maps_upload", "mm3d_maps_free", "mm3d_features_compute", "mm3d_features_count", "mm3d_features_sizes",
     "mm3d_features_export_dev", "mm3d_features_import_dev", "mm3d_features_export_host", "mm3d_features_free",
-    "mm3d_register_pairs", "mm3d_estimate_resident", "mm3d_profile_begin", "mm3d_profile_end", "mm3d_sac_ia",
+    "mm3d_register_pairs", "mm3d_estimate_resident", "mm3d_profile_begin", "mm3d_profile_end", "mm3d_sac_ia", "mm3d_knn_stats", "mm3d_compose_shard_begin", "mm3d_compose_shard_size",
+    "mm3d_compose_shard_histogram", "mm3d_compose_shard_partition", "mm3d_compose_shard_points", "mm3d_shard_free", "mm3d_downsample_dev",
 ]
 
 
@@ -82,6 +83,8 @@ def lib():
         L.mm3d_maps_free.argtypes = [C.c_void_p]
         L.mm3d_features_free.argtypes = [C.c_void_p]
         L.mm3d_features_count.argtypes = [C.c_void_p]
+        L.mm3d_shard_free.argtypes = [C.c_void_p]
+        L.mm3d_compose_shard_size.argtypes = [C.c_void_p, u64p]
         _lib = L
     return _lib
 
@@ -154,6 +157,11 @@ class Context:
     @property
     def launches(self) -> int:
         return int(self.L.mm3d_kernel_launches(self.h))
+
+    def knn_stats(self):
+        out = (C.c_uint64 * 3)()
+        self._check(self.L.mm3d_knn_stats(self.h, out))
+        return dict(rows=int(out[0]), overflow_rows=int(out[1]), candidates=int(out[2]))  # rows, early flushes, exact evaluations
 
     def profile_begin(self):
         self._check(self.L.mm3d_profile_begin(self.h))
@@ -288,6 +296,44 @@ class Context:
             raise MM3DError("composeMaps: clouds and transforms size must be the same.")
         self._check(rc)
         return self._take(out, n.value * 4, np.float32, (-1, 4))
+
+    # ---- composeMaps sharded over ranks ----------------------------------------
+    def compose_shard_begin(self, clouds, transforms):
+        arrs, ptrs, ns = self._cloud_args(clouds)
+        T = np.asarray(transforms, np.float32).reshape(-1, 4, 4)
+        Tc = np.ascontiguousarray(T.transpose(0, 2, 1)) if len(T) else np.zeros((1, 16), np.float32)
+        bbox = np.zeros(6, np.float32); h = C.c_void_p()
+        self._check(self.L.mm3d_compose_shard_begin(self.h, len(clouds), ptrs, ns, Tc.ctypes.data_as(f32p), bbox.ctypes.data_as(f32p), C.byref(h)))
+        n = C.c_uint64()
+        self.L.mm3d_compose_shard_size(h, C.byref(n))
+        return bbox, h, int(n.value)
+
+    def compose_shard_histogram(self, shard, global_bbox, resolution, n_buckets=4096):
+        gb = np.ascontiguousarray(global_bbox, np.float32); hist = np.zeros(n_buckets, np.uint64)
+        rc = self._check(self.L.mm3d_compose_shard_histogram(self.h, shard, gb.ctypes.data_as(f32p), C.c_double(resolution), int(n_buckets),
+                                                             hist.ctypes.data_as(u64p)), ok=(0, 1))
+        return None if rc == 1 else hist
+
+    def compose_shard_partition(self, shard, global_bbox, resolution, splitters, out_dev_ptr, n_buckets=4096):
+        gb = np.ascontiguousarray(global_bbox, np.float32); sp = np.ascontiguousarray(splitters, np.int32)
+        n_ranks = len(sp) - 1
+        counts = np.zeros(n_ranks, np.uint64)
+        self._check(self.L.mm3d_compose_shard_partition(self.h, shard, gb.ctypes.data_as(f32p), C.c_double(resolution), int(n_buckets), n_ranks,
+                                                        sp.ctypes.data_as(i32p), counts.ctypes.data_as(u64p), C.c_void_p(int(out_dev_ptr))))
+        return counts.astype(np.int64)
+
+    def compose_shard_points(self, shard):
+        out = f32p(); no = C.c_uint64()
+        self._check(self.L.mm3d_compose_shard_points(self.h, shard, C.byref(out), C.byref(no)))
+        return self._take(out, no.value * 4, np.float32, (-1, 4))
+
+    def shard_free(self, shard):
+        self.L.mm3d_shard_free(shard)
+
+    def downsample_dev(self, dev_ptr, n, resolution):
+        out = f32p(); no = C.c_uint64()
+        self._check(self.L.mm3d_downsample_dev(self.h, C.c_void_p(int(dev_ptr)), C.c_uint64(int(n)), C.c_double(resolution), C.byref(out), C.byref(no)))
+        return self._take(out, no.value * 4, np.float32, (-1, 4))
 
     # ---- resident interface ---------------------------------------------------
     def maps_upload(self, clouds):

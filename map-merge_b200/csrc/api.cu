@@ -20,6 +20,10 @@ struct mm3d_maps {
   std::vector<DCloud> clouds;
 };
 
+struct mm3d_shard {
+  DCloud cloud;  // this rank's transformed points in (map, point) order
+};
+
 struct MapFeat {
   DCloud cloud;     // downsampled + outlier-filtered cloud (clouds_resized[i])
   DCloud keypoints;
@@ -710,6 +714,20 @@ int mm3d_global_transforms(int n_pairs, const int32_t* st, const float* transfor
   return MM3D_OK;
 }
 
+int mm3d_knn_stats(mm3d_ctx* ctx, uint64_t* out)
+{
+  if (!out) return MM3D_ERR_ARG;
+  MM_TRY(ctx)
+  out[0] = out[1] = out[2] = 0;
+  if (c.knn_stats) {
+    unsigned long long h[3];
+    MM_CUDA(cudaMemcpyAsync(h, c.knn_stats, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+    for (int i = 0; i < 3; ++i) out[i] = h[i];
+  }
+  MM_CATCH
+}
+
 int mm3d_profile_begin(mm3d_ctx* ctx)
 {
   MM_TRY(ctx)
@@ -754,6 +772,96 @@ int mm3d_profile_end(mm3d_ctx* ctx, char** json)
   out += "]";
   *json = (char*)malloc(out.size() + 1);
   memcpy(*json, out.c_str(), out.size() + 1);
+  MM_CATCH
+}
+
+// ---- composeMaps sharded over ranks --------------------------------------------
+
+int mm3d_compose_shard_begin(mm3d_ctx* ctx, int n_maps, const float* const* clouds, const uint64_t* n_points, const float* transforms,
+                             float* bbox, mm3d_shard** shard)
+{
+  if (!bbox || !shard) return MM3D_ERR_ARG;
+  *shard = nullptr;
+  MM_TRY(ctx)
+  std::vector<DCloud> d;
+  std::vector<std::vector<float>> tr;
+  for (int m = 0; m < n_maps; ++m) {
+    float rm[16];
+    from_colmajor(transforms + 16 * m, rm);
+    bool zero = true;
+    for (int k = 0; k < 16; ++k)
+      if (!(std::fabs(rm[k]) <= 1e-5f)) zero = false;
+    if (zero || !clouds[m] || n_points[m] == 0) continue;
+    d.push_back(upload_cloud(c, clouds[m], n_points[m]));
+    tr.emplace_back(rm, rm + 16);
+  }
+  std::vector<CloudView> v;
+  std::vector<const float*> tp;
+  for (size_t i = 0; i < d.size(); ++i) {
+    v.push_back(d[i].view());
+    tp.push_back(tr[i].data());
+  }
+  std::unique_ptr<mm3d_shard> s(new mm3d_shard);
+  transform_concat(c, v, tp, s->cloud);
+  compose_bbox(c, s->cloud, bbox);
+  *shard = s.release();
+  MM_CATCH
+}
+
+int mm3d_compose_shard_size(const mm3d_shard* shard, uint64_t* n)
+{
+  if (!shard || !n) return MM3D_ERR_ARG;
+  *n = (uint64_t)shard->cloud.n;
+  return MM3D_OK;
+}
+
+int mm3d_compose_shard_histogram(mm3d_ctx* ctx, const mm3d_shard* shard, const float* global_bbox, double resolution, int n_buckets,
+                                 uint64_t* hist)
+{
+  if (!shard || !global_bbox || !hist || n_buckets <= 0) return MM3D_ERR_ARG;
+  MM_TRY(ctx)
+  const KeyGeomHost g = compose_geometry(global_bbox, resolution, n_buckets);
+  if (g.passthrough) return 1;  // overflow guard of pcl::VoxelGrid: the composed map is the plain concatenation
+  std::vector<unsigned long long> h(n_buckets);
+  compose_histogram(c, shard->cloud, g, n_buckets, h.data());
+  for (int i = 0; i < n_buckets; ++i) hist[i] = h[i];
+  MM_CATCH
+}
+
+int mm3d_compose_shard_partition(mm3d_ctx* ctx, const mm3d_shard* shard, const float* global_bbox, double resolution, int n_buckets, int n_ranks,
+                                 const int32_t* splitters, uint64_t* send_counts, void* points_dev)
+{
+  if (!shard || !global_bbox || !splitters || !send_counts || n_ranks <= 0) return MM3D_ERR_ARG;
+  MM_TRY(ctx)
+  const KeyGeomHost g = compose_geometry(global_bbox, resolution, n_buckets);
+  std::vector<int> sp(splitters, splitters + n_ranks + 1);
+  std::vector<unsigned long long> cnt(n_ranks);
+  compose_partition(c, shard->cloud, g, n_buckets, sp, n_ranks, cnt.data(), (float4*)points_dev);
+  for (int r = 0; r < n_ranks; ++r) send_counts[r] = cnt[r];
+  MM_CATCH
+}
+
+int mm3d_compose_shard_points(mm3d_ctx* ctx, const mm3d_shard* shard, float** out, uint64_t* n_out)
+{
+  if (!shard || !out || !n_out) return MM3D_ERR_ARG;
+  MM_TRY(ctx)
+  *out = (float*)host_copy(c, shard->cloud.pts.p, (size_t)shard->cloud.n);
+  *n_out = (uint64_t)shard->cloud.n;
+  c.sync();
+  MM_CATCH
+}
+
+void mm3d_shard_free(mm3d_shard* shard) { delete shard; }
+
+int mm3d_downsample_dev(mm3d_ctx* ctx, const void* points_dev, uint64_t n, double resolution, float** out, uint64_t* n_out)
+{
+  if (!out || !n_out) return MM3D_ERR_ARG;
+  MM_TRY(ctx)
+  std::vector<DCloud> res;
+  voxel_downsample_batch(c, {CloudView{(const float4*)points_dev, (int)n}}, (float)resolution, res, nullptr);
+  *out = (float*)host_copy(c, res[0].pts.p, (size_t)res[0].n);
+  *n_out = (uint64_t)res[0].n;
+  c.sync();
   MM_CATCH
 }
 

@@ -6,7 +6,9 @@
 //        pcl::SampleConsensusModelRegistration, boost::mt19937(12345))
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 
 #include "mm3d_internal.cuh"
 
@@ -617,7 +619,20 @@ void match_batch(Ctx& c, const std::vector<const float*>& desc, const std::vecto
     max_ns = std::max(max_ns, ns);
   }
   DBuf<KnnJob> dkj = to_device(c, kj);
-  if (max_rows > 0) {
+  // default: the brute-force FP32 scan below (72 % of the FP32 issue peak on config 3).  MM3D_KNN=tc selects the tcgen05
+  // distance GEMM + exact re-rank (knn_tc.cu): bit-identical results, faster when descriptors are well separated, slower on
+  // tightly clustered ones (hundreds of columns inside the filter's error margin; measured in profiles/README.md).
+  const char* knn_env = std::getenv("MM3D_KNN");
+  const bool use_tc = knn_env && std::string(knn_env) == "tc";
+  if (max_rows > 0 && use_tc) {
+    std::vector<KnnProblem> probs;
+    for (int p = 0; p < P; ++p) {
+      const int a = jobs[p].a, b = jobs[p].b;
+      if (kj[2 * p].na > 0) probs.push_back(KnnProblem{a, b, kj[2 * p].na, kj[2 * p].k, kj[2 * p].idx, kj[2 * p].dist});
+      if (kj[2 * p + 1].na > 0) probs.push_back(KnnProblem{b, a, kj[2 * p + 1].na, kj[2 * p + 1].k, kj[2 * p + 1].idx, kj[2 * p + 1].dist});
+    }
+    knn_tc_batch(c, desc, nk, dim, probs);
+  } else if (max_rows > 0) {
     // the register kernel needs one k for the whole batch (k is clamped per job only when a set is smaller than k)
     bool uniform_k = true;
     for (const KnnJob& q : kj)

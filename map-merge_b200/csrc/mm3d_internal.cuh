@@ -44,6 +44,7 @@ struct Ctx {
   long long launches = 0;  // kernels launched through this context (bench.py's gpu_launches)
   bool profiling = false;
   double next_bytes = 0.0;
+  unsigned long long* knn_stats = nullptr;  // device: rows, rows that fell back to the exact scan, candidates re-ranked
   std::vector<KernelSample> samples;
   std::vector<cudaEvent_t> event_pool;
   void sync() { MM_CUDA(cudaStreamSynchronize(stream)); }
@@ -440,6 +441,16 @@ void shot_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<
 void pfh_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<const float4*>& normals,
                std::vector<DCloud>& keypoints, double radius, std::vector<DBuf<float>>& desc);
 
+// knn_tc.cu — K9 on tensor cores: per row of map a (the first na rows), the k nearest rows of map b, exact after re-rank
+struct KnnProblem {
+  int a, b;  // indices into desc / n_rows
+  int na;
+  int k;
+  int* idx;     // na x k
+  float* dist;  // na x k
+};
+void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vector<int>& n_rows, int D, const std::vector<KnnProblem>& probs);
+
 // matching.cu — K9, K10
 struct PairJob {
   int a, b;  // indices into the per-map arrays
@@ -483,6 +494,20 @@ void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<D
                std::vector<std::vector<long long>>* sums_dbg);
 void score_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<PairJob>& jobs,
                  const std::vector<const float*>& T_rowmajor, double max_range, std::vector<double>& scores);
+
+// compose.cu — composeMaps sharded over ranks
+struct KeyGeomHost {
+  float inv_leaf;
+  int min_b[3];
+  int div_b[3];
+  unsigned long long bucket_width;
+  int passthrough;
+};
+KeyGeomHost compose_geometry(const float* bbox, double resolution, int n_buckets);
+void compose_bbox(Ctx& c, const DCloud& cloud, float* bbox_host);
+void compose_histogram(Ctx& c, const DCloud& cloud, const KeyGeomHost& geom, int n_buckets, unsigned long long* hist_host);
+void compose_partition(Ctx& c, const DCloud& cloud, const KeyGeomHost& geom, int n_buckets, const std::vector<int>& splitters, int n_ranks,
+                       unsigned long long* counts_host, float4* out_dev);
 
 // graph.cpp — host pose graph (a14, a15)
 struct HostEstimate {

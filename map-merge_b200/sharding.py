@@ -56,3 +56,91 @@ def gather_pair_results(dist, torch, device, n_pairs: int, mine, T, conf):
     if n_pairs and dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(res)  # disjoint slots: the sum is a gather
     return res
+
+
+# ---- composeMaps sharded over ranks (map_merging.cpp:277-305) ------------------------------------------
+
+def choose_splitters(hist, world: int):
+    """Balanced key-range splitters from the all-reduced bucket histogram: int32[world + 1], splitters[r] <= bucket <
+    splitters[r + 1] goes to rank r.  Deterministic, identical on every rank."""
+    hist = np.asarray(hist, np.int64)
+    nb = len(hist)
+    cum = np.cumsum(hist)
+    total = int(cum[-1]) if nb else 0
+    sp = np.zeros(world + 1, np.int32)
+    sp[world] = nb
+    for r in range(1, world):
+        target = total * r // world
+        sp[r] = max(int(np.searchsorted(cum, target, side="left")) + (1 if total else 0), int(sp[r - 1]))
+        sp[r] = min(int(sp[r]), nb)
+    return sp
+
+
+class CtxShardOps:
+    """The per-rank steps of the sharded composeMaps on the CUDA library (include/mm3d.h, mm3d_compose_shard_*)."""
+
+    def __init__(self, ctx, torch, device):
+        self.ctx, self.torch, self.device = ctx, torch, device
+
+    def begin(self, clouds, transforms):
+        bbox, self.shard, n = self.ctx.compose_shard_begin(clouds, transforms)
+        return bbox, n
+
+    def histogram(self, gbbox, resolution, n_buckets):
+        return self.ctx.compose_shard_histogram(self.shard, gbbox, resolution, n_buckets)
+
+    def partition(self, gbbox, resolution, n_buckets, splitters, n):
+        send = self.torch.empty((max(n, 1), 4), dtype=self.torch.float32, device=self.device)
+        counts = self.ctx.compose_shard_partition(self.shard, gbbox, resolution, splitters, send.data_ptr(), n_buckets)
+        return send[:n], counts
+
+    def passthrough(self, n):
+        """all of this rank's transformed points, unfiltered (pcl::VoxelGrid's overflow guard fired)"""
+        return self.ctx.compose_shard_points(self.shard)
+
+    def downsample(self, recv, resolution):
+        self.torch.cuda.synchronize(self.device)
+        return self.ctx.downsample_dev(recv.data_ptr(), recv.shape[0], resolution)
+
+    def end(self):
+        self.ctx.shard_free(self.shard)
+
+
+def compose_sharded(ops, dist, torch, device, clouds_local, transforms_local, resolution, n_buckets: int = 4096):
+    """composeMaps with the maps spread over ranks.  Returns this rank's slice of the composed map (float32 [n, 4]); the
+    slices concatenated in rank order are bit-identical to the unsharded result.  The data path has exactly one
+    exchange step — an all-to-all of raw points by owning key range — preceded by two small all-reduces (bounding box,
+    key histogram)."""
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    bbox, n = ops.begin(clouds_local, transforms_local)
+    lo = torch.tensor(bbox[:3], dtype=torch.float32, device=device)
+    hi = torch.tensor(bbox[3:], dtype=torch.float32, device=device)
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    gbbox = np.concatenate([lo.cpu().numpy(), hi.cpu().numpy()]).astype(np.float32)
+    total = torch.tensor([n], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(total)
+    try:
+        if int(total.item()) == 0:
+            return np.zeros((0, 4), np.float32)
+        hist = ops.histogram(gbbox, resolution, n_buckets)
+        if hist is None:
+            return ops.passthrough(n)  # rank order = map order: the concatenation is the reference's output
+        h = torch.from_numpy(hist.astype(np.int64)).to(device)
+        if world > 1:
+            dist.all_reduce(h)
+        splitters = choose_splitters(h.cpu().numpy(), world)
+        send, counts = ops.partition(gbbox, resolution, n_buckets, splitters, n)
+        if world == 1:
+            return ops.downsample(send, resolution)
+        sc = torch.from_numpy(np.asarray(counts, np.int64)).to(device)
+        rc = torch.empty_like(sc)
+        dist.all_to_all_single(rc, sc)
+        recv_counts = [int(x) for x in rc.cpu().numpy()]
+        recv = torch.empty((sum(recv_counts), 4), dtype=torch.float32, device=device)
+        dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=recv_counts, input_split_sizes=[int(x) for x in counts])
+        return ops.downsample(recv, resolution)
+    finally:
+        ops.end()

@@ -115,3 +115,118 @@ def test_lpt_is_balanced_and_deterministic(mm):
     assert loads.max() / loads.mean() < 1.02
     assert sh.map_block(0, 8, 32) == (0, 4, 4) and sh.map_block(7, 8, 32) == (28, 4, 4)
     assert sh.map_block(2, 4, 5) == (4, 1, 2) and sh.map_block(3, 4, 5)[1] == 0
+
+
+# ---- composeMaps sharded over ranks -------------------------------------------------------------------------------------
+class OracleShardOps:
+    """The per-rank steps of sharding.compose_sharded restated on the CPU checker (numpy + oracle), so that the host logic
+    — box / histogram all-reduces, splitter choice, the all-to-all — runs under gloo without a GPU."""
+
+    def __init__(self, oracle, torch):
+        self.o, self.torch = oracle, torch
+
+    def begin(self, clouds, transforms):
+        r = self.o.compose_maps(clouds, transforms, 0.0) if len(clouds) else None  # leaf 0 -> transformed concatenation
+        self.pts = r if r is not None else np.zeros((0, 4), np.float32)
+        big = np.float32(np.finfo(np.float32).max)
+        if len(self.pts) == 0:
+            return np.array([big, big, big, -big, -big, -big], np.float32), 0
+        return np.concatenate([self.pts[:, :3].min(0), self.pts[:, :3].max(0)]).astype(np.float32), len(self.pts)
+
+    def _buckets(self, gbbox, resolution, n_buckets):
+        inv = np.float32(1.0) / np.float32(resolution)
+        ext = [int((gbbox[3 + k] - gbbox[k]) * inv) + 1 for k in range(3)]
+        if not resolution > 0 or ext[0] * ext[1] * ext[2] > 2**31 - 1:
+            return None
+        mn = [int(np.floor(gbbox[k] * inv)) for k in range(3)]
+        dv = [int(np.floor(gbbox[3 + k] * inv)) - mn[k] + 1 for k in range(3)]
+        width = max(1, -(-(dv[0] * dv[1] * dv[2]) // n_buckets))
+        ijk = [(np.floor(self.pts[:, k] * inv) - np.float32(mn[k])).astype(np.int64) for k in range(3)]
+        key = ijk[0] + ijk[1] * dv[0] + ijk[2] * dv[0] * dv[1]
+        return np.minimum(key // width, n_buckets - 1)
+
+    def histogram(self, gbbox, resolution, n_buckets):
+        b = self._buckets(gbbox, resolution, n_buckets)
+        return None if b is None else np.bincount(b, minlength=n_buckets).astype(np.uint64)
+
+    def partition(self, gbbox, resolution, n_buckets, splitters, n):
+        b = self._buckets(gbbox, resolution, n_buckets)
+        dest = np.searchsorted(np.asarray(splitters[1:-1]), b, side="right")
+        order = np.argsort(dest, kind="stable")
+        return self.torch.from_numpy(self.pts[order].copy()), np.bincount(dest, minlength=len(splitters) - 1)
+
+    def passthrough(self, n):
+        return self.pts
+
+    def downsample(self, recv, resolution):
+        return self.o.downsample(recv.numpy(), resolution)[0] if recv.shape[0] else np.zeros((0, 4), np.float32)
+
+    def end(self):
+        pass
+
+
+def _compose_case(seed, n_maps):
+    sys.path.insert(0, ROOT)
+    import mm3d_pkg
+    import importlib
+    mm3d_pkg.load()
+    synth = importlib.import_module("map_merge_b200.synth")
+    maps, truth = synth.make_maps(seed, n_maps, 6000, 20.0, 10.0, 2, 1)
+    T = np.stack([np.linalg.inv(truth[0]) @ t for t in truth]).astype(np.float32)
+    if n_maps > 2:
+        T[2] = 0  # a map that could not be placed is skipped (map_merging.cpp:293-295)
+    return maps, T
+
+
+def _compose_worker(rank, world, port, n_maps, resolution, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import torch.distributed as dist
+    import importlib
+    import oracle_py
+    maps, T = _compose_case(5, n_maps)
+    sh = importlib.import_module("map_merge_b200.sharding")
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        first, count, _per = sh.map_block(rank, world, n_maps)
+        ops = OracleShardOps(oracle_py.Oracle(), torch)
+        out = sh.compose_sharded(ops, dist, torch, torch.device("cpu"), maps[first:first + count], T[first:first + count], resolution)
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_maps,world,resolution", [(4, 2, 0.05), (3, 2, 0.2), (1, 2, 0.05), (4, 2, 1e-3)])
+def test_sharded_compose_matches_unsharded(oracle, n_maps, world, resolution):
+    import torch.multiprocessing as mp
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_compose_worker, args=(r, world, port, n_maps, resolution, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = dict(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    maps, T = _compose_case(5, n_maps)
+    want = oracle.compose_maps(maps, T, resolution)
+    got = np.concatenate([outs[r] for r in range(world)])
+    assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    if n_maps >= 3 and resolution > 1e-2:
+        sizes = [len(outs[r]) for r in range(world)]
+        assert min(sizes) > 0.3 * sum(sizes) / world  # the key-range splitters balance the ranks
+
+
+def test_choose_splitters(mm):
+    import importlib
+    sh = importlib.import_module("map_merge_b200.sharding")
+    h = np.zeros(64, np.int64); h[10:20] = 100
+    sp = sh.choose_splitters(h, 4)
+    assert sp[0] == 0 and sp[-1] == 64 and (np.diff(sp) >= 0).all()
+    loads = [h[sp[r]:sp[r + 1]].sum() for r in range(4)]
+    assert sum(loads) == 1000 and max(loads) <= 300
+    assert list(sh.choose_splitters(np.zeros(8, np.int64), 2)) == [0, 0, 8]
+    assert list(sh.choose_splitters(np.array([5]), 3)) == [0, 1, 1, 1]

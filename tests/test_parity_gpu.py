@@ -244,6 +244,55 @@ def test_match_bit_exact(ctx, oracle, tiny_stages):
     assert len(wp) > 10
 
 
+def test_tensor_core_knn_bit_exact(mm, oracle, tiny_stages, monkeypatch):
+    """MM3D_KNN=tc: the k-NN as a tcgen05 distance GEMM + exact re-rank (knn_tc.cu) — same bits as the FP32 scan, and a row
+    evaluates only a few of its columns exactly."""
+    monkeypatch.setenv("MM3D_KNN", "tc")
+    c = mm.Context(0)
+    a, b = tiny_stages[0]["desc"], tiny_stages[1]["desc"]
+    wp, wd = oracle.match(a, b, 5)
+    gp, gd = c.match(a, b, 5)
+    assert np.array_equal(gp, wp)
+    st = c.knn_stats()
+    assert st["rows"] == len(a) + len(b)
+    assert 5 <= st["candidates"] / st["rows"] < 0.25 * min(len(a), len(b)), st
+    print("exact evaluations per row:", st["candidates"] / st["rows"], "of", len(a), len(b), "early flushes:", st["overflow_rows"])
+    rng = np.random.default_rng(3)
+    s = rng.uniform(0, 1, size=(700, 1344)).astype(np.float32); s /= np.linalg.norm(s, axis=1, keepdims=True)
+    t = rng.uniform(0, 1, size=(900, 1344)).astype(np.float32); t /= np.linalg.norm(t, axis=1, keepdims=True)
+    wp, wd = oracle.match(s, t, 5)
+    gp, gd = c.match(s, t, 5)
+    assert np.array_equal(gp, wp) and np.array_equal(gd.view(np.uint32), wd.view(np.uint32))
+    st2 = c.knn_stats()
+    assert st2["rows"] == st["rows"] + 1600
+    assert (st2["candidates"] - st["candidates"]) / 1600 < 200, (st, st2)
+    # duplicated descriptors: whole groups of columns tie for the k-th place
+    a2 = np.concatenate([a[:200], np.repeat(a[200:201], 150, axis=0)])
+    b2 = np.concatenate([np.repeat(a[200:201], 100, axis=0), b[:300], np.repeat(a[7:8], 90, axis=0)])
+    for k in (1, 5, 12):
+        wp, wd = oracle.match(a2, b2, k)
+        gp, gd = c.match(a2, b2, k)
+        assert np.array_equal(gp, wp) and np.array_equal(gd.view(np.uint32), wd.view(np.uint32))
+    assert c.knn_stats()["overflow_rows"] > st2["overflow_rows"]  # the tie groups forced early exact evaluation
+    c.close()
+
+
+def test_tensor_core_knn_whole_path(mm, tiny_maps, monkeypatch):
+    """estimateMapsTransforms with MM3D_KNN=tc gives the same bits as with the FP32 scan (FPFH, 33 dims, and PFH, 125 dims)."""
+    maps, _ = tiny_maps
+    for desc in ("FPFH", "PFH"):
+        p = mm.default_params(descriptor_type=desc)
+        monkeypatch.delenv("MM3D_KNN", raising=False)
+        c = mm.Context(0)
+        want = c.estimate_maps_transforms(maps, p)
+        assert c.knn_stats()["rows"] == 0
+        monkeypatch.setenv("MM3D_KNN", "tc")
+        got = c.estimate_maps_transforms(maps, p)
+        assert c.knn_stats()["rows"] > 0
+        assert np.array_equal(np.asarray(got).view(np.uint32), np.asarray(want).view(np.uint32))
+        c.close()
+
+
 def test_match_small_sets_and_generic_dim(ctx, oracle):
     rng = np.random.default_rng(7)
     # fewer descriptors than k on either side (the reference reads out of bounds here; both sides clamp k)
@@ -459,3 +508,42 @@ def test_compose_maps_bit_exact(ctx, oracle, tiny_maps):
     # zero transform => that cloud is skipped (map_merging.cpp:293-295)
     T[1] = 0
     assert_same_bits(ctx.compose_maps(maps, T, 0.05), oracle.compose_maps(maps, T, 0.05), "composed map, one skipped")
+
+
+def test_compose_sharded_virtual_ranks(ctx, mm, oracle, tiny_maps):
+    """composeMaps sharded over R ranks (mm3d_compose_shard_*): the ranks' outputs concatenated in rank order
+    are bit-identical to the unsharded composeMaps.  The exchange is done by hand here (R virtual ranks on one GPU);
+    tests/test_multi_rank.py runs the same host logic over a real process group."""
+    import importlib
+    import torch
+    sh = importlib.import_module("map_merge_b200.sharding")
+    maps, truth = tiny_maps
+    T = np.stack([np.linalg.inv(truth[0]) @ t for t in truth]).astype(np.float32)
+    dev = torch.device("cuda:0")
+    for R, res in ((2, 0.05), (3, 0.11), (2, 1e-3)):
+        want = oracle.compose_maps(maps, T, res)
+        assert_same_bits(ctx.compose_maps(maps, T, res), want, "unsharded")
+        blocks = [sh.map_block(r, R, len(maps)) for r in range(R)]
+        begun = [ctx.compose_shard_begin(maps[f:f + c], T[f:f + c]) for f, c, _ in blocks]
+        gb = np.concatenate([np.min([b[0][:3] for b in begun], axis=0), np.max([b[0][3:] for b in begun], axis=0)]).astype(np.float32)
+        hists = [ctx.compose_shard_histogram(b[1], gb, res, 512) for b in begun]
+        if hists[0] is None:  # overflow guard: plain concatenation
+            got = np.concatenate([ctx.compose_shard_points(b[1]) for b in begun])
+        else:
+            sp = sh.choose_splitters(np.sum([h.astype(np.int64) for h in hists], axis=0), R)
+            sends, counts = [], []
+            for b in begun:
+                t = torch.empty((max(b[2], 1), 4), dtype=torch.float32, device=dev)
+                counts.append(ctx.compose_shard_partition(b[1], gb, res, sp, t.data_ptr(), 512))
+                sends.append(t)
+            assert all(int(c.sum()) == b[2] for c, b in zip(counts, begun))
+            outs = []
+            for r in range(R):
+                recv = torch.cat([s[int(c[:r].sum()):int(c[:r + 1].sum())] for s, c in zip(sends, counts)]).contiguous()
+                torch.cuda.synchronize()
+                outs.append(ctx.downsample_dev(recv.data_ptr(), recv.shape[0], res))
+            assert min(len(o) for o in outs) > 0.25 * len(want) / R
+            got = np.concatenate(outs)
+        for b in begun:
+            ctx.shard_free(b[1])
+        assert_same_bits(got, want, f"sharded composeMaps, {R} ranks")
