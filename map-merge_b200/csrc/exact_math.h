@@ -544,5 +544,25 @@ MM_HD long long to_fix(double v, double scale)
 #endif
 }
 
+// rint(v * 2^32) for a finite v >= 0 below 2^31, in integer arithmetic (no FP64): the float's 24-bit significand shifted
+// into place, round-to-nearest-even when bits fall off.  Same value as to_fix((double)v, MM3D_FIX1_SCALE).
+MM_HD long long to_fix32_pos(float v)
+{
+  unsigned int b;
+#if defined(__CUDA_ARCH__)
+  b = __float_as_uint(v);
+#else
+  memcpy(&b, &v, 4);
+#endif
+  const int e = (int)((b >> 23) & 0xffu);
+  const unsigned long long m = (unsigned long long)(b & 0x7fffffu) | (e ? 0x800000ull : 0ull);
+  const int sh = (e ? e : 1) - 118;  // (e - 127 - 23) + 32
+  if (sh >= 0) return (long long)(m << sh);
+  const int s = -sh;
+  if (s > 25) return 0;
+  const unsigned long long r = m >> s, rem = m & ((1ull << s) - 1ull), half = 1ull << (s - 1);
+  return (long long)(r + ((rem > half || (rem == half && (r & 1ull))) ? 1ull : 0ull));
+}
+
 }  // namespace em
 }  // namespace mm3d

@@ -158,36 +158,64 @@ __global__ void __launch_bounds__(256) sift_prep_kernel(const SiftPrepJob* __res
   j.dst[i] = make_float4(p.x, p.y, p.z, sift_intensity(p.w));
 }
 
+// computeScaleSpace, warp per point.  The Gaussian-weighted sums are accumulated in 2^-32 fixed point (int64), which makes
+// them independent of the order the terms arrive in and the same bits as the CPU checker's int64 sums.  (PCL adds the
+// same terms in float, nearest neighbour first; the fixed-point sum is the exactly rounded value of that.)
+// A neighbour at distance d contributes to the scales with d^2 <= 9 sigma^2, i.e. to the LAST cnt of the six: the
+// (neighbour, scale) pairs of a batch of 32 candidates are flattened with a warp scan so that every lane evaluates one
+// exp() per round, instead of most lanes idling on the small scales.
 __global__ void __launch_bounds__(FB) sift_scale_space_kernel(const SiftJob* __restrict__ jobs, SiftScales sc, float r2, int rv)
 {
+  __shared__ long long acc[FB / 32][12][32];  // [warp][scale: num 0..5, den 6..11][lane]
   const SiftJob& j = jobs[blockIdx.y];
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = k < j.g.n;
-  const float4 q = live ? j.g.pts[k] : make_float4(0.f, 0.f, 0.f, 0.f);
-  float num[6], den[6];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int k = blockIdx.x * (FB / 32) + w;
+  if (k >= j.g.n) return;  // warp-uniform
+  const unsigned full = 0xffffffffu;
+  const float4 q = j.g.pts[k];
 #pragma unroll
-  for (int s = 0; s < 6; ++s) { num[s] = 0.f; den[s] = 0.f; }
-  // (three nested walks with two scales each were measured: the extra walks cost more than the saved expf blocks)
-  for_each_in_radius(j.g, live, q.x, q.y, q.z, r2, rv, [&](int, const float4& p, float d2) {
-    const float value = p.w;  // intensity, see sift_prep_kernel
+  for (int s = 0; s < 12; ++s) acc[w][s][lane] = 0;
+  warp_radius_unordered(j.g, q.x, q.y, q.z, r2, rv, [&](bool valid, int, const float4& p, float d2) {
+    int cnt = 0;
+    if (valid) {
 #pragma unroll
-    for (int s = 0; s < 6; ++s) {
-      const float ss = sc.sigma_sqr[s];
-      if (d2 <= 9 * ss) {
-        const float w = em::expf_(-0.5f * d2 / ss);
-        num[s] += value * w;
-        den[s] += w;
+      for (int s = 0; s < 6; ++s) cnt += (d2 <= 9 * sc.sigma_sqr[s]) ? 1 : 0;
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(full, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(full, incl, 31);
+    const int excl = incl - cnt;
+    for (int t0 = 0; t0 < total; t0 += 32) {
+      const int t = t0 + lane;
+      int L = 0;  // owner of pair t: smallest L with incl[L] > t
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1) {
+        const int v = __shfl_sync(full, incl, L + step - 1);
+        if (v <= t) L += step;
+      }
+      L = min(L, 31);
+      const float od2 = __shfl_sync(full, d2, L), oval = __shfl_sync(full, p.w, L);
+      const int oex = __shfl_sync(full, excl, L), ocnt = __shfl_sync(full, cnt, L);
+      if (t < total) {
+        const int s = (6 - ocnt) + (t - oex);
+        const float wgt = em::expf_(-0.5f * od2 / sc.sigma_sqr[s]);
+        acc[w][s][lane] += em::to_fix32_pos(oval * wgt);  // intensity (sift_prep_kernel) times weight
+        acc[w][6 + s][lane] += em::to_fix32_pos(wgt);
       }
     }
   });
-  if (!live) return;
-  float prev = 0.f, resp = 0.f;
-#pragma unroll
-  for (int s = 0; s < 6; ++s) {
-    prev = resp;
-    resp = num[s] / den[s];
-    if (s > 0) j.dog[(size_t)k * 5 + (s - 1)] = resp - prev;
-  }
+  long long mine = 0;  // lanes 0..11 finish one sum each
+  if (lane < 12)
+    for (int l = 0; l < 32; ++l) mine += acc[w][lane][(l + lane) & 31];
+  const long long den = __shfl_down_sync(full, mine, 6);
+  float resp = 0.f;
+  if (lane < 6) resp = (float)((double)mine / MM3D_FIX1_SCALE) / (float)((double)den / MM3D_FIX1_SCALE);
+  const float prev = __shfl_up_sync(full, resp, 1);
+  if (lane >= 1 && lane < 6) j.dog[(size_t)k * 5 + (lane - 1)] = resp - prev;
 }
 
 // findScaleSpaceExtrema, warp per point: the warp gathers the candidates of a small sphere into shared memory,
@@ -794,7 +822,7 @@ void sift_batch(Ctx& c, const std::vector<CloudView>& clouds, float min_scale, i
     MM_LAUNCH(c, sift_prep_kernel, dim3((mx + 255) / 256, M), 256, 0, dpj.p);
     DBuf<SiftJob> djs = to_device(c, jobs_ss);
     { double b = 0; for (int m = 0; m < M; ++m) b += 36.0 * ns[m]; MM_BYTES(c, b); }
-    MM_LAUNCH(c, sift_scale_space_kernel, grid, FB, 0, djs.p, sc, r2, rv);
+    MM_LAUNCH(c, sift_scale_space_kernel, dim3((mx + FB / 32 - 1) / (FB / 32), M), FB, 0, djs.p, sc, r2, rv);
     { double b = 0; for (int m = 0; m < M; ++m) b += 48.0 * ns[m]; MM_BYTES(c, b); }
     MM_LAUNCH(c, sift_extrema_kernel, dim3((mx + FB / 32 - 1) / (FB / 32), M), FB, 0, dj.p, min_contrast);
     std::vector<int> totals;

@@ -593,8 +593,9 @@ static Normals surface_normals(const Cloud& in, double radius)
 // ===========================================================================
 // a6  detectKeypoints(SIFT) -> pcl::SIFTKeypoint<PointXYZRGB, PointWithScale>
 // [REF src/features.cpp:45-62,85-96] [PCL-recall pcl/keypoints/impl/sift_keypoint.hpp]
-// order_mode 0: ascending-index summation (canonical, what the CUDA path does)
-// order_mode 1: ascending-distance summation with PCL's early break (literal)
+// order_mode 0: the Gaussian-weighted sums are taken in 2^-32 fixed point (int64) — order-free, the exactly rounded
+//               value of the sums PCL accumulates in float (canonical, what the CUDA path does)
+// order_mode 1: float summation, nearest neighbour first, with PCL's early break (literal)
 // ===========================================================================
 static inline float sift_intensity(const P4& p)
 {
@@ -647,16 +648,26 @@ static Cloud sift_keypoints(const Cloud& input, float min_scale, int nr_octaves,
       for (int i_scale = 0; i_scale < nscales; ++i_scale) {
         const float ss = sigma_sqr[i_scale];
         float numerator = 0.0f, denominator = 0.0f;
+        long long num_fix = 0, den_fix = 0;
         for (size_t k = 0; k < nn_idx.size(); ++k) {
           const float value = sift_intensity(cloud[nn_idx[k]]);
           const float dist_sqr = nn_dist[k];
           if (dist_sqr <= 9 * ss) {
             const float w = m_expf(-0.5f * dist_sqr / ss);
-            numerator += value * w;
-            denominator += w;
+            if (order_mode == 1) {
+              numerator += value * w;
+              denominator += w;
+            } else {
+              num_fix += mm3d::em::to_fix32_pos(value * w);
+              den_fix += mm3d::em::to_fix32_pos(w);
+            }
           } else if (order_mode == 1) {
             break;  // sorted results: everything after is farther
           }
+        }
+        if (order_mode != 1) {
+          numerator = (float)((double)num_fix / MM3D_FIX1_SCALE);
+          denominator = (float)((double)den_fix / MM3D_FIX1_SCALE);
         }
         previous_filter_response = filter_response;
         filter_response = numerator / denominator;
@@ -2358,6 +2369,8 @@ int orc_compose_maps(int n_maps, const float* const* clouds, const uint64_t* n_p
 // exact_math probes
 float orc_em_expf(float x) { return mm3d::em::expf_(x); }
 float orc_em_atan2f(float y, float x) { return mm3d::em::atan2f_(y, x); }
+long long orc_em_to_fix32_pos(float v) { return mm3d::em::to_fix32_pos(v); }
+long long orc_em_to_fix(double v, double scale) { return mm3d::em::to_fix(v, scale); }
 float orc_em_cosf(float x) { return mm3d::em::cosf_small_(x); }
 float orc_em_sinf(float x) { return mm3d::em::sinf_small_(x); }
 void orc_em_svd3d(const double* A, double* U, double* s, double* V) { mm3d::em::svd3<double>(A, U, s, V); }

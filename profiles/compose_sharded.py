@@ -35,8 +35,11 @@ ctx = mm.Context(local)
 first, count, _ = sh.map_block(rank, world, M)
 all_maps, all_truth = synth.make_maps(11, M, P, 60.0, 30.0, 6, 3)
 maps = all_maps[first:first + count]
-T = np.stack([np.linalg.inv(all_truth[0]) @ t for t in all_truth]).astype(np.float32)[first:first + count]
-del all_maps
+T_all = np.stack([np.linalg.inv(all_truth[0]) @ t for t in all_truth]).astype(np.float32)
+T = T_all[first:first + count]
+check = os.environ.get("CHECK") == "1"
+if not (check and rank == 0):
+    del all_maps
 times = []
 for s in range(steps + 1):
     if world > 1:
@@ -57,5 +60,23 @@ if rank == 0:
     ms = 1e3 * float(np.mean(times))
     print(f"compose_sharded: {M} maps x {P} points, resolution {res}, {world} rank(s): {ms:.1f} ms/step, "
           f"{M * P / ms / 1e3:.1f} Mpoints/s in, {int(n_out.item())} points out (this rank {len(out)})")
+if check:
+    # gather every rank's slice on rank 0 and compare with the unsharded library call, bit for bit
+    sizes = torch.zeros(world, dtype=torch.int64, device=dev); sizes[rank] = len(out)
+    if world > 1:
+        dist.all_reduce(sizes)
+    buf = torch.zeros((int(sizes.max().item()), 4), dtype=torch.float32, device=dev)
+    buf[:len(out)] = torch.from_numpy(out).to(dev)
+    parts = [torch.zeros_like(buf) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(parts, buf)
+    else:
+        parts = [buf]
+    if rank == 0:
+        got = np.concatenate([parts[r][:int(sizes[r].item())].cpu().numpy() for r in range(world)])
+        want = ctx.compose_maps(all_maps, T_all, res)
+        same = got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        print("sharded == unsharded (bit-exact):", same)
+        assert same
 if world > 1:
     dist.destroy_process_group()
