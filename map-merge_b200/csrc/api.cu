@@ -106,8 +106,9 @@ double auto_leaf(double index_leaf, double radius, double ratio)
 void check_supported(const mm3d_params& p)
 {
   if (p.keypoint_type != MM3D_KP_SIFT && p.keypoint_type != MM3D_KP_HARRIS) throw std::runtime_error("unsupported: unknown keypoint_type");
-  if (p.descriptor_type != MM3D_DESC_FPFH && p.descriptor_type != MM3D_DESC_SHOT && p.descriptor_type != MM3D_DESC_PFH)
-    throw std::runtime_error("unsupported: descriptor_type PFHRGB / RSD / SC3D are not built yet (SURVEY.md 8f rank 3)");
+  if (p.descriptor_type != MM3D_DESC_FPFH && p.descriptor_type != MM3D_DESC_SHOT && p.descriptor_type != MM3D_DESC_PFH &&
+      p.descriptor_type != MM3D_DESC_PFHRGB)
+    throw std::runtime_error("unsupported: descriptor_type RSD / SC3D are not built yet (SURVEY.md 8f rank 3)");
   if (p.estimation_method != MM3D_EST_MATCHING && p.estimation_method != MM3D_EST_SAC_IA) throw std::runtime_error("unsupported: unknown estimation_method");
 }
 
@@ -160,7 +161,8 @@ void compute_features(Ctx& c, const std::vector<CloudView>& raw, const mm3d_para
   tm.begin();
   std::vector<DBuf<float>> desc;
   if (p.descriptor_type == MM3D_DESC_SHOT) shot_batch(c, fv, idx, np, kps, p.descriptor_radius, desc, nullptr);
-  else if (p.descriptor_type == MM3D_DESC_PFH) pfh_batch(c, fv, idx, np, kps, p.descriptor_radius, desc);
+  else if (p.descriptor_type == MM3D_DESC_PFH) pfh_batch(c, fv, idx, np, kps, p.descriptor_radius, desc, false);
+  else if (p.descriptor_type == MM3D_DESC_PFHRGB) pfh_batch(c, fv, idx, np, kps, p.descriptor_radius, desc, true);
   else fpfh_batch(c, fv, idx, np, kps, p.descriptor_radius, desc, nullptr);
   tm.end(4);
 
@@ -271,7 +273,7 @@ void register_pairs(Ctx& c, const std::vector<MapFeat>& f, int dim, const std::v
 // returns number of transforms written
 int desc_dim(const mm3d_params& p)
 {
-  return p.descriptor_type == MM3D_DESC_SHOT ? 1344 : (p.descriptor_type == MM3D_DESC_PFH ? 125 : 33);
+  return p.descriptor_type == MM3D_DESC_SHOT ? 1344 : (p.descriptor_type == MM3D_DESC_PFH ? 125 : (p.descriptor_type == MM3D_DESC_PFHRGB ? 250 : 33));
 }
 
 int estimate_from_views(Ctx& c, const std::vector<CloudView>& raw, const mm3d_params& p, float* out_transforms, float* stage_ms)
@@ -546,8 +548,8 @@ int mm3d_descriptors(mm3d_ctx* ctx, const float* pts, uint64_t n, const float* n
 {
   if (!keypoints_out || !n_out || !descriptors) return MM3D_ERR_ARG;
   MM_TRY(ctx)
-  if (type != MM3D_DESC_FPFH && type != MM3D_DESC_SHOT && type != MM3D_DESC_PFH)
-    throw std::runtime_error("unsupported: descriptor_type PFHRGB / RSD / SC3D are not built yet (SURVEY.md 8f rank 3)");
+  if (type != MM3D_DESC_FPFH && type != MM3D_DESC_SHOT && type != MM3D_DESC_PFH && type != MM3D_DESC_PFHRGB)
+    throw std::runtime_error("unsupported: descriptor_type RSD / SC3D are not built yet (SURVEY.md 8f rank 3)");
   DCloud d = upload_cloud(c, pts, n);
   DBuf<float4> nm(c, d.n);
   if (d.n) MM_CUDA(cudaMemcpyAsync(nm.p, normals, (size_t)d.n * sizeof(float4), cudaMemcpyHostToDevice, c.stream));
@@ -556,9 +558,9 @@ int mm3d_descriptors(mm3d_ctx* ctx, const float* pts, uint64_t n, const float* n
   std::vector<DIndex> idx;
   build_index_batch(c, {d.view()}, (float)auto_leaf(index_leaf, radius, 8.0), 2, 0, 0, idx);
   std::vector<DBuf<float>> desc, sp;
-  const int D = type == MM3D_DESC_SHOT ? 1344 : (type == MM3D_DESC_PFH ? 125 : 33);
-  if (type == MM3D_DESC_PFH) {
-    pfh_batch(c, {d.view()}, idx, {nm.p}, kp, radius, desc);
+  const int D = type == MM3D_DESC_SHOT ? 1344 : (type == MM3D_DESC_PFH ? 125 : (type == MM3D_DESC_PFHRGB ? 250 : 33));
+  if (type == MM3D_DESC_PFH || type == MM3D_DESC_PFHRGB) {
+    pfh_batch(c, {d.view()}, idx, {nm.p}, kp, radius, desc, type == MM3D_DESC_PFHRGB);
     if (spfh) { sp.resize(1); }
   } else if (type == MM3D_DESC_SHOT) shot_batch(c, {d.view()}, idx, {nm.p}, kp, radius, desc, spfh ? &sp : nullptr);  // spfh <- reference frames (K' x 9)
   else fpfh_batch(c, {d.view()}, idx, {nm.p}, kp, radius, desc, spfh ? &sp : nullptr);

@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(FB) spfh_kernel(const FpfhJob* __restrict__ jo
     const float4 pq = j.g.pts[q];
     const float4 nq = j.normals[j.g.orig ? j.g.orig[q] : q];
     float f1, f2, f3;
-    pair_features(p, np, pq, nq, &f1, &f2, &f3);
+    if (!pair_features(p, np, pq, nq, &f1, &f2, &f3)) return;  // "if (!computePairFeatures (...)) continue;"
     const int h1 = lookup_bin(thr[0], 11, f1, 11.0f * 0.15915494f, 3.14159274f);
     const int h2 = lookup_bin(thr[1], 11, f2, 5.5f, 1.0f);
     const int h3 = lookup_bin(thr[2], 11, f3, 5.5f, 1.0f);

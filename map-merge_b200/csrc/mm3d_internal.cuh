@@ -515,7 +515,7 @@ void shot_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<
 
 // pfh.cu — PFH 125 (the reference's default descriptor); keypoints filtered in place
 void pfh_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<const float4*>& normals,
-               std::vector<DCloud>& keypoints, double radius, std::vector<DBuf<float>>& desc);
+               std::vector<DCloud>& keypoints, double radius, std::vector<DBuf<float>>& desc, bool rgb = false);
 
 // knn_tc.cu — K9 on tensor cores: per row of map a (the first na rows), the k nearest rows of map b, exact after re-rank
 struct KnnProblem {

@@ -13,14 +13,14 @@ struct BinTable {
 };
 
 #if defined(__CUDACC__)
-// pcl::computePairFeatures [PCL-recall pcl/features/impl/pfh.hpp]; the FPFH member ignores its return
-// value, so degenerate pairs still vote with f1 = f2 = f3 = 0.
-__device__ __forceinline__ void pair_features(const float4& p1, const float4& n1, const float4& p2, const float4& n2, float* f1, float* f2,
+// pcl::computePairFeatures [PCL-recall pcl/features/impl/pfh.hpp]; false = degenerate pair (coincident points, or the
+// normal parallel to the connecting line), which the callers skip like computePointSPFHSignature / computePointPFHSignature.
+__device__ __forceinline__ bool pair_features(const float4& p1, const float4& n1, const float4& p2, const float4& n2, float* f1, float* f2,
                                               float* f3)
 {
   float dx = p2.x - p1.x, dy = p2.y - p1.y, dz = p2.z - p1.z;
   const float f4 = sqrtf((dx * dx + dy * dy) + dz * dz);
-  if (f4 == 0.0f) { *f1 = *f2 = *f3 = 0.0f; return; }
+  if (f4 == 0.0f) { *f1 = *f2 = *f3 = 0.0f; return false; }
   float ax = n1.x, ay = n1.y, az = n1.z, bx = n2.x, by = n2.y, bz = n2.z;
   const float angle1 = ((ax * dx + ay * dy) + az * dz) / f4;
   const float angle2 = ((bx * dx + by * dy) + bz * dz) / f4;
@@ -38,11 +38,32 @@ __device__ __forceinline__ void pair_features(const float4& p1, const float4& n1
   }
   float vx = dy * az - dz * ay, vy = dz * ax - dx * az, vz = dx * ay - dy * ax;
   const float v_norm = sqrtf((vx * vx + vy * vy) + vz * vz);
-  if (v_norm == 0.0f) { *f1 = *f2 = *f3 = 0.0f; return; }
+  if (v_norm == 0.0f) { *f1 = *f2 = *f3 = 0.0f; return false; }
   vx /= v_norm; vy /= v_norm; vz /= v_norm;
   const float wx = ay * vz - az * vy, wy = az * vx - ax * vz, wz = ax * vy - ay * vx;
   *f2 = (vx * bx + vy * by) + vz * bz;
   *f1 = em::atan2f_((wx * bx + wy * by) + wz * bz, (ax * bx + ay * by) + az * bz);
+  return true;
+}
+
+// pcl::computeRGBPairFeatures [PCL-recall pcl/features/impl/pfhrgb.hpp]: the same Darboux frame WITHOUT the source/target
+// swap; the colour ratios are handled by the caller (integer division, see pfh.cu).
+__device__ __forceinline__ bool pair_features_noswap(const float4& p1, const float4& n1, const float4& p2, const float4& n2, float* f1,
+                                                     float* f2, float* f3)
+{
+  const float dx = p2.x - p1.x, dy = p2.y - p1.y, dz = p2.z - p1.z;
+  const float f4 = sqrtf((dx * dx + dy * dy) + dz * dz);
+  if (f4 == 0.0f) return false;
+  const float ax = n1.x, ay = n1.y, az = n1.z, bx = n2.x, by = n2.y, bz = n2.z;
+  *f3 = ((ax * dx + ay * dy) + az * dz) / f4;
+  float vx = dy * az - dz * ay, vy = dz * ax - dx * az, vz = dx * ay - dy * ax;
+  const float v_norm = sqrtf((vx * vx + vy * vy) + vz * vz);
+  if (v_norm == 0.0f) return false;
+  vx /= v_norm; vy /= v_norm; vz /= v_norm;
+  const float wx = ay * vz - az * vy, wy = az * vx - ax * vz, wz = ax * vy - ay * vx;
+  *f2 = (vx * bx + vy * by) + vz * bz;
+  *f1 = em::atan2f_((wx * bx + wy * by) + wz * bz, (ax * bx + ay * by) + az * bz);
+  return true;
 }
 
 

@@ -818,11 +818,13 @@ static Cloud harris_keypoints(const Cloud& input, const Normals& normals, float 
 // [REF src/features.cpp:99-150, src/dispatch_descriptors.h:40]
 // [PCL-recall pcl/features/impl/fpfh.hpp, pcl/features/impl/pfh.hpp computePairFeatures]
 // ===========================================================================
-static void pair_features(const P4& p1, const N4& n1, const P4& p2, const N4& n2, float& f1, float& f2, float& f3, float& f4)
+// returns false for a degenerate pair (coincident points, or normal parallel to the connecting line); the callers skip it
+// ("if (!computePairFeatures (...)) continue;" in computePointSPFHSignature / computePointPFHSignature)
+static bool pair_features(const P4& p1, const N4& n1, const P4& p2, const N4& n2, float& f1, float& f2, float& f3, float& f4)
 {
   float dp[3] = {p2.x - p1.x, p2.y - p1.y, p2.z - p1.z};
   f4 = std::sqrt((dp[0] * dp[0] + dp[1] * dp[1]) + dp[2] * dp[2]);
-  if (f4 == 0.0f) { f1 = f2 = f3 = f4 = 0.0f; return; }
+  if (f4 == 0.0f) { f1 = f2 = f3 = f4 = 0.0f; return false; }
   float a[3] = {n1.nx, n1.ny, n1.nz}, b[3] = {n2.nx, n2.ny, n2.nz};
   const float angle1 = ((a[0] * dp[0] + a[1] * dp[1]) + a[2] * dp[2]) / f4;
   const float angle2 = ((b[0] * dp[0] + b[1] * dp[1]) + b[2] * dp[2]) / f4;
@@ -843,12 +845,44 @@ static void pair_features(const P4& p1, const N4& n1, const P4& p2, const N4& n2
   float v[3];
   cross3(dp, a, v);
   const float v_norm = std::sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
-  if (v_norm == 0.0f) { f1 = f2 = f3 = f4 = 0.0f; return; }
+  if (v_norm == 0.0f) { f1 = f2 = f3 = f4 = 0.0f; return false; }
   for (int i = 0; i < 3; ++i) v[i] /= v_norm;
   float w[3];
   cross3(a, v, w);
   f2 = (v[0] * b[0] + v[1] * b[1]) + v[2] * b[2];
   f1 = m_atan2f((w[0] * b[0] + w[1] * b[1]) + w[2] * b[2], (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]);
+  return true;
+}
+
+// pcl::computeRGBPairFeatures [PCL-recall pcl/features/impl/pfhrgb.hpp + pfh_tools]: the Darboux frame WITHOUT the
+// source/target swap of computePairFeatures, plus three colour ratios taken with INTEGER division and folded into [-1, 1].
+static bool rgb_pair_features(const P4& p1, const N4& n1, const P4& p2, const N4& n2, float f[7])
+{
+  for (int i = 0; i < 7; ++i) f[i] = 0.0f;
+  const float dp[3] = {p2.x - p1.x, p2.y - p1.y, p2.z - p1.z};
+  const float f4 = std::sqrt((dp[0] * dp[0] + dp[1] * dp[1]) + dp[2] * dp[2]);
+  if (f4 == 0.0f) return false;
+  const float a[3] = {n1.nx, n1.ny, n1.nz}, b[3] = {n2.nx, n2.ny, n2.nz};
+  const float angle1 = ((a[0] * dp[0] + a[1] * dp[1]) + a[2] * dp[2]) / f4;
+  float v[3];
+  cross3(dp, a, v);
+  const float v_norm = std::sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+  if (v_norm == 0.0f) return false;
+  for (int i = 0; i < 3; ++i) v[i] /= v_norm;
+  float w[3];
+  cross3(a, v, w);
+  f[3] = f4;
+  f[2] = angle1;
+  f[1] = (v[0] * b[0] + v[1] * b[1]) + v[2] * b[2];
+  f[0] = m_atan2f((w[0] * b[0] + w[1] * b[1]) + w[2] * b[2], (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]);
+  const int c1[3] = {(int)((p1.rgba >> 16) & 0xff), (int)((p1.rgba >> 8) & 0xff), (int)(p1.rgba & 0xff)};
+  const int c2[3] = {(int)((p2.rgba >> 16) & 0xff), (int)((p2.rgba >> 8) & 0xff), (int)(p2.rgba & 0xff)};
+  for (int i = 0; i < 3; ++i) {
+    float r = (c2[i] != 0) ? (float)(c1[i] / c2[i]) : 1.0f;
+    if (r > 1.0f) r = -1.0f / r;
+    f[4 + i] = r;
+  }
+  return true;
 }
 
 static inline int clampbin(int h, int nb)
@@ -885,7 +919,7 @@ static std::vector<float> fpfh_descriptors(const Cloud& surface, const Normals& 
     for (int q : nn_idx) {
       if ((int)p == q) continue;
       float f1, f2, f3, f4;
-      pair_features(surface[p], normals[p], surface[q], normals[q], f1, f2, f3, f4);
+      if (!pair_features(surface[p], normals[p], surface[q], normals[q], f1, f2, f3, f4)) continue;
       int hi = (int)std::floor(NB * ((f1 + M_PI) * d_pi));
       h[clampbin(hi, NB)] += hist_incr;
       hi = (int)std::floor(NB * ((f2 + 1.0) * 0.5));
@@ -955,7 +989,7 @@ static std::vector<float> pfh_descriptors(const Cloud& surface, const Normals& n
     for (size_t i = 0; i < idx.size(); ++i)
       for (size_t j = 0; j < i; ++j) {
         float f1, f2, f3, f4;
-        pair_features(surface[idx[i]], normals[idx[i]], surface[idx[j]], normals[idx[j]], f1, f2, f3, f4);
+        if (!pair_features(surface[idx[i]], normals[idx[i]], surface[idx[j]], normals[idx[j]], f1, f2, f3, f4)) continue;
         int fi[3];
         fi[0] = (int)std::floor(nr_split * ((f1 + M_PI) * d_pi));
         fi[1] = (int)std::floor(nr_split * ((f2 + 1.0) * 0.5));
@@ -972,6 +1006,52 @@ static std::vector<float> pfh_descriptors(const Cloud& surface, const Normals& n
       if (!std::isfinite(v)) finite = false;
     if (!finite) continue;
     desc.insert(desc.end(), h, h + 125);
+    kept.push_back(keypoints[k]);
+  }
+  keypoints.swap(kept);
+  return desc;
+}
+
+// ===========================================================================
+// a8-PFHRGB  computeLocalDescriptors(PFHRGB) -> pcl::PFHRGBEstimation<PointXYZRGB, Normal, PFHRGBSignature250>
+// [REF src/dispatch_descriptors.h:39] [PCL-recall pcl/features/impl/pfhrgb.hpp computePointPFHRGBSignature: all pairs
+//  (i, j < i); 5^3 bins over (f1, f2, f3) in [0, 125) and 5^3 bins over the three colour ratios in [125, 250); every
+//  surviving pair adds 100 / (n (n-1) / 2) to one bin of each half; no NaN marking — an empty neighbourhood leaves zeros]
+// ===========================================================================
+static std::vector<float> pfhrgb_descriptors(const Cloud& surface, const Normals& normals, Cloud& keypoints, double radius)
+{
+  const int nr_split = 5;
+  Grid tree;
+  tree.build(surface, (float)radius);
+  const float d_pi = 1.0f / (2.0f * (float)M_PI);
+  std::vector<int> idx;
+  std::vector<float> sqd;
+  std::vector<float> desc;
+  Cloud kept;
+  for (size_t k = 0; k < keypoints.size(); ++k) {
+    tree.radius_sorted(keypoints[k].x, keypoints[k].y, keypoints[k].z, radius, idx, sqd);
+    float h[250];
+    for (float& v : h) v = 0.f;
+    const float hist_incr = 100.0f / (float)(idx.size() * (idx.size() - 1) / 2);  // inf for n < 2, never added
+    for (size_t i = 0; i < idx.size(); ++i)
+      for (size_t j = 0; j < i; ++j) {
+        float f[7];
+        if (!rgb_pair_features(surface[idx[i]], normals[idx[i]], surface[idx[j]], normals[idx[j]], f)) continue;
+        int fi[7];
+        fi[0] = clampbin((int)std::floor(nr_split * ((f[0] + M_PI) * d_pi)), nr_split);
+        fi[1] = clampbin((int)std::floor(nr_split * ((f[1] + 1.0) * 0.5)), nr_split);
+        fi[2] = clampbin((int)std::floor(nr_split * ((f[2] + 1.0) * 0.5)), nr_split);
+        fi[4] = clampbin((int)std::floor(nr_split * ((f[4] + 1.0) * 0.5)), nr_split);
+        fi[5] = clampbin((int)std::floor(nr_split * ((f[5] + 1.0) * 0.5)), nr_split);
+        fi[6] = clampbin((int)std::floor(nr_split * ((f[6] + 1.0) * 0.5)), nr_split);
+        h[fi[0] + 5 * fi[1] + 25 * fi[2]] += hist_incr;
+        h[125 + fi[4] + 5 * fi[5] + 25 * fi[6]] += hist_incr;
+      }
+    bool finite = true;
+    for (float v : h)
+      if (!std::isfinite(v)) finite = false;
+    if (!finite) continue;
+    desc.insert(desc.end(), h, h + 250);
     kept.push_back(keypoints[k]);
   }
   keypoints.swap(kept);
@@ -1969,8 +2049,9 @@ static void map_features(const Cloud& in, const Params& p, MapFeatures& f, Stage
   double t4 = now_s();
   if (p.descriptor_type == 4) f.desc = shot_descriptors(f.cloud, f.normals, f.keypoints, p.descriptor_radius);
   else if (p.descriptor_type == 0) f.desc = pfh_descriptors(f.cloud, f.normals, f.keypoints, p.descriptor_radius);
+  else if (p.descriptor_type == 1) f.desc = pfhrgb_descriptors(f.cloud, f.normals, f.keypoints, p.descriptor_radius);
   else f.desc = fpfh_descriptors(f.cloud, f.normals, f.keypoints, p.descriptor_radius);
-  f.dim = p.descriptor_type == 4 ? 1344 : (p.descriptor_type == 0 ? 125 : 33);
+  f.dim = p.descriptor_type == 4 ? 1344 : (p.descriptor_type == 0 ? 125 : (p.descriptor_type == 1 ? 250 : 33));
   double t5 = now_s();
   if (st) {
     st->t[0] += t1 - t0; st->t[1] += t2 - t1; st->t[2] += t3 - t2; st->t[3] += t4 - t3; st->t[4] += t5 - t4;
@@ -2147,6 +2228,20 @@ int orc_pfh(const float* pts, uint64_t n, const float* normals, const float* kp_
   if (n) memcpy(nm.data(), normals, n * sizeof(N4));
   Cloud kp = to_cloud(kp_in, nk_in);
   std::vector<float> d = pfh_descriptors(surf, nm, kp, radius);
+  *kp_out = dup_f(kp.data(), kp.size() * sizeof(P4));
+  *nk_out = kp.size();
+  *desc = dup_f(d.data(), d.size() * 4);
+  return 0;
+}
+
+int orc_pfhrgb(const float* pts, uint64_t n, const float* normals, const float* kp_in, uint64_t nk_in, double radius, float** kp_out,
+               uint64_t* nk_out, float** desc)
+{
+  Cloud surf = to_cloud(pts, n);
+  Normals nm(n);
+  if (n) memcpy(nm.data(), normals, n * sizeof(N4));
+  Cloud kp = to_cloud(kp_in, nk_in);
+  std::vector<float> d = pfhrgb_descriptors(surf, nm, kp, radius);
   *kp_out = dup_f(kp.data(), kp.size() * sizeof(P4));
   *nk_out = kp.size();
   *desc = dup_f(d.data(), d.size() * 4);

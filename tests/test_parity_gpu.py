@@ -182,6 +182,27 @@ def test_pfh_bit_exact(ctx, mm, oracle, tiny_stages):
     assert_same_bits(gd, wd, "PFH descriptors (large neighbourhood)")
 
 
+def test_pfhrgb_bit_exact(ctx, mm, oracle, tiny_stages, tiny_maps):
+    """PFHRGB (250 = 125 geometric + 125 colour-ratio bins): stage parity, then the whole path with descriptor_type PFHRGB."""
+    import oracle_py
+    for st in tiny_stages:
+        kp_in = np.concatenate([st["kp_sift"][:50], np.array([[70, 70, 70, 0]], np.float32)])  # the last one has no neighbours
+        wk, wd = oracle.pfhrgb(st["filtered"], st["normals"], kp_in, 0.8)
+        gk, gd = ctx.descriptors(st["filtered"], st["normals"], kp_in, type="PFHRGB", radius=0.8, index_leaf=0.1)
+        assert len(wk) == 51 and wd.shape == (51, 250)  # an empty neighbourhood leaves a zero histogram, which is kept
+        assert_same_bits(gk, wk, "kept keypoints")
+        assert_same_bits(gd, wd, "PFHRGB descriptors")
+        np.testing.assert_allclose(gd[:50, :125].sum(1), 100.0, rtol=1e-3)
+        np.testing.assert_allclose(gd[:50, 125:].sum(1), 100.0, rtol=1e-3)
+        assert (gd[:50, 125:] > 0).sum(1).min() >= 2  # the colour half is populated by more than one bin
+        assert not gd[50].any()
+    maps, _ = tiny_maps
+    sub = [m[:12000] for m in maps]
+    want = oracle.estimate_maps_transforms(sub, oracle_py.default_params(descriptor_type=1))
+    got = ctx.estimate_maps_transforms(sub, mm.default_params(descriptor_type="PFHRGB"))
+    np.testing.assert_allclose(got, want["transforms"], rtol=0, atol=1e-5)
+
+
 def test_default_params_pipeline_matches_oracle(ctx, mm, oracle, tiny_maps):
     """MapMergingParams() as shipped: SIFT + PFH + MATCHING + ICP (map_merging.h:29-44)."""
     import oracle_py
@@ -547,3 +568,44 @@ def test_compose_sharded_virtual_ranks(ctx, mm, oracle, tiny_maps):
         for b in begun:
             ctx.shard_free(b[1])
         assert_same_bits(got, want, f"sharded composeMaps, {R} ranks")
+
+
+def test_estimate_and_compose_run_concurrently(mm, tiny_maps):
+    """The ROS node calls estimateMapsTransforms and composeMaps from different spinner threads
+    (src/map_merge_node.cpp:32-40,264-265).  One context per thread: concurrent calls give the sequential results."""
+    import threading
+    maps, truth = tiny_maps
+    p = mm.default_params(descriptor_type="FPFH")
+    T = np.stack([np.linalg.inv(truth[0]) @ t for t in truth]).astype(np.float32)
+    c0 = mm.Context(0)
+    want_T = c0.estimate_maps_transforms(maps, p)
+    want_map = c0.compose_maps(maps, T, 0.05)
+    c0.close()
+    out, errs = {}, []
+
+    def estimate():
+        try:
+            c = mm.Context(0)
+            out["T"] = [c.estimate_maps_transforms(maps, p) for _ in range(3)]
+            c.close()
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    def compose():
+        try:
+            c = mm.Context(0)
+            out["map"] = [c.compose_maps(maps, T, 0.05) for _ in range(6)]
+            c.close()
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=estimate), threading.Thread(target=compose)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for got in out["T"]:
+        assert np.array_equal(np.asarray(got).view(np.uint32), np.asarray(want_T).view(np.uint32))
+    for got in out["map"]:
+        assert_same_bits(got, want_map, "composed map under concurrency")
