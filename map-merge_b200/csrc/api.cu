@@ -107,8 +107,8 @@ void check_supported(const mm3d_params& p)
 {
   if (p.keypoint_type != MM3D_KP_SIFT && p.keypoint_type != MM3D_KP_HARRIS) throw std::runtime_error("unsupported: unknown keypoint_type");
   if (p.descriptor_type != MM3D_DESC_FPFH && p.descriptor_type != MM3D_DESC_SHOT && p.descriptor_type != MM3D_DESC_PFH &&
-      p.descriptor_type != MM3D_DESC_PFHRGB)
-    throw std::runtime_error("unsupported: descriptor_type RSD / SC3D are not built yet (SURVEY.md 8f rank 3)");
+      p.descriptor_type != MM3D_DESC_PFHRGB && p.descriptor_type != MM3D_DESC_RSD)
+    throw std::runtime_error("unsupported: descriptor_type SC3D is not built yet (SURVEY.md 8f rank 3)");
   if (p.estimation_method != MM3D_EST_MATCHING && p.estimation_method != MM3D_EST_SAC_IA) throw std::runtime_error("unsupported: unknown estimation_method");
 }
 
@@ -163,6 +163,7 @@ void compute_features(Ctx& c, const std::vector<CloudView>& raw, const mm3d_para
   if (p.descriptor_type == MM3D_DESC_SHOT) shot_batch(c, fv, idx, np, kps, p.descriptor_radius, desc, nullptr);
   else if (p.descriptor_type == MM3D_DESC_PFH) pfh_batch(c, fv, idx, np, kps, p.descriptor_radius, desc, false);
   else if (p.descriptor_type == MM3D_DESC_PFHRGB) pfh_batch(c, fv, idx, np, kps, p.descriptor_radius, desc, true);
+  else if (p.descriptor_type == MM3D_DESC_RSD) rsd_batch(c, fv, idx, np, kps, p.descriptor_radius, desc);
   else fpfh_batch(c, fv, idx, np, kps, p.descriptor_radius, desc, nullptr);
   tm.end(4);
 
@@ -273,7 +274,13 @@ void register_pairs(Ctx& c, const std::vector<MapFeat>& f, int dim, const std::v
 // returns number of transforms written
 int desc_dim(const mm3d_params& p)
 {
-  return p.descriptor_type == MM3D_DESC_SHOT ? 1344 : (p.descriptor_type == MM3D_DESC_PFH ? 125 : (p.descriptor_type == MM3D_DESC_PFHRGB ? 250 : 33));
+  switch (p.descriptor_type) {
+    case MM3D_DESC_SHOT: return 1344;
+    case MM3D_DESC_PFH: return 125;
+    case MM3D_DESC_PFHRGB: return 250;
+    case MM3D_DESC_RSD: return 2;
+    default: return 33;
+  }
 }
 
 int estimate_from_views(Ctx& c, const std::vector<CloudView>& raw, const mm3d_params& p, float* out_transforms, float* stage_ms)
@@ -548,8 +555,8 @@ int mm3d_descriptors(mm3d_ctx* ctx, const float* pts, uint64_t n, const float* n
 {
   if (!keypoints_out || !n_out || !descriptors) return MM3D_ERR_ARG;
   MM_TRY(ctx)
-  if (type != MM3D_DESC_FPFH && type != MM3D_DESC_SHOT && type != MM3D_DESC_PFH && type != MM3D_DESC_PFHRGB)
-    throw std::runtime_error("unsupported: descriptor_type RSD / SC3D are not built yet (SURVEY.md 8f rank 3)");
+  if (type != MM3D_DESC_FPFH && type != MM3D_DESC_SHOT && type != MM3D_DESC_PFH && type != MM3D_DESC_PFHRGB && type != MM3D_DESC_RSD)
+    throw std::runtime_error("unsupported: descriptor_type SC3D is not built yet (SURVEY.md 8f rank 3)");
   DCloud d = upload_cloud(c, pts, n);
   DBuf<float4> nm(c, d.n);
   if (d.n) MM_CUDA(cudaMemcpyAsync(nm.p, normals, (size_t)d.n * sizeof(float4), cudaMemcpyHostToDevice, c.stream));
@@ -558,8 +565,11 @@ int mm3d_descriptors(mm3d_ctx* ctx, const float* pts, uint64_t n, const float* n
   std::vector<DIndex> idx;
   build_index_batch(c, {d.view()}, (float)auto_leaf(index_leaf, radius, 8.0), 2, 0, 0, idx);
   std::vector<DBuf<float>> desc, sp;
-  const int D = type == MM3D_DESC_SHOT ? 1344 : (type == MM3D_DESC_PFH ? 125 : (type == MM3D_DESC_PFHRGB ? 250 : 33));
-  if (type == MM3D_DESC_PFH || type == MM3D_DESC_PFHRGB) {
+  const int D = type == MM3D_DESC_SHOT ? 1344 : (type == MM3D_DESC_PFH ? 125 : (type == MM3D_DESC_PFHRGB ? 250 : (type == MM3D_DESC_RSD ? 2 : 33)));
+  if (type == MM3D_DESC_RSD) {
+    rsd_batch(c, {d.view()}, idx, {nm.p}, kp, radius, desc);
+    if (spfh) { sp.resize(1); }
+  } else if (type == MM3D_DESC_PFH || type == MM3D_DESC_PFHRGB) {
     pfh_batch(c, {d.view()}, idx, {nm.p}, kp, radius, desc, type == MM3D_DESC_PFHRGB);
     if (spfh) { sp.resize(1); }
   } else if (type == MM3D_DESC_SHOT) shot_batch(c, {d.view()}, idx, {nm.p}, kp, radius, desc, spfh ? &sp : nullptr);  // spfh <- reference frames (K' x 9)

@@ -55,7 +55,9 @@ static inline float m_expf(float x) { return ::expf(x); }
 static inline float m_atan2f(float y, float x) { return ::atan2f(y, x); }
 static inline float m_cosf(float x) { return ::cosf(x); }
 static inline float m_sinf(float x) { return ::sinf(x); }
+static inline double m_acos(double x) { return ::acos(x); }
 #else
+static inline double m_acos(double x) { return em::acos_d_(x); }
 static inline float m_expf(float x) { return em::expf_(x); }
 static inline float m_atan2f(float y, float x) { return em::atan2f_(y, x); }
 static inline float m_cosf(float x) { return em::cosf_small_(x); }
@@ -1059,6 +1061,79 @@ static std::vector<float> pfhrgb_descriptors(const Cloud& surface, const Normals
 }
 
 // ===========================================================================
+// a8-RSD  computeLocalDescriptors(RSD) -> pcl::RSDEstimation<PointXYZRGB, Normal, PrincipalRadiiRSD>
+// [REF src/dispatch_descriptors.h:43; the matcher sees 2 floats (r_min, r_max): DefaultPointRepresentation = sizeof / 4]
+// [PCL-recall pcl/features/impl/rsd.hpp computeRSD (surface, normals, indices, max_dist, nr_subdiv, plane_radius, radii):
+//  nr_subdiv_ = 5, plane_radius_ = 0.2; the centre of the patch is indices[0], i.e. the NEAREST surface point of the
+//  keypoint (sorted radius search); for every other neighbour the angle between the normals (orientation ignored) and the
+//  distance to the centre go into per-distance-bin min / max angles; radii from the least-squares lines through them.]
+// Canonical choices: nearest = smallest (d^2, index); sqrt of the float distance sum taken in double (unqualified C sqrt);
+// a neighbour at exactly max_dist would index bin nr_subdiv in PCL (one past the end) — it goes to the last bin here.
+// ===========================================================================
+static std::vector<float> rsd_descriptors(const Cloud& surface, const Normals& normals, Cloud& keypoints, double radius)
+{
+  const int nr_subdiv = 5;
+  const double plane_radius = 0.2, max_dist = radius;
+  Grid tree;
+  tree.build(surface, (float)radius);
+  std::vector<int> idx;
+  std::vector<float> sqd;
+  std::vector<float> desc;
+  Cloud kept;
+  for (size_t k = 0; k < keypoints.size(); ++k) {
+    tree.radius_sorted(keypoints[k].x, keypoints[k].y, keypoints[k].z, radius, idx, sqd);
+    float r_min = 0.0f, r_max = 0.0f;
+    if (idx.size() >= 2) {
+      size_t b = 0;
+      for (size_t i = 1; i < idx.size(); ++i)
+        if (sqd[i] < sqd[b]) b = i;  // ascending index: the first minimum is the lowest index
+      const int c = idx[b];
+      double mn[5], mx[5];
+      mn[0] = mx[0] = 0.0;
+      for (int d = 1; d < nr_subdiv; ++d) { mn[d] = DBL_MAX; mx[d] = -DBL_MAX; }
+      for (size_t i = 0; i < idx.size(); ++i) {
+        if (i == b) continue;
+        const int q = idx[i];
+        double cosine = (normals[q].nx * normals[c].nx + normals[q].ny * normals[c].ny) + normals[q].nz * normals[c].nz;
+        if (cosine > 1) cosine = 1;
+        if (cosine < -1) cosine = -1;
+        double angle = m_acos(cosine);
+        if (angle > M_PI / 2) angle = M_PI - angle;
+        const float dx = surface[q].x - surface[c].x, dy = surface[q].y - surface[c].y, dz = surface[q].z - surface[c].z;
+        const double dist = std::sqrt((double)((dx * dx + dy * dy) + dz * dz));
+        if (dist > max_dist) continue;
+        int bin_d = (int)std::floor(nr_subdiv * dist / max_dist);
+        if (bin_d > nr_subdiv - 1) bin_d = nr_subdiv - 1;
+        if (mn[bin_d] > angle) mn[bin_d] = angle;
+        if (mx[bin_d] < angle) mx[bin_d] = angle;
+      }
+      double Amint_Amin = 0, Amint_d = 0, Amaxt_Amax = 0, Amaxt_d = 0;
+      for (int d = 0; d < nr_subdiv; ++d) {
+        if (mx[d] >= 0) {
+          const double f = (d + 0.5) * max_dist / nr_subdiv;
+          Amint_Amin += mn[d] * mn[d];
+          Amint_d += mn[d] * f;
+          Amaxt_Amax += mx[d] * mx[d];
+          Amaxt_d += mx[d] * f;
+        }
+      }
+      float min_radius = Amint_Amin == 0.0f ? (float)plane_radius : (float)std::min(Amint_d / Amint_Amin, plane_radius);
+      float max_radius = Amaxt_Amax == 0.0f ? (float)plane_radius : (float)std::min(Amaxt_d / Amaxt_Amax, plane_radius);
+      min_radius *= 1.1f;
+      max_radius *= 0.9f;
+      if (min_radius < max_radius) { r_min = min_radius; r_max = max_radius; }
+      else { r_max = min_radius; r_min = max_radius; }
+    }
+    if (!std::isfinite(r_min) || !std::isfinite(r_max)) continue;
+    desc.push_back(r_min);
+    desc.push_back(r_max);
+    kept.push_back(keypoints[k]);
+  }
+  keypoints.swap(kept);
+  return desc;
+}
+
+// ===========================================================================
 // a8-SHOT  computeLocalDescriptors(SHOT) -> pcl::SHOTColorEstimation<PointXYZRGB, Normal, SHOT1344>
 // [REF src/dispatch_descriptors.h:46, src/features.cpp:99-150]
 // [PCL-recall pcl/features/impl/shot.hpp (computeFeature, computePointSHOT, createBinDistanceShape,
@@ -2050,8 +2125,9 @@ static void map_features(const Cloud& in, const Params& p, MapFeatures& f, Stage
   if (p.descriptor_type == 4) f.desc = shot_descriptors(f.cloud, f.normals, f.keypoints, p.descriptor_radius);
   else if (p.descriptor_type == 0) f.desc = pfh_descriptors(f.cloud, f.normals, f.keypoints, p.descriptor_radius);
   else if (p.descriptor_type == 1) f.desc = pfhrgb_descriptors(f.cloud, f.normals, f.keypoints, p.descriptor_radius);
+  else if (p.descriptor_type == 3) f.desc = rsd_descriptors(f.cloud, f.normals, f.keypoints, p.descriptor_radius);
   else f.desc = fpfh_descriptors(f.cloud, f.normals, f.keypoints, p.descriptor_radius);
-  f.dim = p.descriptor_type == 4 ? 1344 : (p.descriptor_type == 0 ? 125 : (p.descriptor_type == 1 ? 250 : 33));
+  f.dim = p.descriptor_type == 4 ? 1344 : (p.descriptor_type == 0 ? 125 : (p.descriptor_type == 1 ? 250 : (p.descriptor_type == 3 ? 2 : 33)));
   double t5 = now_s();
   if (st) {
     st->t[0] += t1 - t0; st->t[1] += t2 - t1; st->t[2] += t3 - t2; st->t[3] += t4 - t3; st->t[4] += t5 - t4;
@@ -2242,6 +2318,20 @@ int orc_pfhrgb(const float* pts, uint64_t n, const float* normals, const float* 
   if (n) memcpy(nm.data(), normals, n * sizeof(N4));
   Cloud kp = to_cloud(kp_in, nk_in);
   std::vector<float> d = pfhrgb_descriptors(surf, nm, kp, radius);
+  *kp_out = dup_f(kp.data(), kp.size() * sizeof(P4));
+  *nk_out = kp.size();
+  *desc = dup_f(d.data(), d.size() * 4);
+  return 0;
+}
+
+int orc_rsd(const float* pts, uint64_t n, const float* normals, const float* kp_in, uint64_t nk_in, double radius, float** kp_out,
+            uint64_t* nk_out, float** desc)
+{
+  Cloud surf = to_cloud(pts, n);
+  Normals nm(n);
+  if (n) memcpy(nm.data(), normals, n * sizeof(N4));
+  Cloud kp = to_cloud(kp_in, nk_in);
+  std::vector<float> d = rsd_descriptors(surf, nm, kp, radius);
   *kp_out = dup_f(kp.data(), kp.size() * sizeof(P4));
   *nk_out = kp.size();
   *desc = dup_f(d.data(), d.size() * 4);

@@ -203,6 +203,29 @@ def test_pfhrgb_bit_exact(ctx, mm, oracle, tiny_stages, tiny_maps):
     np.testing.assert_allclose(got, want["transforms"], rtol=0, atol=1e-5)
 
 
+def test_rsd_bit_exact(ctx, mm, oracle, tiny_stages, tiny_maps):
+    """RSD (r_min, r_max): stage parity, then the whole path with descriptor_type RSD (2-D descriptors: ties everywhere)."""
+    import oracle_py
+    for st in tiny_stages:
+        kp_in = np.concatenate([st["kp_sift"][:400], np.array([[70, 70, 70, 0]], np.float32)])  # the last one has no neighbours
+        wk, wd = oracle.rsd(st["filtered"], st["normals"], kp_in, 0.8)
+        gk, gd = ctx.descriptors(st["filtered"], st["normals"], kp_in, type="RSD", radius=0.8, index_leaf=0.1)
+        assert wd.shape == (401, 2) and not wd[400].any()  # fewer than two neighbours -> (0, 0), kept
+        assert_same_bits(gk, wk, "kept keypoints")
+        assert_same_bits(gd, wd, "RSD radii")
+        assert (gd[:400, 0] <= gd[:400, 1]).all() and (gd[:400, 1] <= 0.2 * 1.1 + 1e-6).all()
+        # at 0.8 m nearly everything saturates at plane_radius (0.18, 0.22); a small support radius resolves the edges
+        wk, wd = oracle.rsd(st["filtered"], st["normals"], kp_in, 0.25)
+        gk, gd = ctx.descriptors(st["filtered"], st["normals"], kp_in, type="RSD", radius=0.25, index_leaf=0.1)
+        assert_same_bits(gd, wd, "RSD radii, 0.25 m support")
+        assert len(np.unique(gd[:400, 0])) > 5
+    maps, _ = tiny_maps
+    sub = [m[:12000] for m in maps]
+    want = oracle.estimate_maps_transforms(sub, oracle_py.default_params(descriptor_type=3))
+    got = ctx.estimate_maps_transforms(sub, mm.default_params(descriptor_type="RSD"))
+    np.testing.assert_allclose(got, want["transforms"], rtol=0, atol=1e-5)
+
+
 def test_default_params_pipeline_matches_oracle(ctx, mm, oracle, tiny_maps):
     """MapMergingParams() as shipped: SIFT + PFH + MATCHING + ICP (map_merging.h:29-44)."""
     import oracle_py
