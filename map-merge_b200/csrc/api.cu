@@ -106,9 +106,7 @@ double auto_leaf(double index_leaf, double radius, double ratio)
 void check_supported(const mm3d_params& p)
 {
   if (p.keypoint_type != MM3D_KP_SIFT && p.keypoint_type != MM3D_KP_HARRIS) throw std::runtime_error("unsupported: unknown keypoint_type");
-  if (p.descriptor_type != MM3D_DESC_FPFH && p.descriptor_type != MM3D_DESC_SHOT && p.descriptor_type != MM3D_DESC_PFH &&
-      p.descriptor_type != MM3D_DESC_PFHRGB && p.descriptor_type != MM3D_DESC_RSD)
-    throw std::runtime_error("unsupported: descriptor_type SC3D is not built yet (SURVEY.md 8f rank 3)");
+  if (p.descriptor_type < MM3D_DESC_PFH || p.descriptor_type > MM3D_DESC_SC3D) throw std::runtime_error("unsupported: unknown descriptor_type");
   if (p.estimation_method != MM3D_EST_MATCHING && p.estimation_method != MM3D_EST_SAC_IA) throw std::runtime_error("unsupported: unknown estimation_method");
 }
 
@@ -164,6 +162,7 @@ void compute_features(Ctx& c, const std::vector<CloudView>& raw, const mm3d_para
   else if (p.descriptor_type == MM3D_DESC_PFH) pfh_batch(c, fv, idx, np, kps, p.descriptor_radius, desc, false);
   else if (p.descriptor_type == MM3D_DESC_PFHRGB) pfh_batch(c, fv, idx, np, kps, p.descriptor_radius, desc, true);
   else if (p.descriptor_type == MM3D_DESC_RSD) rsd_batch(c, fv, idx, np, kps, p.descriptor_radius, desc);
+  else if (p.descriptor_type == MM3D_DESC_SC3D) sc3d_batch(c, fv, idx, np, kps, p.descriptor_radius, desc);
   else fpfh_batch(c, fv, idx, np, kps, p.descriptor_radius, desc, nullptr);
   tm.end(4);
 
@@ -279,6 +278,7 @@ int desc_dim(const mm3d_params& p)
     case MM3D_DESC_PFH: return 125;
     case MM3D_DESC_PFHRGB: return 250;
     case MM3D_DESC_RSD: return 2;
+    case MM3D_DESC_SC3D: return 1980;
     default: return 33;
   }
 }
@@ -555,8 +555,7 @@ int mm3d_descriptors(mm3d_ctx* ctx, const float* pts, uint64_t n, const float* n
 {
   if (!keypoints_out || !n_out || !descriptors) return MM3D_ERR_ARG;
   MM_TRY(ctx)
-  if (type != MM3D_DESC_FPFH && type != MM3D_DESC_SHOT && type != MM3D_DESC_PFH && type != MM3D_DESC_PFHRGB && type != MM3D_DESC_RSD)
-    throw std::runtime_error("unsupported: descriptor_type SC3D is not built yet (SURVEY.md 8f rank 3)");
+  if (type < MM3D_DESC_PFH || type > MM3D_DESC_SC3D) throw std::runtime_error("unsupported: unknown descriptor_type");
   DCloud d = upload_cloud(c, pts, n);
   DBuf<float4> nm(c, d.n);
   if (d.n) MM_CUDA(cudaMemcpyAsync(nm.p, normals, (size_t)d.n * sizeof(float4), cudaMemcpyHostToDevice, c.stream));
@@ -565,9 +564,10 @@ int mm3d_descriptors(mm3d_ctx* ctx, const float* pts, uint64_t n, const float* n
   std::vector<DIndex> idx;
   build_index_batch(c, {d.view()}, (float)auto_leaf(index_leaf, radius, 8.0), 2, 0, 0, idx);
   std::vector<DBuf<float>> desc, sp;
-  const int D = type == MM3D_DESC_SHOT ? 1344 : (type == MM3D_DESC_PFH ? 125 : (type == MM3D_DESC_PFHRGB ? 250 : (type == MM3D_DESC_RSD ? 2 : 33)));
-  if (type == MM3D_DESC_RSD) {
-    rsd_batch(c, {d.view()}, idx, {nm.p}, kp, radius, desc);
+  const int D = type == MM3D_DESC_SHOT ? 1344 : (type == MM3D_DESC_PFH ? 125 : (type == MM3D_DESC_PFHRGB ? 250 : (type == MM3D_DESC_RSD ? 2 : (type == MM3D_DESC_SC3D ? 1980 : 33))));
+  if (type == MM3D_DESC_RSD || type == MM3D_DESC_SC3D) {
+    if (type == MM3D_DESC_RSD) rsd_batch(c, {d.view()}, idx, {nm.p}, kp, radius, desc);
+    else sc3d_batch(c, {d.view()}, idx, {nm.p}, kp, radius, desc);
     if (spfh) { sp.resize(1); }
   } else if (type == MM3D_DESC_PFH || type == MM3D_DESC_PFHRGB) {
     pfh_batch(c, {d.view()}, idx, {nm.p}, kp, radius, desc, type == MM3D_DESC_PFHRGB);

@@ -520,6 +520,8 @@ void pfh_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<D
 // knn_tc.cu — K9 on tensor cores: per row of map a (the first na rows), the k nearest rows of map b, exact after re-rank
 void rsd_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<const float4*>& normals,
                std::vector<DCloud>& keypoints, double radius, std::vector<DBuf<float>>& desc);
+void sc3d_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<const float4*>& normals,
+                std::vector<DCloud>& keypoints, double radius, std::vector<DBuf<float>>& desc);
 struct KnnProblem {
   int a, b;  // indices into desc / n_rows
   int na;

@@ -56,8 +56,10 @@ static inline float m_atan2f(float y, float x) { return ::atan2f(y, x); }
 static inline float m_cosf(float x) { return ::cosf(x); }
 static inline float m_sinf(float x) { return ::sinf(x); }
 static inline double m_acos(double x) { return ::acos(x); }
+static inline float m_acosf(float x) { return ::acosf(x); }
 #else
 static inline double m_acos(double x) { return em::acos_d_(x); }
+static inline float m_acosf(float x) { return (float)em::acos_d_((double)x); }
 static inline float m_expf(float x) { return em::expf_(x); }
 static inline float m_atan2f(float y, float x) { return em::atan2f_(y, x); }
 static inline float m_cosf(float x) { return em::cosf_small_(x); }
@@ -1134,6 +1136,149 @@ static std::vector<float> rsd_descriptors(const Cloud& surface, const Normals& n
 }
 
 // ===========================================================================
+// a8-SC3D  computeLocalDescriptors(SC3D) -> pcl::ShapeContext3DEstimation<PointXYZRGB, Normal, ShapeContext1980>
+// [REF src/dispatch_descriptors.h:47-48] [PCL-recall pcl/features/impl/3dsc.hpp initCompute + computePoint, 3dsc.h ctor:
+//  azimuth 12 x elevation 11 x radius 15 = 1980 bins, min_radius 0.1, point_density_radius 0.2; log-spaced radii;
+//  volume LUT 1 / cbrt(V); x axis = three draws of boost::uniform_01<mt19937> (seed 12345u, one estimator per call)
+//  made orthogonal to the normal of the NEAREST surface point; every neighbour adds 1 / (local density * cbrt(V))
+//  to its (azimuth, elevation, radius) bin.  The rf[9] of ShapeContext1980 is zeroed and is not part of the matcher's
+//  point representation.]
+// Canonical choices: neighbours in ascending index (PCL: ascending distance) for the float bin sums; nearest = smallest
+// (d^2, index); Eigen's 3-vector reductions taken left to right; the LUTs use the host libm (both sides build them on the
+// host with the same calls).
+// ===========================================================================
+struct Sc3dTables {
+  float radii[16], theta_div[12], phi_div[13], volume_lut[1980];
+};
+static void sc3d_tables(double search_radius, Sc3dTables& t)
+{
+  const size_t azimuth_bins = 12, elevation_bins = 11, radius_bins = 15;
+  const double min_radius = 0.1;
+  const float azimuth_interval = 360.0f / (float)azimuth_bins;
+  const float elevation_interval = 180.0f / (float)elevation_bins;
+  for (size_t j = 0; j < radius_bins + 1; j++)
+    t.radii[j] = (float)(exp(log(min_radius) + (((float)j / (float)radius_bins) * log(search_radius / min_radius))));
+  for (size_t k = 0; k < elevation_bins + 1; k++) t.theta_div[k] = (float)k * elevation_interval;
+  for (size_t l = 0; l < azimuth_bins + 1; l++) t.phi_div[l] = (float)l * azimuth_interval;
+  const float integr_phi = (t.phi_div[1] * 0.017453293f) - (t.phi_div[0] * 0.017453293f);  // pcl::deg2rad (float)
+  const float e = 1.0f / 3.0f;
+  for (size_t j = 0; j < radius_bins; j++) {
+    const float integr_r =
+        (t.radii[j + 1] * t.radii[j + 1] * t.radii[j + 1] / 3.0f) - (t.radii[j] * t.radii[j] * t.radii[j] / 3.0f);
+    for (size_t k = 0; k < elevation_bins; k++) {
+      const float integr_theta = cosf(t.theta_div[k] * 0.017453293f) - cosf(t.theta_div[k + 1] * 0.017453293f);
+      const float V = integr_phi * integr_theta * integr_r;
+      for (size_t l = 0; l < azimuth_bins; l++) t.volume_lut[(l * elevation_bins * radius_bins) + k * radius_bins + j] = 1.0f / powf(V, e);
+    }
+  }
+}
+
+static std::vector<float> sc3d_descriptors(const Cloud& surface, const Normals& normals, Cloud& keypoints, double radius)
+{
+  const size_t azimuth_bins = 12, elevation_bins = 11, radius_bins = 15;
+  const double point_density_radius = 0.2, min_radius = 0.1;
+  std::vector<float> out;
+  Cloud kept;
+  if (radius < min_radius) {  // initCompute fails: "search_radius_ must be GREATER than min_radius_" -> empty output
+    keypoints.swap(kept);
+    return out;
+  }
+  Sc3dTables tb;
+  sc3d_tables(radius, tb);
+  Grid tree;
+  tree.build(surface, (float)radius);
+  // local point density of every surface point (computed on demand in PCL, identical values)
+  std::vector<int> density(surface.size(), -1);
+  const float dr2 = (float)(point_density_radius * point_density_radius);
+  std::mt19937 rng(12345u);                                                  // == boost::mt19937
+  auto rnd = [&]() { return (double)rng() * (1.0 / 4294967296.0); };         // boost::uniform_01<mt19937>
+  auto is_zero = [](float v) { return std::fabs(v - 0.0f) < FLT_MIN; };      // pcl::utils::equal (v, 0.0f)
+  std::vector<int> idx;
+  std::vector<float> sqd;
+  std::vector<float> desc(1980);
+  for (size_t kp = 0; kp < keypoints.size(); ++kp) {
+    const P4& o = keypoints[kp];
+    if (!std::isfinite(o.x) || !std::isfinite(o.y) || !std::isfinite(o.z)) continue;  // NaN descriptor -> dropped
+    tree.radius_sorted(o.x, o.y, o.z, radius, idx, sqd);
+    if (idx.empty()) continue;  // NaN descriptor -> dropped; no random numbers drawn
+    size_t b = 0;
+    for (size_t i = 1; i < idx.size(); ++i)
+      if (sqd[i] < sqd[b]) b = i;
+    const float normal[3] = {normals[idx[b]].nx, normals[idx[b]].ny, normals[idx[b]].nz};
+    float x_axis[3];
+    x_axis[0] = (float)rnd();
+    x_axis[1] = (float)rnd();
+    x_axis[2] = (float)rnd();
+    if (!is_zero(normal[2])) x_axis[2] = -(normal[0] * x_axis[0] + normal[1] * x_axis[1]) / normal[2];
+    else if (!is_zero(normal[1])) x_axis[1] = -(normal[0] * x_axis[0] + normal[2] * x_axis[2]) / normal[1];
+    else if (!is_zero(normal[0])) x_axis[0] = -(normal[1] * x_axis[1] + normal[2] * x_axis[2]) / normal[0];
+    {
+      const float z = (x_axis[0] * x_axis[0] + x_axis[1] * x_axis[1]) + x_axis[2] * x_axis[2];  // Eigen normalize()
+      if (z > 0.0f) {
+        const float nrm = std::sqrt(z);
+        for (int a = 0; a < 3; ++a) x_axis[a] /= nrm;
+      }
+    }
+    for (float& v : desc) v = 0.0f;
+    for (size_t ne = 0; ne < idx.size(); ++ne) {
+      if (is_zero(sqd[ne])) continue;
+      const P4& q = surface[idx[ne]];
+      const float r = std::sqrt(sqd[ne]);
+      // pcl::geometry::project (neighbour, origin, normal, proj); proj -= origin
+      const float po[3] = {q.x - o.x, q.y - o.y, q.z - o.z};
+      const float lambda = (normal[0] * po[0] + normal[1] * po[1]) + normal[2] * po[2];
+      float proj[3] = {q.x - lambda * normal[0], q.y - lambda * normal[1], q.z - lambda * normal[2]};
+      proj[0] -= o.x; proj[1] -= o.y; proj[2] -= o.z;
+      {
+        const float z = (proj[0] * proj[0] + proj[1] * proj[1]) + proj[2] * proj[2];
+        if (z > 0.0f) {
+          const float nrm = std::sqrt(z);
+          for (int a = 0; a < 3; ++a) proj[a] /= nrm;
+        }
+      }
+      float cr[3];
+      cross3(x_axis, proj, cr);
+      const float cr_norm = std::sqrt((cr[0] * cr[0] + cr[1] * cr[1]) + cr[2] * cr[2]);
+      float phi = m_atan2f(cr_norm, (x_axis[0] * proj[0] + x_axis[1] * proj[1]) + x_axis[2] * proj[2]) * 57.29578f;  // pcl::rad2deg
+      phi = ((cr[0] * normal[0] + cr[1] * normal[1]) + cr[2] * normal[2]) < 0.f ? (360.0f - phi) : phi;
+      float no[3] = {po[0], po[1], po[2]};
+      {
+        const float z = (no[0] * no[0] + no[1] * no[1]) + no[2] * no[2];
+        if (z > 0.0f) {
+          const float nrm = std::sqrt(z);
+          for (int a = 0; a < 3; ++a) no[a] /= nrm;
+        }
+      }
+      float theta = (normal[0] * no[0] + normal[1] * no[1]) + normal[2] * no[2];
+      theta = m_acosf(std::min(1.0f, std::max(-1.0f, theta))) * 57.29578f;
+      size_t j = 0, k = 0, l = 0;
+      for (size_t rad = 1; rad < radius_bins + 1; rad++)
+        if (r <= tb.radii[rad]) { j = rad - 1; break; }
+      for (size_t ang = 1; ang < elevation_bins + 1; ang++)
+        if (theta <= tb.theta_div[ang]) { k = ang - 1; break; }
+      for (size_t ang = 1; ang < azimuth_bins + 1; ang++)
+        if (phi <= tb.phi_div[ang]) { l = ang - 1; break; }
+      int& dens = density[idx[ne]];
+      if (dens < 0) {
+        dens = 0;
+        tree.for_radius(q.x, q.y, q.z, (float)point_density_radius, dr2, [&](int, float) { ++dens; });
+      }
+      if (dens == 0) continue;
+      const float w = (1.0f / (float)dens) * tb.volume_lut[(l * elevation_bins * radius_bins) + (k * radius_bins) + j];
+      desc[(l * elevation_bins * radius_bins) + (k * radius_bins) + j] += w;
+    }
+    bool finite = true;
+    for (float v : desc)
+      if (!std::isfinite(v)) finite = false;
+    if (!finite) continue;
+    out.insert(out.end(), desc.begin(), desc.end());
+    kept.push_back(keypoints[kp]);
+  }
+  keypoints.swap(kept);
+  return out;
+}
+
+// ===========================================================================
 // a8-SHOT  computeLocalDescriptors(SHOT) -> pcl::SHOTColorEstimation<PointXYZRGB, Normal, SHOT1344>
 // [REF src/dispatch_descriptors.h:46, src/features.cpp:99-150]
 // [PCL-recall pcl/features/impl/shot.hpp (computeFeature, computePointSHOT, createBinDistanceShape,
@@ -2126,8 +2271,9 @@ static void map_features(const Cloud& in, const Params& p, MapFeatures& f, Stage
   else if (p.descriptor_type == 0) f.desc = pfh_descriptors(f.cloud, f.normals, f.keypoints, p.descriptor_radius);
   else if (p.descriptor_type == 1) f.desc = pfhrgb_descriptors(f.cloud, f.normals, f.keypoints, p.descriptor_radius);
   else if (p.descriptor_type == 3) f.desc = rsd_descriptors(f.cloud, f.normals, f.keypoints, p.descriptor_radius);
+  else if (p.descriptor_type == 5) f.desc = sc3d_descriptors(f.cloud, f.normals, f.keypoints, p.descriptor_radius);
   else f.desc = fpfh_descriptors(f.cloud, f.normals, f.keypoints, p.descriptor_radius);
-  f.dim = p.descriptor_type == 4 ? 1344 : (p.descriptor_type == 0 ? 125 : (p.descriptor_type == 1 ? 250 : (p.descriptor_type == 3 ? 2 : 33)));
+  f.dim = p.descriptor_type == 4 ? 1344 : (p.descriptor_type == 0 ? 125 : (p.descriptor_type == 1 ? 250 : (p.descriptor_type == 3 ? 2 : (p.descriptor_type == 5 ? 1980 : 33))));
   double t5 = now_s();
   if (st) {
     st->t[0] += t1 - t0; st->t[1] += t2 - t1; st->t[2] += t3 - t2; st->t[3] += t4 - t3; st->t[4] += t5 - t4;
@@ -2332,6 +2478,20 @@ int orc_rsd(const float* pts, uint64_t n, const float* normals, const float* kp_
   if (n) memcpy(nm.data(), normals, n * sizeof(N4));
   Cloud kp = to_cloud(kp_in, nk_in);
   std::vector<float> d = rsd_descriptors(surf, nm, kp, radius);
+  *kp_out = dup_f(kp.data(), kp.size() * sizeof(P4));
+  *nk_out = kp.size();
+  *desc = dup_f(d.data(), d.size() * 4);
+  return 0;
+}
+
+int orc_sc3d(const float* pts, uint64_t n, const float* normals, const float* kp_in, uint64_t nk_in, double radius, float** kp_out,
+             uint64_t* nk_out, float** desc)
+{
+  Cloud surf = to_cloud(pts, n);
+  Normals nm(n);
+  if (n) memcpy(nm.data(), normals, n * sizeof(N4));
+  Cloud kp = to_cloud(kp_in, nk_in);
+  std::vector<float> d = sc3d_descriptors(surf, nm, kp, radius);
   *kp_out = dup_f(kp.data(), kp.size() * sizeof(P4));
   *nk_out = kp.size();
   *desc = dup_f(d.data(), d.size() * 4);

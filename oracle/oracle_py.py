@@ -166,6 +166,14 @@ class Oracle:
         d = _take(desc, nko.value * 2, np.float32, (-1, 2)); self._free(desc)
         return kout, d
 
+    def sc3d(self, pts, normals, kp, radius):
+        a, ap = _f(pts); nm, nmp = _f(normals); k, kpp = _f(kp)
+        ko = f32p(); nko = C.c_uint64(); desc = f32p()
+        self.lib.orc_sc3d(ap, C.c_uint64(len(a)), nmp, kpp, C.c_uint64(len(k)), C.c_double(radius), C.byref(ko), C.byref(nko), C.byref(desc))
+        kout = _take(ko, nko.value * 4, np.float32, (-1, 4)); self._free(ko)
+        d = _take(desc, nko.value * 1980, np.float32, (-1, 1980)); self._free(desc)
+        return kout, d
+
     def shot(self, pts, normals, kp, radius, debug=False):
         a, ap = _f(pts); nm, nmp = _f(normals); k, kpp = _f(kp)
         ko = f32p(); nko = C.c_uint64(); desc = f32p(); rf = f32p()

@@ -226,6 +226,29 @@ def test_rsd_bit_exact(ctx, mm, oracle, tiny_stages, tiny_maps):
     np.testing.assert_allclose(got, want["transforms"], rtol=0, atol=1e-5)
 
 
+def test_sc3d_bit_exact(ctx, mm, oracle, tiny_stages, tiny_maps):
+    """3D shape context (1980 bins; random x axis from the estimator's mt19937(12345) stream, three draws per keypoint that
+    has neighbours): stage parity, then the whole path with descriptor_type SC3D."""
+    import oracle_py
+    for st in tiny_stages:
+        # a keypoint without neighbours in the middle: dropped, and it must not consume random numbers
+        kp_in = np.concatenate([st["kp_sift"][:100], np.array([[70, 70, 70, 0]], np.float32), st["kp_sift"][100:200]])
+        wk, wd = oracle.sc3d(st["filtered"], st["normals"], kp_in, 0.8)
+        gk, gd = ctx.descriptors(st["filtered"], st["normals"], kp_in, type="SC3D", radius=0.8, index_leaf=0.1)
+        assert wd.shape == (200, 1980)
+        assert_same_bits(gk, wk, "kept keypoints")
+        assert_same_bits(gd, wd, "SC3D descriptors")
+        assert ((gd > 0).sum(1) > 20).all()
+    # support radius below min_radius (0.1): initCompute fails in PCL, nothing comes back
+    gk, gd = ctx.descriptors(st["filtered"], st["normals"], kp_in, type="SC3D", radius=0.05, index_leaf=0.1)
+    assert len(gk) == 0 and gd.size == 0
+    maps, _ = tiny_maps
+    sub = [m[:12000] for m in maps]
+    want = oracle.estimate_maps_transforms(sub, oracle_py.default_params(descriptor_type=5))
+    got = ctx.estimate_maps_transforms(sub, mm.default_params(descriptor_type="SC3D"))
+    np.testing.assert_allclose(got, want["transforms"], rtol=0, atol=1e-5)
+
+
 def test_default_params_pipeline_matches_oracle(ctx, mm, oracle, tiny_maps):
     """MapMergingParams() as shipped: SIFT + PFH + MATCHING + ICP (map_merging.h:29-44)."""
     import oracle_py
