@@ -186,7 +186,8 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
 
 
 def cpu_baseline_sample(maps, M, P):
@@ -222,11 +223,12 @@ class Job:
         self.sh = importlib.import_module("map_merge_b200.sharding")
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.rank = int(os.environ.get("RANK", "0"))
+        self.phases_on = os.environ.get("MM3D_BENCH_PHASES") == "1"
+        self.phase_ms = {}
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
         if self.world > 1:
-            os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
             dist.init_process_group("nccl", device_id=self.dev)
         self.ctx = self.mm.Context(self.local, stream=torch.cuda.current_stream().cuda_stream)
         self.p = self.mm.default_params(descriptor_type="FPFH")
@@ -252,10 +254,22 @@ class Job:
         return self.ctx.estimate_resident(self.resident, self.p)
 
     # -- sharded -----------------------------------------------------------
+    def _phase(self, name):
+        """MM3D_BENCH_PHASES=1: synchronising per-phase wall times on every rank (diagnostic; perturbs the step)."""
+        if not self.phases_on:
+            return
+        self.torch.cuda.synchronize()
+        now = time.perf_counter()
+        self.phase_ms[name] = self.phase_ms.get(name, 0.0) + (now - self._t_phase) * 1e3
+        self._t_phase = now
+
     def step_sharded(self, from_host: bool):
         torch, dist = self.torch, self.dist
+        if self.phases_on:
+            torch.cuda.synchronize(); self._t_phase = time.perf_counter()
         maps = self.ctx.maps_upload([t.numpy() for t in self.host]) if from_host else self.resident
         feats = self.ctx.features_compute(maps, 0, self.count, self.p)
+        self._phase("features")
         npt, nk, dim = feats.sizes()
         per = -(-self.M // self.world)
         sizes = torch.zeros((per, 2), dtype=torch.int32, device=self.dev)
@@ -274,6 +288,7 @@ class Job:
             feats.export_dev(m, base, base + max_pt * 16, base + (max_pt + max_kp) * 16)
         recv = torch.empty((self.world, per, row), dtype=torch.float32, device=self.dev)
         dist.all_gather_into_tensor(recv, send)
+        self._phase("exchange")
         n_points, n_kp, pp, kp, dp = [], [], [], [], []
         for m in range(self.M):
             r, l = self.owner_of_map[m], m - self.owner_of_map[m] * per
@@ -285,7 +300,9 @@ class Job:
         ij = self.sh.pair_list(n_kp)
         owner = self.sh.lpt_assign(self.sh.pair_costs(ij, n_points, n_kp, dim), self.world) if ij else np.zeros(0, np.int64)
         mine = [k for k in range(len(ij)) if owner[k] == self.rank]
+        self._phase("import")
         T, conf, stats = self.ctx.register_pairs(allf, [ij[k] for k in mine], self.p)
+        self._phase("register")
         # every rank fills its own slots of the row-major pair list (keeps the reference's pair order)
         res = self.sh.gather_pair_results(dist, torch, self.dev, len(ij), mine, T, conf)
         out = None
@@ -293,6 +310,7 @@ class Job:
             h = res.cpu().numpy()
             out, _ = self.mm.global_transforms(np.array(ij, np.int32), h[:, :16].reshape(-1, 4, 4).astype(np.float32), h[:, 16],
                                                self.p.confidence_threshold)
+        self._phase("results+graph")
         return out
 
     def step(self, from_host: bool):
@@ -333,7 +351,11 @@ def run_gpu(args):
     if job.rank == 0:
         sampler.start()  # nvidia-smi needs ~0.5 s to produce its first sample: start it one (identical, untimed) pass early
     job.timed(max(args.steps, 10), from_host=False, profile=True)  # untimed: also fills the library's CUDA-event pool
+    job.phase_ms = {}
     ms, launches, prof, out = job.timed(args.steps, from_host=False, profile=True)
+    if job.phases_on:
+        print(f"[phases] rank {job.rank}: " + ", ".join(f"{k} {v / args.steps:.2f} ms" for k, v in job.phase_ms.items()) +
+              f"; step {ms / args.steps:.2f} ms", file=sys.stderr, flush=True)
     clocks = sampler.stop() if job.rank == 0 else None
     job.step(True)  # warm the host path
     ms_e2e, _, _, out_e2e = job.timed(args.steps, from_host=True, profile=False)
@@ -380,9 +402,13 @@ def run_gpu(args):
         line["cpu_baseline"] = cb
     else:
         line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "timed at N=1 only"}
-    print(json.dumps(line), flush=True)
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
     if job.world > 1:
         job.dist.destroy_process_group()
+
+
+_OUT = sys.stdout
 
 
 def main():
@@ -394,6 +420,12 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: keep a private handle to it and point fd 1 at stderr, so that anything a
+    # library writes to stdout (NCCL prints its version banner there) cannot get in front of the line
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
