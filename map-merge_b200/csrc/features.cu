@@ -360,13 +360,16 @@ struct FpfhJob {
   uint32_t* valid3;       // nk x 3
 };
 
+// marks the surface points whose SPFH is needed (the neighbours of the keypoints): warp per keypoint, order-free walk
 __global__ void __launch_bounds__(FB) fpfh_mark_kernel(const FpfhJob* __restrict__ jobs, float r2, int rv)
 {
   const FpfhJob& j = jobs[blockIdx.y];
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = t < j.nk;
-  const float4 q = live ? j.kp[t] : make_float4(0.f, 0.f, 0.f, 0.f);
-  for_each_in_radius(j.g, live, q.x, q.y, q.z, r2, rv, [&](int k, const float4&, float) { j.need[k] = 1u; });
+  const int t = blockIdx.x * (FB / 32) + (threadIdx.x >> 5);
+  if (t >= j.nk) return;  // warp-uniform
+  const float4 q = j.kp[t];
+  warp_radius_unordered(j.g, q.x, q.y, q.z, r2, rv, [&](bool valid, int k, const float4&, float) {
+    if (valid) j.need[k] = 1u;
+  });
 }
 
 // warp per surface point: candidates that pass the radius test are queued so that the pair-feature block always
@@ -411,41 +414,62 @@ __global__ void __launch_bounds__(FB) spfh_kernel(const FpfhJob* __restrict__ jo
   }
 }
 
-// weightPointSPFHSignature: one thread per (keypoint, feature block of 11 bins)
+// weightPointSPFHSignature, warp per keypoint: lane L owns bin L (lane 0 also bin 32), so one coalesced 132-byte row read
+// per neighbour feeds all 33 float sums; the neighbours of a batch are replayed in ascending index order through shuffles.
+// The three block sums are sequential double sums over (neighbour, bin) — lanes 0, 11 and 22 collect their block's eleven
+// values in order with per-lane shuffle sources.
 __global__ void __launch_bounds__(FB) fpfh_weight_kernel(const FpfhJob* __restrict__ jobs, float r2, int rv)
 {
+  __shared__ int queues[FB / 32][64];
   const FpfhJob& j = jobs[blockIdx.y];
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = t < j.nk * 3;
-  const int kp = live ? t / 3 : 0, f = live ? t - kp * 3 : 0;
-  const float4 q = live ? j.kp[kp] : make_float4(0.f, 0.f, 0.f, 0.f);
-  float acc[11];
-#pragma unroll
-  for (int i = 0; i < 11; ++i) acc[i] = 0.f;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kp = blockIdx.x * (FB / 32) + w;
+  if (kp >= j.nk) return;  // warp-uniform
+  const unsigned full = 0xffffffffu;
+  const float4 q = j.kp[kp];
+  const int f = lane < 11 ? 0 : (lane < 22 ? 1 : 2);  // feature block of bin `lane`
+  const int base = f * 11;                             // collector lanes are 0, 11, 22
+  float acc = 0.f, acc32 = 0.f;
   double sum = 0.0;
-  int found = 0;
-  for_each_in_radius(j.g, live, q.x, q.y, q.z, r2, rv, [&](int k, const float4&, float d2) {
-    ++found;
-    if (d2 == 0.f) return;
-    const float weight = 1.0f / d2;
-    const float* h = j.spfh + (size_t)k * 33 + f * 11;
+  const int found = warp_radius_query<true>(j.g, q.x, q.y, q.z, r2, rv, queues[w], [&](int slot) {
+    float weight = 0.f;
+    if (slot >= 0) {
+      const float4 p = j.g.pts[slot];
+      const float d2 = em::dist2_3(q.x, q.y, q.z, p.x, p.y, p.z);
+      weight = d2 == 0.f ? 0.f : 1.0f / d2;  // a neighbour at distance 0 is skipped
+    }
+    const unsigned have = __ballot_sync(full, slot >= 0);
+    const int m = __popc(have);
+    for (int t = 0; t < m; ++t) {
+      const int s = __shfl_sync(full, slot, t);
+      const float wt = __shfl_sync(full, weight, t);
+      if (wt == 0.f) continue;  // warp-uniform
+      const float* h = j.spfh + (size_t)s * 33;
+      const float val = h[lane] * wt;
+      const float val32 = lane == 0 ? h[32] * wt : 0.f;
+      acc += val;
+      acc32 += val32;
+      const float v32 = __shfl_sync(full, val32, 0);
 #pragma unroll
-    for (int i = 0; i < 11; ++i) {
-      const float val = h[i] * weight;
-      sum += (double)val;
-      acc[i] += val;
+      for (int i = 0; i < 11; ++i) {
+        float v = __shfl_sync(full, val, (base + i) & 31);
+        if (base + i == 32) v = v32;
+        sum += (double)v;  // meaningful on lanes 0, 11, 22
+      }
     }
   });
-  if (!live) return;
+  // 100 / sum of the block, broadcast from its collector lane
   if (sum != 0.0) sum = 100.0 / sum;
-  bool ok = found > 0;
-#pragma unroll
-  for (int i = 0; i < 11; ++i) {
-    const float v = acc[i] * (float)sum;
-    if (!isfinite(v)) ok = false;
-    j.desc_raw[(size_t)kp * 33 + f * 11 + i] = v;
-  }
-  j.valid3[t] = ok ? 1u : 0u;
+  const float scale = (float)__shfl_sync(full, sum, base);
+  const float scale2 = (float)__shfl_sync(full, sum, 22);
+  const float v = acc * scale;
+  const float v32 = acc32 * scale2;
+  bool fin = isfinite(v);
+  if (lane == 0) fin = fin && isfinite(v32);
+  const bool ok = __all_sync(full, fin) && found > 0;
+  j.desc_raw[(size_t)kp * 33 + lane] = v;
+  if (lane == 0) j.desc_raw[(size_t)kp * 33 + 32] = v32;
+  if (lane < 3) j.valid3[kp * 3 + lane] = ok ? 1u : 0u;
 }
 
 struct FpfhFlagJob {
@@ -894,12 +918,12 @@ void fpfh_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<
   DBuf<FpfhJob> dj = to_device(c, jobs);
   const float r2 = (float)(radius * radius);
   const int rv = radius_voxels(radius, idx[0].v.leaf);
-  MM_LAUNCH(c, fpfh_mark_kernel, dim3((mxk + FB - 1) / FB, M), FB, 0, dj.p, r2, rv);
+  MM_LAUNCH(c, fpfh_mark_kernel, dim3((mxk + FB / 32 - 1) / (FB / 32), M), FB, 0, dj.p, r2, rv);
   { double b = 0; for (int m = 0; m < M; ++m) b += (32.0 + 132.0 + 4.0) * clouds[m].n; MM_BYTES(c, b); }
   static const BinTable bins = make_bin_table(11);
   MM_LAUNCH(c, spfh_kernel, dim3((mx + FB / 32 - 1) / (FB / 32), M), FB, 0, dj.p, r2, rv, bins);
   { double b = 0; for (int m = 0; m < M; ++m) b += (16.0 + 132.0) * clouds[m].n + (16.0 + 132.0) * nks[m]; MM_BYTES(c, b); }
-  MM_LAUNCH(c, fpfh_weight_kernel, dim3((mxk * 3 + FB - 1) / FB, M), FB, 0, dj.p, r2, rv);
+  MM_LAUNCH(c, fpfh_weight_kernel, dim3((mxk + FB / 32 - 1) / (FB / 32), M), FB, 0, dj.p, r2, rv);
   DBuf<uint32_t> flags(c, totalk), pos(c, totalk);
   std::vector<FpfhFlagJob> fj(M);
   for (int m = 0; m < M; ++m) fj[m] = FpfhFlagJob{valid3[m].p, flags.p + segk[m].off, nks[m]};

@@ -235,7 +235,9 @@ __device__ __forceinline__ void for_each_in_radius(const GridView& g, bool live,
 //   visit(slot)           called by every lane that has a passing candidate `slot` (dense: lanes 0..m-1)
 //   returns the number of candidates that passed
 // queue: 64 ints of shared memory owned by this warp.
-template <typename F>
+// ALL = true: visit is always called by all 32 lanes (slot = -1 on the lanes past the end of the last batch), so it may use
+// warp collectives.
+template <bool ALL = false, typename F>
 __device__ __forceinline__ int warp_radius_query(const GridView& g, float qx, float qy, float qz, float r2, int rv, int* queue, F visit)
 {
   const int lane = threadIdx.x & 31;
@@ -320,7 +322,11 @@ __device__ __forceinline__ int warp_radius_query(const GridView& g, float qx, fl
       }
     }
   }
-  if (lane < qcount) visit(queue[lane]);
+  if (ALL) {
+    if (qcount > 0) visit(lane < qcount ? queue[lane] : -1);
+  } else if (lane < qcount) {
+    visit(queue[lane]);
+  }
   __syncwarp();
   return passed;
 }
