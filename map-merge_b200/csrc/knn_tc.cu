@@ -49,6 +49,8 @@ struct TcJob {
   const float4* padB;
   float bmax;  // max ||b - mean||^2
   int k;
+  int* dense_rows;            // rows of this job that are handed to the exact scan (D = 33 path), capacity na
+  unsigned int* dense_count;  // their number
   int* idx;     // na x k
   float* dist;  // na x k
 };
@@ -308,6 +310,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
     }
     float thr = live ? INF : -INF;   // acc-space filter bound, only ever shrinks
     float thr_exact = INF;
+    bool dense = false;  // D = 33 path: the row is tie-heavy and goes to the exact scan instead
     int n = 0;
     unsigned evals = 0, early = 0;
     float* lv = list_v + lrow;
@@ -345,6 +348,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
       const int jbase = nt * TN + c0;
       const int left = job.nb - jbase;  // columns past nb are zero rows of the B form
       if (left < 32) mask &= left <= 0 ? 0u : ((1u << left) - 1u);
+      if (DREG > 0 && ch >= 4 && __popc(mask) >= 8) {
+        // a quarter of a chunk inside the margin after 128 columns have tightened the bound: a tie-heavy row (an ordinary
+        // row passes ~2 columns here).  Hand it to the exact scan now instead of filling and compacting its list first;
+        // a false positive only costs time.
+        dense = true;
+        ++early;
+        n = 0;
+        thr = -INF;
+        mask = 0;
+      }
       while (mask) {
         const int c = __ffs(mask) - 1;
         mask &= mask - 1;
@@ -387,7 +400,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
           }
         }
         n = w;
-        if (n > LIST_CAP - 32 || last) {
+        if (DREG > 0 && n > LIST_CAP - 32 && !last) {
+          // more than LIST_CAP - 32 columns tie with the k-th nearest inside the error margin (clustered descriptors):
+          // evaluating them here would stall the pipeline on a few diverged lanes — the exact scan kernel takes the row
+          dense = true;
+          ++early;
+          n = 0;
+          thr = -INF;
+        } else if (n > LIST_CAP - 32 || last) {
           if (!last) ++early;
           for (int t = 0; t < n; ++t) {
             const int jcol = lj[t * TM];
@@ -423,7 +443,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
 #pragma unroll
       for (int c = 0; c < 32; ++c) r[c] = rn[c];
     }
-    if (live) {
+    if (live && dense) {
+      job.dense_rows[atomicAdd(job.dense_count, 1u)] = row;
+    } else if (live) {
       const int k = job.k;
 #pragma unroll
       for (int t = 0; t < KCAP; ++t)
@@ -448,6 +470,81 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+// Exact FP32 scan of the rows the tensor-core pass handed over (same arithmetic and tie order as knn_small_kernel in
+// matching.cu): one thread per listed row, B streams through shared memory dimension-major.
+template <int D, int K>
+__global__ void __launch_bounds__(128) knn_dense_rows_kernel(const TcJob* __restrict__ jobs)
+{
+  constexpr int TB = 64;
+  __shared__ __align__(16) float sb[D * TB];
+  const TcJob j = jobs[blockIdx.y];
+  const int n_dense = (int)*j.dense_count;
+  if ((int)(blockIdx.x * blockDim.x) >= n_dense) return;
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = li < n_dense;
+  const int row = live ? j.dense_rows[li] : 0;
+  float a[D];
+#pragma unroll
+  for (int t = 0; t < D; ++t) a[t] = live ? j.origA[(size_t)row * D + t] : 0.f;
+  float bd[K];
+  int bi[K];
+#pragma unroll
+  for (int t = 0; t < K; ++t) {
+    bd[t] = __int_as_float(0x7f800000);
+    bi[t] = -1;
+  }
+  for (int base = 0; base < j.nb; base += TB) {
+    const int tb = min(TB, j.nb - base);
+    __syncthreads();
+    for (int e = threadIdx.x; e < TB * D; e += blockDim.x) {
+      const int r = e / D, t = e - r * D;
+      sb[t * TB + r] = (r < tb) ? j.origB[(size_t)(base + r) * D + t] : 0.f;
+    }
+    __syncthreads();
+    if (!live) continue;
+    for (int r0 = 0; r0 < tb; r0 += 4) {
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+      for (int t = 0; t < D; ++t) {
+        const float4 b = *reinterpret_cast<const float4*>(&sb[t * TB + r0]);
+        const float d0 = a[t] - b.x, d1 = a[t] - b.y, d2 = a[t] - b.z, d3 = a[t] - b.w;
+        acc0 += d0 * d0;
+        acc1 += d1 * d1;
+        acc2 += d2 * d2;
+        acc3 += d3 * d3;
+      }
+      const float accs[4] = {acc0, acc1, acc2, acc3};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float cd = accs[u];
+        if (r0 + u < tb && cd < bd[K - 1]) {
+          int ci = base + r0 + u;
+#pragma unroll
+          for (int t = 0; t < K; ++t) {  // strict <: ties keep the lower column
+            if (cd < bd[t]) {
+              const float td = bd[t];
+              const int ti = bi[t];
+              bd[t] = cd;
+              bi[t] = ci;
+              cd = td;
+              ci = ti;
+            }
+          }
+        }
+      }
+    }
+  }
+  if (live) {
+    const int k = j.k;
+#pragma unroll
+    for (int t = 0; t < K; ++t)
+      if (t < k) {
+        j.idx[(size_t)row * k + t] = bi[t];
+        j.dist[(size_t)row * k + t] = bi[t] >= 0 ? bd[t] : 0.f;
+      }
   }
 }
 
@@ -635,9 +732,19 @@ void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vect
   std::vector<TcJob> tj;
   int max_na = 0, kmax = 0;
   double bytes = 0;
+  size_t rows_total = 0, n_jobs = 0;
+  for (const KnnProblem& p : probs)
+    if (p.na > 0 && n_rows[p.b] > 0) { rows_total += (size_t)p.na; ++n_jobs; }
+  DBuf<int> dense_rows(c, reg_path ? rows_total : 0);
+  DBuf<unsigned int> dense_count(c, n_jobs);
+  dense_count.zero(c);
+  size_t row_off = 0;
   for (const KnnProblem& p : probs) {
     if (p.na == 0 || n_rows[p.b] == 0) continue;
     TcJob j;
+    j.dense_rows = reg_path ? dense_rows.p + row_off : nullptr;
+    j.dense_count = dense_count.p + tj.size();
+    row_off += (size_t)p.na;
     j.a_map = p.a;
     j.b_map = p.b;
     j.na = p.na;
@@ -675,9 +782,17 @@ void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vect
     MM_LAUNCH(c, (knn_tc_kernel<KCAP, DREG, RES>), grid, TC_THREADS, smem, dtj.p, dA.p, dB.p, kblocks, D, c.knn_stats);          \
   } while (0)
   const bool res = kblocks <= A_RES_MAX_KB;
-  if (reg_path && kmax <= 5) MM_TC(5, 33, true);
-  else if (reg_path && kmax <= 10) MM_TC(10, 33, true);
-  else if (reg_path) MM_TC(KMAXTC, 33, true);
+  const dim3 dgrid((max_na + 127) / 128, (unsigned)tj.size());  // blocks past a job's dense count exit at once
+  if (reg_path && kmax <= 5) {
+    MM_TC(5, 33, true);
+    MM_LAUNCH(c, (knn_dense_rows_kernel<33, 5>), dgrid, 128, 0, dtj.p);
+  } else if (reg_path && kmax <= 10) {
+    MM_TC(10, 33, true);
+    MM_LAUNCH(c, (knn_dense_rows_kernel<33, 10>), dgrid, 128, 0, dtj.p);
+  } else if (reg_path) {
+    MM_TC(KMAXTC, 33, true);
+    MM_LAUNCH(c, (knn_dense_rows_kernel<33, KMAXTC>), dgrid, 128, 0, dtj.p);
+  }
   else if (res && kmax <= 5) MM_TC(5, 0, true);
   else if (res) MM_TC(KMAXTC, 0, true);
   else if (kmax <= 1) MM_TC(1, 0, false);

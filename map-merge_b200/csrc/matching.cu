@@ -619,11 +619,16 @@ void match_batch(Ctx& c, const std::vector<const float*>& desc, const std::vecto
     max_ns = std::max(max_ns, ns);
   }
   DBuf<KnnJob> dkj = to_device(c, kj);
-  // default: the brute-force FP32 scan below (72 % of the FP32 issue peak on config 3).  MM3D_KNN=tc selects the tcgen05
-  // distance GEMM + exact re-rank (knn_tc.cu): bit-identical results, faster when descriptors are well separated, slower on
-  // tightly clustered ones (hundreds of columns inside the filter's error margin; measured in profiles/README.md).
+  // 33-dimensional descriptors (FPFH, the BASELINE configs): tcgen05 distance GEMM as a filter + exact re-rank, tie-heavy
+  // rows handed to an exact scan (knn_tc.cu) — bit-identical to the FP32 scan below and faster (config 3: 197 vs 294 ms).
+  // Other dimensions default to the scan (the filter's exact evaluations still run in the epilogue there).
+  // MM3D_KNN=tc forces the tensor-core path for every dimension, MM3D_KNN=exact the scan.
   const char* knn_env = std::getenv("MM3D_KNN");
-  const bool use_tc = knn_env && std::string(knn_env) == "tc";
+  const std::string knn_mode = knn_env ? knn_env : "";
+  bool k_fits = true;
+  for (const KnnJob& q : kj)
+    if (q.na > 0 && q.k > 16) k_fits = false;  // KMAXTC
+  const bool use_tc = k_fits && (knn_mode == "tc" || (knn_mode != "exact" && dim == 33));
   if (max_rows > 0 && use_tc) {
     std::vector<KnnProblem> probs;
     for (int p = 0; p < P; ++p) {

@@ -39,8 +39,9 @@ for centred in (False, True):
         glob = 2 * E * (na[rows, None] + nb.max())
         loc = 2 * E * (na[rows, None] + nb[None, :])
         cg = (Dm <= kth[:, None] + glob).sum(1); cl = (Dm <= kth[:, None] + loc).sum(1)
-        print(f"   E={E:g}: columns within margin (global bmax) mean {cg.mean():.1f} p90 {np.percentile(cg, 90):.0f} max {cg.max()};"
-              f" (per-column norm) mean {cl.mean():.1f} p90 {np.percentile(cl, 90):.0f} max {cl.max()}")
+        print(f"   E={E:g}: columns within margin (global bmax) mean {cg.mean():.1f} median {np.median(cg):.0f} p90 {np.percentile(cg, 90):.0f} max {cg.max()}"
+              f" rows>32: {np.mean(cg > 32) * 100:.0f}%; (per-column norm) mean {cl.mean():.1f} median {np.median(cl):.0f} p90 {np.percentile(cl, 90):.0f}"
+              f" max {cl.max()} rows>32: {np.mean(cl > 32) * 100:.0f}%")
 m0 = ctx.knn_stats()
 ctx.match(descs[0], descs[1], 5)
 m1 = ctx.knn_stats()

@@ -301,13 +301,18 @@ def test_harris_shot_pipeline_matches_oracle(ctx, mm, oracle, small_maps):
 
 
 # ---------------------------------------------------------------- K9 matching
-def test_match_bit_exact(ctx, oracle, tiny_stages):
+def test_match_bit_exact(ctx, oracle, tiny_stages, monkeypatch):
     a, b = tiny_stages[0]["desc"], tiny_stages[1]["desc"]
-    for k in (1, 5, 8):
-        wp, wd = oracle.match(a, b, k)
-        gp, gd = ctx.match(a, b, k)
-        assert np.array_equal(gp, wp), f"correspondence indices differ (k={k})"
-        assert_same_bits(gd, wd, "correspondence distances")
+    for mode in (None, "exact"):  # default (tensor-core filter for 33-dim descriptors) and the plain FP32 scan
+        if mode:
+            monkeypatch.setenv("MM3D_KNN", mode)
+        else:
+            monkeypatch.delenv("MM3D_KNN", raising=False)
+        for k in (1, 5, 8, 12):
+            wp, wd = oracle.match(a, b, k)
+            gp, gd = ctx.match(a, b, k)
+            assert np.array_equal(gp, wp), f"correspondence indices differ (k={k}, mode={mode})"
+            assert_same_bits(gd, wd, "correspondence distances")
     assert len(wp) > 10
 
 
@@ -345,11 +350,12 @@ def test_tensor_core_knn_bit_exact(mm, oracle, tiny_stages, monkeypatch):
 
 
 def test_tensor_core_knn_whole_path(mm, tiny_maps, monkeypatch):
-    """estimateMapsTransforms with MM3D_KNN=tc gives the same bits as with the FP32 scan (FPFH, 33 dims, and PFH, 125 dims)."""
+    """estimateMapsTransforms with the tensor-core k-NN (default for 33-dim descriptors, MM3D_KNN=tc for the others) gives the
+    same bits as with the FP32 scan (MM3D_KNN=exact)."""
     maps, _ = tiny_maps
     for desc in ("FPFH", "PFH"):
         p = mm.default_params(descriptor_type=desc)
-        monkeypatch.delenv("MM3D_KNN", raising=False)
+        monkeypatch.setenv("MM3D_KNN", "exact")
         c = mm.Context(0)
         want = c.estimate_maps_transforms(maps, p)
         assert c.knn_stats()["rows"] == 0
