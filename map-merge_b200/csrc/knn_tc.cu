@@ -348,16 +348,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
       const int jbase = nt * TN + c0;
       const int left = job.nb - jbase;  // columns past nb are zero rows of the B form
       if (left < 32) mask &= left <= 0 ? 0u : ((1u << left) - 1u);
-      if (DREG > 0 && ch >= 4 && __popc(mask) >= 8) {
-        // a quarter of a chunk inside the margin after 128 columns have tightened the bound: a tie-heavy row (an ordinary
-        // row passes ~2 columns here).  Hand it to the exact scan now instead of filling and compacting its list first;
-        // a false positive only costs time.
-        dense = true;
-        ++early;
-        n = 0;
-        thr = -INF;
-        mask = 0;
-      }
+      // (marking a row dense as soon as one chunk passes >= 8 columns was measured: no faster on config 2, and 25 % false
+      //  positives on small sets, where the bound is still loose after 128 columns)
       while (mask) {
         const int c = __ffs(mask) - 1;
         mask &= mask - 1;

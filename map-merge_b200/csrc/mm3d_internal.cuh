@@ -253,6 +253,7 @@ __device__ __forceinline__ int warp_radius_query(const GridView& g, float qx, fl
   yhi = min(yhi, g.div_v[1] - 1) >> g.shift[1];
   const int ny = yhi - ylo + 1;
   const int n_rows = (zhi - zlo + 1) * ny;
+  const unsigned ny_magic = 0xFFFFFFFFu / (unsigned)ny + 1u;
   const float r2v = r2 * g.inv_leaf * g.inv_leaf;
   int qcount = 0, passed = 0;
   for (int row0 = 0; row0 < n_rows; row0 += 32) {
@@ -260,7 +261,8 @@ __device__ __forceinline__ int warp_radius_query(const GridView& g, float qx, fl
     int s = 0, e = 0;
     const int row = row0 + lane;
     if (row < n_rows) {
-      const int cz = zlo + row / ny, cy = ylo + row % ny;
+      const int rq = (int)__umulhi((unsigned)row, ny_magic);  // row / ny (exact for row < 2^18, ny < 512)
+      const int cz = zlo + rq, cy = ylo + (row - rq * ny);
       const int z0 = cz << g.shift[2], z1 = z0 + (1 << g.shift[2]) - 1;
       const int y0 = cy << g.shift[1], y1 = y0 + (1 << g.shift[1]) - 1;
       const float fz = (float)max(max(max(z0 - vz, vz - z1), 0) - 1, 0);
@@ -351,12 +353,14 @@ __device__ __forceinline__ void warp_radius_unordered(const GridView& g, float q
   yhi = min(yhi, g.div_v[1] - 1) >> g.shift[1];
   const int ny = yhi - ylo + 1;
   const int n_rows = (zhi - zlo + 1) * ny;
+  const unsigned ny_magic = 0xFFFFFFFFu / (unsigned)ny + 1u;
   const float r2v = r2 * g.inv_leaf * g.inv_leaf;
   for (int row0 = 0; row0 < n_rows; row0 += 32) {
     int s = 0, e = 0;
     const int row = row0 + lane;
     if (row < n_rows) {
-      const int cz = zlo + row / ny, cy = ylo + row % ny;
+      const int rq = (int)__umulhi((unsigned)row, ny_magic);  // row / ny (exact for row < 2^18, ny < 512)
+      const int cz = zlo + rq, cy = ylo + (row - rq * ny);
       const int z0 = cz << g.shift[2], z1 = z0 + (1 << g.shift[2]) - 1;
       const int y0 = cy << g.shift[1], y1 = y0 + (1 << g.shift[1]) - 1;
       const float fz = (float)max(max(max(z0 - vz, vz - z1), 0) - 1, 0);
