@@ -47,7 +47,7 @@ struct TcJob {
   const float* origB;
   const float4* padA;  // rows padded to a multiple of 4 floats (D = 33 only), else null
   const float4* padB;
-  float bmax;  // max ||b - mean||^2
+  const float* normB;  // ||b - mean||^2
   int k;
   int* dense_rows;            // rows of this job that are handed to the exact scan (D = 33 path), capacity na
   unsigned int* dense_count;  // their number
@@ -167,6 +167,9 @@ __device__ __forceinline__ float exact_dist(const float* __restrict__ a_reg, con
 // dropped a_lo.b_lo and TF32 truncation of the lo parts (3 * 2^-20), FP32 accumulation inside the tensor core, FP32 norms,
 // centring; derived in DESIGN.md §3 (K9) and padded.
 constexpr float TC_ERR = 3.0e-5f;
+// The B form carries (1 - TC_ERR_STORE) ||b'||^2, so the accumulator is a LOWER bound of the exact distance minus
+// (1 - TC_ERR_STORE) ||a'||^2; TC_ERR_STORE exceeds TC_ERR by more than the rounding of that product.
+constexpr float TC_ERR_STORE = 3.1e-5f;
 
 // KCAP = capacity of the register top lists (>= k; the first k are written out); DREG = descriptor length when the query
 // row is cached in registers (and rows are read as float4 from the padded copies), 0 = scalar reads from global memory;
@@ -275,12 +278,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
     }
   } else {
     // ===== epilogue: one query row per thread =====
-    // The accumulator holds acc = ||b'||^2 - 2 a'.b' (the norm rides along as three extra dimensions).  Per row:
-    //   * t5[]: the KCAP smallest acc seen so far; a column can be among the exact nearest only if
-    //     acc <= t5[KCAP-1] + 2 * slack  (both sides approximate), so only those columns are appended to the row's list;
+    // The accumulator holds acc = (1 - e) ||b'||^2 - 2 a'.b' (the scaled norm rides along as three extra dimensions), a
+    // lower bound of (exact distance - (1 - e) ||a'||^2); acc + 2 e (||a'||^2 + ||b'||^2) is an upper bound.  Per row:
+    //   * t5[]: the KCAP smallest UPPER bounds seen so far; a column can be among the exact nearest only if its lower
+    //     bound acc <= t5[KCAP-1], so only those columns are appended to the row's list (the error term is per column:
+    //     a far column with a large norm does not loosen the bound for the near ones);
     //   * the list is compacted against the (shrinking) bound when it runs low on room; if that does not help — ties:
-    //     duplicated descriptors — the listed columns are evaluated EXACTLY there and then ("early flush"), after which
-    //     the exact k-th distance tightens the bound to one slack;
+    //     clustered or duplicated descriptors — the row goes to the exact scan (D = 33) or the listed columns are
+    //     evaluated EXACTLY there and then ("early flush"), after which the exact k-th distance bounds acc directly;
     //   * after the last tile the survivors are evaluated exactly, in ascending column order with strict <, which is
     //     the brute-force scan's (distance, index) order bit for bit.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
@@ -288,7 +293,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
     const int row = m0 + lrow;
     const bool live = row < job.na;
     const float na = live ? job.normA[row] : 0.f;
-    const float slack = TC_ERR * (na + job.bmax) + 1e-6f;
+    const float na_low = (1.0f - TC_ERR_STORE) * na;  // acc + na_low <= exact distance
     const float INF = __int_as_float(0x7f800000);
     float t5[KCAP], bd[KCAP];
     int bi[KCAP];
@@ -368,15 +373,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
           lv[n * TM] = v;
           lj[n * TM] = jbase + c;
           ++n;
-          if (v < t5[KCAP - 1]) {
-            float cv = v;
+          // upper bound of this column in acc space
+          const float up = v + (2.0f * TC_ERR_STORE) * (na + __ldg(&job.normB[jbase + c])) + 1e-6f;
+          if (up < t5[KCAP - 1]) {
+            float cv = up;
 #pragma unroll
             for (int t = 0; t < KCAP; ++t) {
               const float lo_ = fminf(t5[t], cv);
               cv = fmaxf(t5[t], cv);
               t5[t] = lo_;
             }
-            thr = fminf(t5[KCAP - 1] + 2.0f * slack, thr_exact);
+            thr = fminf(t5[KCAP - 1], thr_exact);
           }
         }
       }
@@ -422,7 +429,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
             }
           }
           n = 0;
-          thr_exact = (bd[KCAP - 1] + slack) - na;
+          thr_exact = (bd[KCAP - 1] - na_low) + 1e-6f * (1.0f + fabsf(bd[KCAP - 1]) + na);  // acc <= exact k-th - na_low (+ rounding pad)
           thr = fminf(thr, thr_exact);
         }
       }
@@ -596,7 +603,7 @@ __global__ void __launch_bounds__(128) knn_tc_prep_kernel(const PrepJob* __restr
     s_norm = s;
   }
   __syncthreads();
-  const float nrm = s_norm;
+  const float nrm = (1.0f - TC_ERR_STORE) * s_norm;  // the B form carries the lower-bound norm (see knn_tc_kernel)
   const float nh = tf32_hi(nrm), r1 = nrm - nh, nm = tf32_hi(r1), nl = r1 - nm;
   for (int t = threadIdx.x; t < Kp; t += blockDim.x) {
     const int kb = t >> 5, w = t & 31, is_lo = w >> 4, dim = kb * 16 + (w & 15);
@@ -616,26 +623,6 @@ __global__ void __launch_bounds__(128) knn_tc_prep_kernel(const PrepJob* __restr
   }
   if (j.pad)
     for (int t = threadIdx.x; t < padw; t += blockDim.x) j.pad[(size_t)row * padw + t] = t < D ? a[t] : 0.f;
-}
-
-struct MaxJob {
-  const float* v;
-  int n;
-  float* out;
-};
-__global__ void __launch_bounds__(256) max_kernel(const MaxJob* __restrict__ jobs)
-{
-  const MaxJob& j = jobs[blockIdx.x];
-  float m = 0.f;
-  for (int i = threadIdx.x; i < j.n; i += blockDim.x) m = fmaxf(m, j.v[i]);
-  __shared__ float sh[256];
-  sh[threadIdx.x] = m;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) sh[threadIdx.x] = fmaxf(sh[threadIdx.x], sh[threadIdx.x + o]);
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *j.out = sh[0];
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -682,9 +669,7 @@ void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vect
   std::vector<char> used(M, 0);
   for (const KnnProblem& p : probs) { used[p.a] = 1; used[p.b] = 1; }
   std::vector<DBuf<float>> formA(M), formB(M), norm(M), pad(M);
-  DBuf<float> bmax(c, M);
   std::vector<PrepJob> pj;
-  std::vector<MaxJob> mj;
   int mxn = 0;
   for (int m = 0; m < M; ++m) {
     if (!used[m] || n_rows[m] == 0) continue;
@@ -693,7 +678,6 @@ void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vect
     norm[m].alloc(c, n_rows[m]);
     if (reg_path) pad[m].alloc(c, (size_t)n_rows[m] * padw);
     pj.push_back(PrepJob{desc[m], formA[m].p, formB[m].p, norm[m].p, reg_path ? pad[m].p : nullptr, n_rows[m]});
-    mj.push_back(MaxJob{norm[m].p, n_rows[m], bmax.p + m});
     mxn = std::max(mxn, n_rows[m]);
   }
   if (pj.empty()) return;
@@ -705,10 +689,6 @@ void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vect
   MM_LAUNCH(c, knn_tc_mean_partial_kernel, dim3(MEAN_CHUNKS, (unsigned)pj.size()), 128, 0, dpj.p, D, partial.p);
   MM_LAUNCH(c, knn_tc_mean_kernel, (D + 127) / 128, 128, 0, partial.p, (int)pj.size() * MEAN_CHUNKS, D, 1.0 / (double)rows_all, mean.p);
   MM_LAUNCH(c, knn_tc_prep_kernel, dim3(mxn, (unsigned)pj.size()), 128, 0, dpj.p, mean.p, D, Kp, padw);
-  DBuf<MaxJob> dmj = to_device(c, mj);
-  MM_LAUNCH(c, max_kernel, (unsigned)mj.size(), 256, 0, dmj.p);
-  std::vector<float> hbmax(M, 0.f);
-  bmax.download(c, hbmax.data(), M);
   std::vector<CUtensorMap> hA(M), hB(M);
   for (int m = 0; m < M; ++m) {
     if (!used[m] || n_rows[m] == 0) {
@@ -720,7 +700,6 @@ void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vect
     hB[m] = make_map(formB[m].p, n_rows[m], Kp);
   }
   DBuf<CUtensorMap> dA = to_device(c, hA), dB = to_device(c, hB);
-  c.sync();  // bmax on the host
   std::vector<TcJob> tj;
   int max_na = 0, kmax = 0;
   double bytes = 0;
@@ -746,7 +725,7 @@ void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vect
     j.origB = desc[p.b];
     j.padA = reg_path ? (const float4*)pad[p.a].p : nullptr;
     j.padB = reg_path ? (const float4*)pad[p.b].p : nullptr;
-    j.bmax = hbmax[p.b];
+    j.normB = norm[p.b].p;
     j.k = p.k;
     j.idx = p.idx;
     j.dist = p.dist;
