@@ -385,6 +385,9 @@ void mm3d_destroy(mm3d_ctx* ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->c.device);
   cudaStreamSynchronize(ctx->c.stream);
+  if (ctx->c.knn_stats) cudaFree(ctx->c.knn_stats);
+  for (cudaEvent_t e : ctx->c.event_pool) cudaEventDestroy(e);
+  for (KernelSample& s : ctx->c.samples) { cudaEventDestroy(s.e0); cudaEventDestroy(s.e1); }
   if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.stream);
   delete ctx;
 }

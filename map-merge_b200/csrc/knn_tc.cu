@@ -745,11 +745,8 @@ void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vect
 #define MM_TC(KCAP, DREG, RES)                                                                                                   \
   do {                                                                                                                           \
     const size_t smem = RES ? TC_SMEM_RES : TC_SMEM_STREAM;                                                                      \
-    static bool attr_set = false;                                                                                                \
-    if (!attr_set) {                                                                                                             \
-      MM_CUDA(cudaFuncSetAttribute(knn_tc_kernel<KCAP, DREG, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-      attr_set = true;                                                                                                           \
-    }                                                                                                                            \
+    /* per device and cheap: set on every call (a process may drive several GPUs) */                                            \
+    MM_CUDA(cudaFuncSetAttribute(knn_tc_kernel<KCAP, DREG, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
     MM_LAUNCH(c, (knn_tc_kernel<KCAP, DREG, RES>), grid, TC_THREADS, smem, dtj.p, dA.p, dB.p, kblocks, D, c.knn_stats);          \
   } while (0)
   const bool res = kblocks <= A_RES_MAX_KB;

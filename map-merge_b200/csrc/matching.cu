@@ -717,11 +717,8 @@ void ransac_batch(Ctx& c, const std::vector<CloudView>& keypoints, const std::ve
   for (int p = 0; p < P; ++p) max_c = std::max(max_c, corr[p].n);
   const int stage_cap = std::min(std::max(max_c, 1), (200 * 1024 - 624 * 4) / 16);
   const size_t rs_smem = 624 * 4 + (size_t)stage_cap * 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MM_CUDA(cudaFuncSetAttribute(ransac_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  // per device and cheap: set on every call (a process may drive several GPUs)
+  MM_CUDA(cudaFuncSetAttribute(ransac_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   MM_LAUNCH(c, ransac_sample_kernel, P, 128, rs_smem, drj.p, stage_cap);
   MM_LAUNCH(c, ransac_score_kernel, dim3((MAX_HYP + 3) / 4, P), 128, 0, drj.p, thresh);
   MM_LAUNCH(c, ransac_select_kernel, P, 32, 0, drj.p, thresh);
