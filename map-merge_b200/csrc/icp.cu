@@ -39,6 +39,7 @@ struct IcpJob {
   int* ticket;       // blocks of this pair that finished the current iteration
   float t0[16];      // initial guess, row-major
   long long* sums_log;  // optional max_log x NSUM
+  int* nn_slot;      // per source point: the target slot matched in the previous iteration (-1 = none)
 };
 
 __global__ void __launch_bounds__(256) icp_init_kernel(const IcpJob* __restrict__ jobs)
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(256) icp_init_kernel(const IcpJob* __restrict_
     em::transform_point(j.t0, p.x, p.y, p.z, &o.x, &o.y, &o.z);  // pcl::transformPointCloud(source, initial_guess)
     o.w = p.w;
     j.work[i] = o;
+    j.nn_slot[i] = -1;
   }
 }
 
@@ -168,7 +170,10 @@ __global__ void __launch_bounds__(IB) icp_iteration_kernel(const IcpJob* __restr
     int idx;
     float d2;
     float4 q;
-    if (nearest_bounded(j.tgt, p.x, p.y, p.z, max_dist_sqr, rv, &idx, &d2, &q)) {
+    int slot;
+    const bool hit = nearest_bounded(j.tgt, p.x, p.y, p.z, max_dist_sqr, rv, &idx, &d2, &q, j.nn_slot[i], &slot);
+    j.nn_slot[i] = slot;  // the transform moves little between iterations: last iteration's match seeds the next search
+    if (hit) {
       const double pp[3] = {(double)p.x, (double)p.y, (double)p.z};
       const double qq[3] = {(double)q.x, (double)q.y, (double)q.z};
       v[0] = 1;
@@ -206,6 +211,7 @@ struct ScoreJob {
   int ns;
   float t[16];
   long long* sums;  // Sd, nr
+  const int* nn_guess;  // optional: the slots matched in the last ICP iteration
 };
 
 __global__ void __launch_bounds__(IB) score_kernel(const ScoreJob* __restrict__ jobs, double max_range, int rv)
@@ -222,7 +228,7 @@ __global__ void __launch_bounds__(IB) score_kernel(const ScoreJob* __restrict__ 
     float d2;
     float4 q;
     // the reference compares the squared distance with the plain range
-    if (nearest_bounded(j.tgt, x, y, z, max_range, rv, &idx, &d2, &q)) {
+    if (nearest_bounded(j.tgt, x, y, z, max_range, rv, &idx, &d2, &q, j.nn_guess ? j.nn_guess[i] : -1)) {
       v[0] = em::to_fix((double)d2, MM3D_FIXD_SCALE);
       v[1] = 1;
     }
@@ -234,10 +240,11 @@ __global__ void __launch_bounds__(IB) score_kernel(const ScoreJob* __restrict__ 
 
 void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<PairJob>& jobs,
                const std::vector<const float*>& T0, double max_dist, int max_it, double eps, std::vector<IcpOut>& out,
-               std::vector<std::vector<long long>>* sums_dbg)
+               std::vector<std::vector<long long>>* sums_dbg, IcpNeighbours* nn_keep)
 {
   const int P = (int)jobs.size();
   out.assign(P, IcpOut());
+  if (nn_keep) nn_keep->offset.assign(P, -1);
   if (sums_dbg) { sums_dbg->clear(); sums_dbg->resize(P); }
   if (P == 0) return;
   const int max_log = sums_dbg ? 64 : 0;
@@ -264,6 +271,9 @@ void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<D
     mx = std::max(mx, clouds[jobs[act[a]].a].n);
   }
   DBuf<float4> work(c, tot + 1);
+  DBuf<int> nn_local;
+  DBuf<int>& nn = nn_keep ? nn_keep->slots : nn_local;
+  nn.alloc(c, tot + 1);
   DBuf<long long> sums(c, (size_t)A * NSUM);
   sums.zero(c);
   DBuf<int> tickets(c, A);
@@ -289,6 +299,8 @@ void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<D
     ij[a].src = clouds[pj.a].pts;
     ij[a].ns = clouds[pj.a].n;
     ij[a].work = work.p + off;
+    ij[a].nn_slot = nn.p + off;
+    if (nn_keep) nn_keep->offset[act[a]] = (long long)off;
     ij[a].sums = sums.p + (size_t)a * NSUM;
     ij[a].st = dst.p + a;
     ij[a].ticket = tickets.p + a;
@@ -344,7 +356,7 @@ void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<D
 }
 
 void score_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<PairJob>& jobs,
-                 const std::vector<const float*>& T, double max_range, std::vector<double>& scores)
+                 const std::vector<const float*>& T, double max_range, std::vector<double>& scores, const IcpNeighbours* nn_guess)
 {
   const int P = (int)jobs.size();
   scores.assign(P, 1.7976931348623157e308);
@@ -359,6 +371,7 @@ void score_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector
     sj[p].ns = clouds[jobs[p].a].n;
     for (int k = 0; k < 16; ++k) sj[p].t[k] = T[p][k];
     sj[p].sums = sums.p + (size_t)p * 2;
+    sj[p].nn_guess = (nn_guess && p < (int)nn_guess->offset.size() && nn_guess->offset[p] >= 0) ? nn_guess->slots.p + nn_guess->offset[p] : nullptr;
     mx = std::max(mx, sj[p].ns);
   }
   if (mx == 0) return;

@@ -414,8 +414,10 @@ __device__ __forceinline__ void warp_radius_unordered(const GridView& g, float q
 // Nearest neighbour among points with (double)d2 <= bound; ties -> lower
 // original index.  Rows are visited outward from the query row so the running
 // best prunes the rest.  rv = ceil(sqrt(bound) / leaf) + 1 voxels.
+// guess_slot >= 0: a slot (position in g.pts) expected to be close, e.g. the answer for a slightly different query; it
+// only seeds the running best (the search still visits everything that could beat or tie it), so the result is the same.
 __device__ __forceinline__ bool nearest_bounded(const GridView& g, float qx, float qy, float qz, double bound, int rv, int* out_idx,
-                                                float* out_d2, float4* out_pt)
+                                                float* out_d2, float4* out_pt, int guess_slot = -1, int* out_slot = nullptr)
 {
   const int vx = floor_to_int(qx * g.inv_leaf) - g.min_b[0];
   const int vy = floor_to_int(qy * g.inv_leaf) - g.min_b[1];
@@ -427,26 +429,57 @@ __device__ __forceinline__ bool nearest_bounded(const GridView& g, float qx, flo
   const int cyq = min(max(vy, 0), g.div_v[1] - 1) >> g.shift[1];
   bool found = false;
   float best = 0.0f;
-  int best_idx = 0x7fffffff;
+  int best_idx = 0x7fffffff, best_slot = -1;
   float4 best_pt = make_float4(0.f, 0.f, 0.f, 0.f);
   // pruning threshold in voxel units; starts at the bound
   float lim_v = (float)bound * g.inv_leaf * g.inv_leaf * 1.0001f + 1e-3f;
+  if (guess_slot >= 0 && guess_slot < g.n) {
+    const float4 p = g.pts[guess_slot];
+    const float d2 = em::dist2_3(qx, qy, qz, p.x, p.y, p.z);
+    if ((double)d2 <= bound) {
+      found = true;
+      best = d2;
+      best_idx = g.orig ? g.orig[guess_slot] : guess_slot;
+      best_slot = guess_slot;
+      best_pt = p;
+      lim_v = d2 * g.inv_leaf * g.inv_leaf * 1.0001f + 1e-3f;
+    }
+  }
   const int nz = zhi - zlo + 1, ny = yhi - ylo + 1;
+  // Rows are visited in zig-zag order (0, +1, -1, +2, ...).  In one direction the row distance never decreases and the
+  // pruning threshold only shrinks, so a direction that is out of range or pruned once stays so: it is closed, and the
+  // loop ends when both directions are closed.
+  bool zc0 = false, zc1 = false;  // direction closed: 0 = towards lower rows (and the query row), 1 = towards higher rows
   for (int iz = 0; iz < 2 * nz + 1; ++iz) {
-    const int cz = czq + ((iz & 1) ? (iz + 1) / 2 : -(iz / 2));
-    if (cz < zlo || cz > zhi) continue;
+    const bool zdir = iz & 1;
+    if (zdir ? zc1 : zc0) {
+      if (zc0 && zc1) break;
+      continue;
+    }
+    const int cz = czq + (zdir ? (iz + 1) / 2 : -(iz / 2));
     const int z0 = cz << g.shift[2], z1 = z0 + (1 << g.shift[2]) - 1;
     const int dz = max(max(z0 - vz, vz - z1), 0);
     const float fz = (float)max(dz - 1, 0);
-    if (fz * fz > lim_v) continue;
+    if (cz < zlo || cz > zhi || fz * fz > lim_v) {
+      if (zdir) zc1 = true; else zc0 = true;
+      continue;
+    }
+    bool yc0 = false, yc1 = false;
     for (int iy = 0; iy < 2 * ny + 1; ++iy) {
-      const int cy = cyq + ((iy & 1) ? (iy + 1) / 2 : -(iy / 2));
-      if (cy < ylo || cy > yhi) continue;
+      const bool ydir = iy & 1;
+      if (ydir ? yc1 : yc0) {
+        if (yc0 && yc1) break;
+        continue;
+      }
+      const int cy = cyq + (ydir ? (iy + 1) / 2 : -(iy / 2));
       const int y0 = cy << g.shift[1], y1 = y0 + (1 << g.shift[1]) - 1;
       const int dy = max(max(y0 - vy, vy - y1), 0);
       const float fy = (float)max(dy - 1, 0);
       const float rem = lim_v - fz * fz - fy * fy;
-      if (rem < 0.0f) continue;
+      if (cy < ylo || cy > yhi || rem < 0.0f) {
+        if (ydir) yc1 = true; else yc0 = true;
+        continue;
+      }
       const int rx = (int)sqrtf(rem) + 2;
       int xlo = vx - rx, xhi = vx + rx;
       if (xhi < 0 || xlo >= g.div_v[0]) continue;
@@ -463,6 +496,7 @@ __device__ __forceinline__ bool nearest_bounded(const GridView& g, float qx, flo
           found = true;
           best = d2;
           best_idx = oi;
+          best_slot = k;
           best_pt = p;
           lim_v = d2 * g.inv_leaf * g.inv_leaf * 1.0001f + 1e-3f;
         }
@@ -472,6 +506,7 @@ __device__ __forceinline__ bool nearest_bounded(const GridView& g, float qx, flo
   *out_idx = best_idx;
   *out_d2 = best;
   *out_pt = best_pt;
+  if (out_slot) *out_slot = found ? best_slot : -1;
   return found;
 }
 
@@ -579,11 +614,17 @@ struct IcpOut {
   int iterations;
   int converged;
 };
+// the target slot each source point matched in its pair's last ICP iteration (-1: none): a warm start for the score's search
+struct IcpNeighbours {
+  DBuf<int> slots;
+  std::vector<long long> offset;  // per pair job, -1 = not available
+};
 void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<PairJob>& jobs,
                const std::vector<const float*>& T0_rowmajor, double max_dist, int max_it, double eps, std::vector<IcpOut>& out,
-               std::vector<std::vector<long long>>* sums_dbg);
+               std::vector<std::vector<long long>>* sums_dbg, IcpNeighbours* nn_keep = nullptr);
 void score_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<PairJob>& jobs,
-                 const std::vector<const float*>& T_rowmajor, double max_range, std::vector<double>& scores);
+                 const std::vector<const float*>& T_rowmajor, double max_range, std::vector<double>& scores,
+                 const IcpNeighbours* nn_guess = nullptr);
 
 // compose.cu — composeMaps sharded over ranks
 struct KeyGeomHost {
