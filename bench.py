@@ -377,6 +377,19 @@ def run_gpu(args):
         roof["achieved"] = top["algorithmic_bytes"] / (top["ms_annotated"] * 1e-3) / 1e9
         roof["frac"] = roof["achieved"] / peak
         roof["algorithmic_bytes_per_launch"] = top["algorithmic_bytes"] / top["launches"]
+    # what actually bounds the kernel (ncu --set full capture of the same kernel, committed under profiles/)
+    try:
+        import csv
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_summary_v2.csv")) as fh:
+            rows = [r for r in csv.DictReader(fh) if r["kernel"] == top["kernel"]]
+        if rows:
+            r0 = max(rows, key=lambda r: float(r["gpu__time_duration.sum [ms]"]))
+            roof["ncu"] = {"issue_slots_busy_pct": float(r0["smsp__issue_active.avg.pct_of_peak_sustained_active [%]"]),
+                           "active_lanes_per_warp": float(r0["smsp__thread_inst_executed_per_inst_executed.ratio []"]),
+                           "l1_hit_pct": float(r0["l1tex__t_sector_hit_rate.pct [%]"]),
+                           "source": "profiles/r01_ncu_summary_v2.csv (issue bound, not HBM bound)"}
+    except Exception:
+        pass
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
