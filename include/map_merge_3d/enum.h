@@ -36,6 +36,7 @@ struct Names;  // specialised per enum: static const char* const* list(); static
       static const char* const n[] = {LIST(MM3D_ENUM_STR_)};                         \
       return (int)(sizeof(n) / sizeof(n[0]));                                        \
     }                                                                                \
+    static const char* type_name() { return #EnumType; }                             \
   };                                                                                 \
   inline const char* to_string(EnumType e)                                           \
   {                                                                                  \
@@ -54,7 +55,8 @@ std::enable_if_t<std::is_enum<T>::value, T> from_string(const std::string& s)
 {
   for (int i = 0; i < Names<T>::count(); ++i)
     if (s == Names<T>::list()[i]) return static_cast<T>(i);
-  throw std::runtime_error("from_string: " + s + " is invalid value for enum");
+  // same text as the reference's ENUM_CLASS (enum.h:58-60)
+  throw std::runtime_error("from_string: " + s + " is invalid value for enum " + Names<T>::type_name());
 }
 }  // namespace enums
 }  // namespace map_merge_3d

@@ -2,6 +2,7 @@
 refuses to run without a device (no CPU fallback), and answers the reference's degenerate cases without one."""
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -76,3 +77,43 @@ def test_cpp_shim_and_reference_gtest_cases():
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "5 passed" in r.stdout
+
+
+# ---------------------------------------------------------------- pinned by the reference's own headers
+GOLDEN_PARAMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "params_ref.json")
+
+
+def test_c_abi_defaults_and_enums_match_reference_headers(mm):
+    """tests/golden/params_ref.json is the output of the REFERENCE's public headers compiled unmodified (oracle/_ref/params_ref,
+    tests/golden/make_params_golden.py): MapMergingParams defaults to the last bit, enum order and names."""
+    import json
+    g = json.load(open(GOLDEN_PARAMS))
+    p = mm.default_params()
+    for k, v in g["defaults"].items():
+        assert getattr(p, k) == v, (k, getattr(p, k), v)
+    for table, names in ((mm.DESC, g["Descriptor"]["names"]), (mm.KEYPOINT, g["Keypoint"]["names"]), (mm.METHOD, g["EstimationMethod"]["names"])):
+        assert [k for k, _ in sorted(table.items(), key=lambda kv: kv[1])] == names
+        assert sorted(table.values()) == list(range(len(names)))
+
+
+def test_shim_headers_match_reference_headers(tmp_path):
+    """The same program (oracle/params_ref_shim.cpp) compiled against the shim's include/ prints what it prints against the
+    reference's include/: defaults, enum names, round trips, and the exception text of from_string."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "params_shim")
+    subprocess.check_call(["g++", "-O1", "-std=c++14", "-I" + os.path.join(root, "include"), "-o", exe, os.path.join(root, "oracle", "params_ref_shim.cpp")])
+    got = json.loads(subprocess.check_output([exe], text=True))
+    assert got == json.load(open(GOLDEN_PARAMS))
+
+
+def test_reference_headers_live_if_present():
+    """In the build container the golden file is regenerated from /root/reference and must not have drifted."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref_inc = "/root/reference/map_merge_3d/include"
+    if not os.path.isdir(ref_inc):
+        pytest.skip("reference tree absent (GPU box)")
+    subprocess.check_call(["make", "-C", os.path.join(root, "oracle"), "ref"], stdout=subprocess.DEVNULL)
+    got = json.loads(subprocess.check_output([os.path.join(root, "oracle", "_ref", "params_ref")], text=True))
+    assert got == json.load(open(GOLDEN_PARAMS))
