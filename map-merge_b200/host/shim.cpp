@@ -364,8 +364,8 @@ MapMergingParams MapMergingParams::fromCommandLine(int argc, char** argv)
   str("--estimation_method", estimation_method);
   if (!estimation_method.empty()) params.estimation_method = enums::from_string<EstimationMethod>(estimation_method);
   int refine = params.refine_transform ? 1 : 0;
-  integer("--refine_transform", refine);  // pcl::console::parse_argument(bool&) reads an integer
-  params.refine_transform = refine != 0;
+  integer("--refine_transform", refine);  // pcl::console::parse_argument(bool&): val = atoi(arg) == 1
+  params.refine_transform = refine == 1;
   dbl("--inlier_threshold", params.inlier_threshold);
   dbl("--max_correspondence_distance", params.max_correspondence_distance);
   integer("--max_iterations", params.max_iterations);

@@ -1,30 +1,47 @@
-// Stand-in for the reference's <map_merge_3d/typedefs.h> (which needs PCL) so that the REFERENCE's own public headers
-// — enum.h, features.h, matching.h, map_merging.h — compile here unmodified (see ../params_ref_shim.cpp).  Only opaque
-// handles: nothing in those headers looks inside the types.  Test infrastructure only.
+// Stand-in for the reference's <map_merge_3d/typedefs.h> (which needs PCL) so that the REFERENCE's own public headers and
+// its map_merging.cpp compile here unmodified (see ../params_ref_shim.cpp, ../mapmerging_ref_shim.cpp).  Plain containers
+// with the few members map_merging.cpp touches (size(), operator+=).  Test infrastructure only.
 #ifndef MAP_MERGE_TYPEDEFS_H_
 #define MAP_MERGE_TYPEDEFS_H_
+#include <cstddef>
+#include <cstdint>
 #include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
-namespace Eigen
-{
-struct Matrix4f {
-  float m[16];
-};
-}  // namespace Eigen
+
+#include <Eigen/Core>
+
 namespace map_merge_3d
 {
-struct PointCloud {};
+struct PointT {
+  float x, y, z;
+  uint32_t rgba;
+};
+struct PointCloud {
+  std::vector<PointT> points;
+  size_t size() const { return points.size(); }
+  PointCloud& operator+=(const PointCloud& o)
+  {
+    points.insert(points.end(), o.points.begin(), o.points.end());
+    return *this;
+  }
+};
 typedef std::shared_ptr<PointCloud> PointCloudPtr;
 typedef std::shared_ptr<const PointCloud> PointCloudConstPtr;
-struct SurfaceNormals {};
+struct SurfaceNormals {
+  std::vector<float> v;  // n x (nx, ny, nz, curvature)
+};
 typedef std::shared_ptr<SurfaceNormals> SurfaceNormalsPtr;
 typedef std::shared_ptr<const SurfaceNormals> SurfaceNormalsConstPtr;
-struct LocalDescriptors {};
+struct LocalDescriptors {
+  std::vector<float> v;  // n x dim
+  int dim = 0;
+};
 typedef std::shared_ptr<LocalDescriptors> LocalDescriptorsPtr;
 typedef std::shared_ptr<const LocalDescriptors> LocalDescriptorsConstPtr;
-struct Correspondences {};
+struct Correspondences {
+};
 typedef std::shared_ptr<Correspondences> CorrespondencesPtr;
 }  // namespace map_merge_3d
 #endif

@@ -12,9 +12,15 @@
 // Each stage below is therefore a restatement of upstream PCL 1.8.1 from its
 // published algorithm ("[PCL-recall <upstream file>]"), anchored on the
 // reference's call sites ("[REF file:line]").  What IS pinned by reference code
-// compiled here: the pose-graph step (oracle/_ref builds the reference's
-// graph.cpp unmodified; tests compare orc_graph_* against it) and the five
-// degenerate gtest cases.
+// compiled here (oracle/_ref, `make ref`; outputs committed under tests/golden/):
+//   * the pose-graph step: the reference's graph.cpp unmodified (libgraph_ref.so);
+//   * the DRIVER: the reference's map_merging.cpp + graph.cpp unmodified, running on
+//     this file's stage functions (libmapmerging_ref.so, mapmerging_ref_shim.cpp) —
+//     estimateMapsTransforms / computeGlobalTransforms / composeMaps control flow,
+//     the command-line flag table and the params printout;
+//   * MapMergingParams defaults and the enum layer: the reference's public headers
+//     unmodified (params_ref);
+//   * the five degenerate gtest cases.
 //
 // Canonical choices where PCL is implementation-defined:
 //   * voxel centroid summation order = ascending original point index

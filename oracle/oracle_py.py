@@ -309,3 +309,44 @@ class GraphRef:
         self.lib.ref_graph(n, st.ctypes.data_as(i32p), conf.ctypes.data_as(f64p), C.c_double(thr), inc.ctypes.data_as(i32p),
                            te.ctypes.data_as(i32p), C.byref(nte), cen.ctypes.data_as(i32p), C.byref(nc), C.byref(nn))
         return inc, te[:nte.value].copy(), cen[:nc.value].copy(), nn.value
+
+
+class MapMergingRef:
+    """The reference's own driver code (src/map_merging.cpp + src/graph.cpp compiled unmodified into
+    oracle/_ref/libmapmerging_ref.so by `make -C oracle ref`) running on the checker's stage functions."""
+
+    def __init__(self):
+        path = os.path.join(_HERE, "_ref", "libmapmerging_ref.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        self.lib.orc_free.argtypes = [C.c_void_p]
+
+    def estimate_maps_transforms(self, clouds, params: Params):
+        m = len(clouds)
+        arrs = [np.ascontiguousarray(c, np.float32) for c in clouds]
+        ptrs = (f32p * max(m, 1))(*[a.ctypes.data_as(f32p) for a in arrs])
+        ns = (C.c_uint64 * max(m, 1))(*[len(a) for a in arrs])
+        out = np.zeros((max(m, 1), 16), np.float32); n_out = C.c_int()
+        self.lib.ref_estimate_maps_transforms(m, ptrs, ns, C.byref(params), out.ctypes.data_as(f32p), C.byref(n_out))
+        return out[:n_out.value].reshape(-1, 4, 4).transpose(0, 2, 1).copy()
+
+    def compose_maps(self, clouds, transforms, resolution):
+        m = len(clouds)
+        arrs = [np.ascontiguousarray(c, np.float32) for c in clouds]
+        ptrs = (f32p * max(m, 1))(*[a.ctypes.data_as(f32p) for a in arrs])
+        ns = (C.c_uint64 * max(m, 1))(*[len(a) for a in arrs])
+        T = np.ascontiguousarray(np.asarray(transforms, np.float32).reshape(-1, 4, 4).transpose(0, 2, 1)) if len(transforms) else np.zeros((1, 16), np.float32)
+        out = f32p(); n = C.c_uint64()
+        rc = self.lib.ref_compose_maps(m, ptrs, ns, len(transforms), T.ctypes.data_as(f32p), C.c_double(resolution), C.byref(out), C.byref(n))
+        if rc == 1:
+            return None
+        if rc == 2:
+            raise RuntimeError("composeMaps: clouds and transforms size must be the same.")
+        r = _take(out, n.value * 4, np.float32, (-1, 4))
+        self.lib.orc_free(C.cast(out, C.c_void_p))
+        return r
+
+    def params_text(self, args):
+        """MapMergingParams::fromCommandLine + operator<< of the reference (oracle/_ref/mapmerging_params)."""
+        return subprocess.check_output([os.path.join(_HERE, "_ref", "mapmerging_params")] + list(args), text=True)

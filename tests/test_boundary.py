@@ -117,3 +117,28 @@ def test_reference_headers_live_if_present():
     subprocess.check_call(["make", "-C", os.path.join(root, "oracle"), "ref"], stdout=subprocess.DEVNULL)
     got = json.loads(subprocess.check_output([os.path.join(root, "oracle", "_ref", "params_ref")], text=True))
     assert got == json.load(open(GOLDEN_PARAMS))
+
+
+# ---------------------------------------------------------------- pinned by the reference's own driver code
+GOLDEN_DRIVER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mapmerging_ref.json")
+
+
+def test_shim_command_line_matches_reference_driver(tmp_path):
+    """MapMergingParams::fromCommandLine + operator<< of the shim print, for every command line of the golden file, what the
+    reference's own map_merging.cpp printed (oracle/_ref/mapmerging_params, tests/golden/make_mapmerging_golden.py):
+    flag table, enum parsing and its exception text, the matching_k > 0 rule, the frozen dependent defaults, the format."""
+    import json
+    g = json.load(open(GOLDEN_DRIVER))
+    lib_dir = os.path.join(ROOT, "map-merge_b200")
+    subprocess.check_call(["make", "-C", lib_dir, "libmm3d_shim.so"], stdout=subprocess.DEVNULL)
+    src = tmp_path / "cmdline.cpp"
+    src.write_text('#include <iostream>\n#include <map_merge_3d/map_merging.h>\n'
+                   'int main(int argc, char** argv) {\n'
+                   '  try { std::cout << map_merge_3d::MapMergingParams::fromCommandLine(argc, argv); }\n'
+                   '  catch (const std::exception& e) { std::cout << "EXCEPTION: " << e.what(); }\n  return 0;\n}\n')
+    exe = str(tmp_path / "cmdline")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-o", exe, str(src), "-L" + lib_dir, "-lmm3d_shim", "-lmm3d",
+                           "-Wl,-rpath," + lib_dir])
+    for c in g["command_lines"]:
+        got = subprocess.check_output([exe] + c["argv"], text=True)
+        assert got == c["text"], (c["argv"], got, c["text"])
