@@ -1,6 +1,6 @@
-// Stand-in for the reference's <map_merge_3d/typedefs.h> (which needs PCL) so that the REFERENCE's own public headers and
-// its map_merging.cpp compile here unmodified (see ../params_ref_shim.cpp, ../mapmerging_ref_shim.cpp).  Plain containers
-// with the few members map_merging.cpp touches (size(), operator+=).  Test infrastructure only.
+// Stand-in for the reference's <map_merge_3d/typedefs.h> (which needs PCL) so that the REFERENCE's own public headers, its
+// map_merging.cpp and its matching.cpp compile here unmodified (see ../params_ref_shim.cpp, ../mapmerging_ref_shim.cpp).
+// Plain containers with the few members that code touches.  Test infrastructure only.
 #ifndef MAP_MERGE_TYPEDEFS_H_
 #define MAP_MERGE_TYPEDEFS_H_
 #include <cstddef>
@@ -11,12 +11,16 @@
 #include <vector>
 
 #include <Eigen/Core>
+#include <pcl/stub_types.h>
 
 namespace map_merge_3d
 {
 struct PointT {
   float x, y, z;
   uint32_t rgba;
+};
+struct NormalT {
+  float normal_x, normal_y, normal_z, curvature;
 };
 struct PointCloud {
   std::vector<PointT> points;
@@ -34,14 +38,17 @@ struct SurfaceNormals {
 };
 typedef std::shared_ptr<SurfaceNormals> SurfaceNormalsPtr;
 typedef std::shared_ptr<const SurfaceNormals> SurfaceNormalsConstPtr;
-struct LocalDescriptors {
-  std::vector<float> v;  // n x dim
+struct PCLPointField {
+  std::string name;
+};
+struct LocalDescriptors {          // pcl::PCLPointCloud2: fields[0].name selects the descriptor type
+  std::vector<PCLPointField> fields;
+  std::vector<float> v;            // n x dim
   int dim = 0;
 };
 typedef std::shared_ptr<LocalDescriptors> LocalDescriptorsPtr;
 typedef std::shared_ptr<const LocalDescriptors> LocalDescriptorsConstPtr;
-struct Correspondences {
-};
-typedef std::shared_ptr<Correspondences> CorrespondencesPtr;
+using pcl::Correspondences;
+using pcl::CorrespondencesPtr;
 }  // namespace map_merge_3d
 #endif

@@ -1,0 +1,3 @@
+// Stand-in: see <pcl/registration/stub_registration.h>.
+#pragma once
+#include <pcl/registration/stub_registration.h>

@@ -1,12 +1,16 @@
 // The REFERENCE's own driver — src/map_merging.cpp (estimateMapsTransforms, computeGlobalTransforms, composeMaps,
-// MapMergingParams::fromCommandLine, operator<<) and src/graph.cpp — compiled unmodified where it lies under
-// /root/reference, on top of the CPU checker's stage functions.  PCL / Eigen / ROS are replaced by the stand-in headers of
-// hdr_stub/ and eigen_stub/; this file supplies what those headers only declare:
-//   * map_merge_3d::downSample ... transformScore  (features.h / matching.h)  -> the checker's restatements
+// MapMergingParams::fromCommandLine, operator<<), src/matching.cpp (findFeatureCorrespondences with its reciprocal
+// cross-match, estimateTransformFromCorrespondences, estimateTransformFromDescriptorsSets, estimateTransformICP,
+// estimateTransform, transformScore) and src/graph.cpp — compiled unmodified where it lies under /root/reference, on top of
+// the CPU checker's stage functions.  PCL / Eigen / ROS are replaced by the stand-in headers of hdr_stub/ and
+// eigen_stub/; this file supplies what those headers only declare:
+//   * map_merge_3d::downSample ... computeSurfaceNormals  (features.h)          -> the checker's restatements
+//   * the PCL registration classes matching.cpp configures (RANSAC rejector, SVD, SAC-IA, ICP, validation) -> the checker
 //   * Eigen::Matrix4f arithmetic, pcl::transformPointCloud                      -> the checker's 4x4 routines
-// So the control flow (stage order, pair generation, confidence = 1 / score, pose graph, chaining with inverses, the
-// composeMaps skip / exception rules, the command-line flag table and the params printout) is the reference's own code,
-// and only the PCL-backed arithmetic underneath is restated.  Output: oracle/_ref/libmapmerging_ref.so, and (with
+// So the control flow (stage order, pair generation, the k-NN cross-match, which parameter configures which PCL object, the
+// "identity means RANSAC failed" rule, final * initial_guess, confidence = 1 / score, pose graph, chaining with inverses,
+// the composeMaps skip / exception rules, the command-line flag table and the params printout) is the reference's own
+// code, and only the PCL-internal arithmetic underneath is restated.  Output: oracle/_ref/libmapmerging_ref.so, and (with
 // -DMAPMERGING_REF_MAIN) oracle/_ref/mapmerging_params, which prints the parsed command line.
 // Test infrastructure only.
 #include "mm3d_oracle.cpp"  // the checker, as one translation unit (its functions are internal)
@@ -41,6 +45,8 @@ bool Matrix4f::isZero(float prec) const
     if (!(std::fabs(m[i]) <= prec)) return false;
   return true;
 }
+bool Matrix4f::isIdentity(float) const { return orc::is_identity(to_orc(*this)); }
+void Matrix4f::setZero() { *this = Zero(); }
 }  // namespace Eigen
 
 static orc::Cloud to_orc_cloud(const map_merge_3d::PointCloud& c)
@@ -72,7 +78,60 @@ void transformPointCloud(const map_merge_3d::PointCloud& in, map_merge_3d::Point
 }
 }  // namespace pcl
 
-// ---- features.h / matching.h on the checker -----------------------------------------------------------------------------------
+// ---- the PCL registration classes matching.cpp drives -----------------------------------------------------------------------
+#include <pcl/registration/stub_registration.h>
+namespace pcl
+{
+namespace stub
+{
+static std::vector<orc::Corr> to_orc_corr(const Correspondences& c)
+{
+  std::vector<orc::Corr> o(c.size());
+  for (size_t i = 0; i < c.size(); ++i) o[i] = orc::Corr{c[i].index_query, c[i].index_match, c[i].distance};
+  return o;
+}
+void RansacRejector::getCorrespondences(Correspondences& remaining)
+{
+  const std::vector<orc::Corr> oc = to_orc_corr(*corr);
+  std::vector<int> inl;
+  orc::Mat4 b;
+  if (orc::ransac_reject(to_orc_cloud(*src), to_orc_cloud(*tgt), oc, thr, inl, b)) {
+    remaining.clear();
+    for (int i : inl) remaining.push_back((*corr)[i]);
+    best = Eigen::from_orc(b);
+  } else {  // PCL keeps the original correspondences and an identity transformation
+    remaining = *corr;
+    best = Eigen::Matrix4f::Identity();
+  }
+}
+void SvdEstimator::estimateRigidTransformation(const map_merge_3d::PointCloud& src, const map_merge_3d::PointCloud& tgt, const Correspondences& corr,
+                                               Eigen::Matrix4f& out) const
+{
+  const std::vector<orc::Corr> oc = to_orc_corr(corr);
+  std::vector<int> all(oc.size());
+  for (size_t i = 0; i < all.size(); ++i) all[i] = (int)i;
+  out = Eigen::from_orc(orc::svd_transform(to_orc_cloud(src), to_orc_cloud(tgt), oc, all));
+}
+void Icp::align(map_merge_3d::PointCloud&)
+{
+  // the source arrives already transformed by the initial guess (matching.cpp:208-210)
+  final_t = Eigen::from_orc(orc::icp_refine(to_orc_cloud(*src), to_orc_cloud(*tgt), orc::Mat4::identity(), max_corr, max_it, eps));
+}
+double Validator::validateTransformation(const map_merge_3d::PointCloudPtr& src, const map_merge_3d::PointCloudPtr& tgt, const Eigen::Matrix4f& t) const
+{
+  return orc::transform_score(to_orc_cloud(*src), to_orc_cloud(*tgt), Eigen::to_orc(t), max_range);
+}
+Eigen::Matrix4f sac_ia_run(const map_merge_3d::PointCloud& skp, const float* sdesc, const map_merge_3d::PointCloud& tkp, const float* tdesc, int dim,
+                           double min_sample_distance, double max_corr, int max_it)
+{
+  const std::vector<float> s(sdesc, sdesc + skp.points.size() * (size_t)dim), t(tdesc, tdesc + tkp.points.size() * (size_t)dim);
+  return Eigen::from_orc(orc::sac_ia_transform(to_orc_cloud(skp), s, to_orc_cloud(tkp), t, dim, min_sample_distance, max_corr, max_it,
+                                               orc::g_pipeline_rand));
+}
+}  // namespace stub
+}  // namespace pcl
+
+// ---- features.h on the checker (matching.h comes from the reference's matching.cpp) ----------------------------------------------
 namespace map_merge_3d
 {
 PointCloudPtr downSample(const PointCloudConstPtr& input, double resolution)
@@ -111,42 +170,18 @@ LocalDescriptorsPtr computeLocalDescriptors(const PointCloudConstPtr& points, co
   const orc::Normals n = to_orc_normals(*normals);
   orc::Cloud kp = to_orc_cloud(*keypoints);
   LocalDescriptorsPtr d(new LocalDescriptors);
+  const char* field = "";  // the PointCloud2 field name dispatch_descriptors.h:38-48 gives each descriptor type
   switch (descriptor) {
-    case Descriptor::PFH: d->v = orc::pfh_descriptors(c, n, kp, feature_radius); d->dim = 125; break;
-    case Descriptor::PFHRGB: d->v = orc::pfhrgb_descriptors(c, n, kp, feature_radius); d->dim = 250; break;
-    case Descriptor::FPFH: d->v = orc::fpfh_descriptors(c, n, kp, feature_radius); d->dim = 33; break;
-    case Descriptor::RSD: d->v = orc::rsd_descriptors(c, n, kp, feature_radius); d->dim = 2; break;
-    case Descriptor::SHOT: d->v = orc::shot_descriptors(c, n, kp, feature_radius); d->dim = 1344; break;
-    case Descriptor::SC3D: d->v = orc::sc3d_descriptors(c, n, kp, feature_radius); d->dim = 1980; break;
+    case Descriptor::PFH: d->v = orc::pfh_descriptors(c, n, kp, feature_radius); d->dim = 125; field = "pfh"; break;
+    case Descriptor::PFHRGB: d->v = orc::pfhrgb_descriptors(c, n, kp, feature_radius); d->dim = 250; field = "pfhrgb"; break;
+    case Descriptor::FPFH: d->v = orc::fpfh_descriptors(c, n, kp, feature_radius); d->dim = 33; field = "fpfh"; break;
+    case Descriptor::RSD: d->v = orc::rsd_descriptors(c, n, kp, feature_radius); d->dim = 2; field = "r_min"; break;
+    case Descriptor::SHOT: d->v = orc::shot_descriptors(c, n, kp, feature_radius); d->dim = 1344; field = "shot"; break;
+    case Descriptor::SC3D: d->v = orc::sc3d_descriptors(c, n, kp, feature_radius); d->dim = 1980; field = "shape_context"; break;
   }
+  d->fields.push_back(PCLPointField{field});
   keypoints->points = from_orc_cloud(kp)->points;  // the reference filters the keypoints in place (features.cpp:137-141)
   return d;
-}
-Eigen::Matrix4f estimateTransform(const PointCloudPtr& source_points, const PointCloudPtr& source_keypoints,
-                                  const LocalDescriptorsPtr& source_descriptors, const PointCloudPtr& target_points,
-                                  const PointCloudPtr& target_keypoints, const LocalDescriptorsPtr& target_descriptors, EstimationMethod method,
-                                  bool refine, double inlier_threshold, double max_correspondence_distance, int max_iterations, size_t matching_k,
-                                  double transform_epsilon)
-{
-  // the glue of matching.cpp:223-257 (a PCL translation unit), restated
-  const orc::Cloud skp = to_orc_cloud(*source_keypoints), tkp = to_orc_cloud(*target_keypoints);
-  orc::Mat4 t;
-  if (method == EstimationMethod::SAC_IA) {
-    t = orc::sac_ia_transform(skp, source_descriptors->v, tkp, target_descriptors->v, source_descriptors->dim, inlier_threshold,
-                              max_correspondence_distance, max_iterations, orc::g_pipeline_rand);
-  } else {
-    const std::vector<orc::Corr> corr = orc::find_correspondences(source_descriptors->v.data(), skp.size(), target_descriptors->v.data(), tkp.size(),
-                                                                  source_descriptors->dim, matching_k);
-    std::vector<int> inl;
-    t = orc::ransac_transform(skp, tkp, corr, inlier_threshold, inl);
-  }
-  if (refine)
-    t = orc::icp_refine(to_orc_cloud(*source_points), to_orc_cloud(*target_points), t, max_correspondence_distance, max_iterations, transform_epsilon);
-  return Eigen::from_orc(t);
-}
-double transformScore(const PointCloudPtr& source_points, const PointCloudPtr& target_points, const Eigen::Matrix4f& transform, double max_distance)
-{
-  return orc::transform_score(to_orc_cloud(*source_points), to_orc_cloud(*target_points), Eigen::to_orc(transform), max_distance);
 }
 }  // namespace map_merge_3d
 
@@ -210,6 +245,30 @@ extern "C" int ref_compose_maps(int n_maps, const float* const* clouds, const ui
   } catch (...) {
     return 2;
   }
+}
+
+// findFeatureCorrespondences (matching.cpp:31-108, the reference's reciprocal k-NN cross-match) on plain descriptor arrays;
+// dim selects the descriptor type the way the PointCloud2 field name does.  pairs / dist are malloc'ed (n_corr x 2, n_corr).
+extern "C" int ref_find_correspondences(const float* ds, uint64_t ns, const float* dt, uint64_t nt, int dim, uint64_t k, int32_t** pairs,
+                                        float** dist, uint64_t* n_corr)
+{
+  const char* field = dim == 125 ? "pfh" : dim == 250 ? "pfhrgb" : dim == 33 ? "fpfh" : dim == 2 ? "r_min" : dim == 1344 ? "shot" : "shape_context";
+  map_merge_3d::LocalDescriptorsPtr s(new map_merge_3d::LocalDescriptors), t(new map_merge_3d::LocalDescriptors);
+  s->fields.push_back(map_merge_3d::PCLPointField{field});
+  t->fields.push_back(map_merge_3d::PCLPointField{field});
+  s->dim = t->dim = dim;
+  s->v.assign(ds, ds + ns * (size_t)dim);
+  t->v.assign(dt, dt + nt * (size_t)dim);
+  const map_merge_3d::CorrespondencesPtr c = map_merge_3d::findFeatureCorrespondences(s, t, (size_t)k);
+  *n_corr = c->size();
+  *pairs = (int32_t*)malloc(std::max<size_t>(c->size(), 1) * 8);
+  *dist = (float*)malloc(std::max<size_t>(c->size(), 1) * 4);
+  for (size_t i = 0; i < c->size(); ++i) {
+    (*pairs)[2 * i] = (*c)[i].index_query;
+    (*pairs)[2 * i + 1] = (*c)[i].index_match;
+    (*dist)[i] = (*c)[i].distance;
+  }
+  return 0;
 }
 
 #ifdef MAPMERGING_REF_MAIN

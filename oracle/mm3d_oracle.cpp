@@ -14,10 +14,12 @@
 // reference's call sites ("[REF file:line]").  What IS pinned by reference code
 // compiled here (oracle/_ref, `make ref`; outputs committed under tests/golden/):
 //   * the pose-graph step: the reference's graph.cpp unmodified (libgraph_ref.so);
-//   * the DRIVER: the reference's map_merging.cpp + graph.cpp unmodified, running on
-//     this file's stage functions (libmapmerging_ref.so, mapmerging_ref_shim.cpp) —
-//     estimateMapsTransforms / computeGlobalTransforms / composeMaps control flow,
-//     the command-line flag table and the params printout;
+//   * the DRIVER and the pair-level glue: the reference's map_merging.cpp, matching.cpp
+//     and graph.cpp unmodified, running on this file's stage functions
+//     (libmapmerging_ref.so, mapmerging_ref_shim.cpp) — estimateMapsTransforms /
+//     computeGlobalTransforms / composeMaps control flow, findFeatureCorrespondences
+//     (the reciprocal k-NN cross-match), how matching.cpp configures RANSAC / SAC-IA /
+//     ICP / validation, the command-line flag table and the params printout;
 //   * MapMergingParams defaults and the enum layer: the reference's public headers
 //     unmodified (params_ref);
 //   * the five degenerate gtest cases.
@@ -1720,13 +1722,17 @@ static bool is_identity(const Mat4& t)
   return true;
 }
 
-static Mat4 ransac_transform(const Cloud& skp, const Cloud& tkp, const std::vector<Corr>& corr, double inlier_threshold,
-                             std::vector<int>& inliers /* positions in corr */, RansacDebug* dbg = nullptr)
+// pcl::registration::CorrespondenceRejectorSampleConsensus::getRemainingCorrespondences: true = a model was found and it has
+// at least three inliers (inliers = positions in corr, best = getBestTransformation()); false = PCL keeps the original
+// correspondences and an identity best transformation.
+static bool ransac_reject(const Cloud& skp, const Cloud& tkp, const std::vector<Corr>& corr, double inlier_threshold,
+                          std::vector<int>& inliers /* positions in corr */, Mat4& best, RansacDebug* dbg = nullptr)
 {
   inliers.clear();
+  best = Mat4::identity();
   const int nc = (int)corr.size();
   const int max_iterations = 1000;  // CorrespondenceRejectorSampleConsensus default; the reference never overrides it
-  if (nc == 0) return Mat4::zero();  // fence: the reference reads an uninitialised matrix here
+  if (nc == 0) return false;  // fence: the reference reads an uninitialised matrix here
   std::vector<int> indices(nc), indices_tgt(nc);
   for (int i = 0; i < nc; ++i) { indices[i] = corr[i].q; indices_tgt[i] = corr[i].m; }
   std::map<int, int> correspondences;  // computeOriginalIndexMapping
@@ -1815,7 +1821,7 @@ static Mat4 ransac_transform(const Cloud& skp, const Cloud& tkp, const std::vect
     if (iterations > max_iterations) break;
   }
   if (dbg) { dbg->iterations = iterations; dbg->best_count = n_best; dbg->best_model = best_coefficients; }
-  if (model.empty()) return Mat4::zero();  // computeModel false -> identity -> reference returns zero
+  if (model.empty()) return false;  // computeModel false -> identity -> reference returns zero
   // selectWithinDistance
   for (int i = 0; i < nc; ++i) {
     const P4& sp = skp[indices[i]];
@@ -1825,11 +1831,17 @@ static Mat4 ransac_transform(const Cloud& skp, const Cloud& tkp, const std::vect
     const float ex = px - tp.x, ey = py - tp.y, ez = pz - tp.z;
     if (((ex * ex + ey * ey) + ez * ez) < thresh) inliers.push_back(i);
   }
-  if (inliers.size() < 3 || is_identity(best_coefficients)) {  // matching.cpp:128-133
+  if (inliers.size() < 3) {
     inliers.clear();
-    return Mat4::zero();
+    return false;
   }
-  // TransformationEstimationSVD<PointT, PointT, float> over the inliers (matching.cpp:135-137)
+  best = best_coefficients;
+  return true;
+}
+
+// TransformationEstimationSVD<PointT, PointT, float>::estimateRigidTransformation over correspondences
+static Mat4 svd_transform(const Cloud& skp, const Cloud& tkp, const std::vector<Corr>& corr, const std::vector<int>& inliers)
+{
   std::vector<float> sv(inliers.size() * 3), tv(inliers.size() * 3);
   for (size_t i = 0; i < inliers.size(); ++i) {
     const P4& sp = skp[corr[inliers[i]].q];
@@ -1840,6 +1852,18 @@ static Mat4 ransac_transform(const Cloud& skp, const Cloud& tkp, const std::vect
   Mat4 result;
   umeyama<float>(sv, tv, inliers.size(), result.m);
   return result;
+}
+
+// estimateTransformFromCorrespondences (matching.cpp:110-140): RANSAC rejection, "identity means failure", SVD on the inliers
+static Mat4 ransac_transform(const Cloud& skp, const Cloud& tkp, const std::vector<Corr>& corr, double inlier_threshold,
+                             std::vector<int>& inliers /* positions in corr */, RansacDebug* dbg = nullptr)
+{
+  Mat4 best;
+  if (!ransac_reject(skp, tkp, corr, inlier_threshold, inliers, best, dbg) || is_identity(best)) {  // matching.cpp:128-133
+    inliers.clear();
+    return Mat4::zero();
+  }
+  return svd_transform(skp, tkp, corr, inliers);
 }
 
 // ===========================================================================

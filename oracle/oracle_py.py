@@ -347,6 +347,16 @@ class MapMergingRef:
         self.lib.orc_free(C.cast(out, C.c_void_p))
         return r
 
+    def match(self, ds, dt, k=5):
+        """findFeatureCorrespondences of the reference's matching.cpp (its reciprocal k-NN cross-match)."""
+        a = np.ascontiguousarray(ds, np.float32); b = np.ascontiguousarray(dt, np.float32)
+        pairs = C.POINTER(C.c_int32)(); dist = f32p(); n = C.c_uint64()
+        self.lib.ref_find_correspondences(a.ctypes.data_as(f32p), C.c_uint64(len(a)), b.ctypes.data_as(f32p), C.c_uint64(len(b)), int(a.shape[1]),
+                                          C.c_uint64(k), C.byref(pairs), C.byref(dist), C.byref(n))
+        p = _take(pairs, n.value * 2, np.int32, (-1, 2)); d = _take(dist, n.value, np.float32)
+        self.lib.orc_free(C.cast(pairs, C.c_void_p)); self.lib.orc_free(C.cast(dist, C.c_void_p))
+        return p, d
+
     def params_text(self, args):
         """MapMergingParams::fromCommandLine + operator<< of the reference (oracle/_ref/mapmerging_params)."""
         return subprocess.check_output([os.path.join(_HERE, "_ref", "mapmerging_params")] + list(args), text=True)

@@ -50,6 +50,16 @@ def compose_cases(maps, transforms):
     return [dict(name="all", T=T, res=0.05), dict(name="one_skipped", T=T0, res=0.05), dict(name="coarse", T=T, res=0.3)]
 
 
+def match_cases():
+    rng = np.random.default_rng(77)
+    fp = lambda n: (rng.dirichlet(np.ones(11), size=(n, 3)).reshape(n, 33) * 100).astype(np.float32)  # FPFH-like rows
+    a = fp(300)
+    b = np.concatenate([a[:120] + rng.normal(0, 0.5, (120, 33)).astype(np.float32), fp(200)])
+    dup = np.concatenate([a[:50], np.repeat(a[50:51], 20, axis=0)])  # ties: equal distances everywhere
+    r2 = rng.uniform(0.1, 0.22, (150, 2)).astype(np.float32)
+    return [("fpfh_like", a, b), ("ties", dup, np.concatenate([dup[::-1][:40], a[100:160]])), ("rsd_2d", r2, r2[::-1][:100] + np.float32(0.001))]
+
+
 def bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32).reshape(-1).tolist()
 
@@ -59,7 +69,7 @@ def main():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
     ref = oracle_py.MapMergingRef()
     maps, _ = inputs()
-    out = dict(estimate=[], compose=[], command_lines=[])
+    out = dict(estimate=[], compose=[], command_lines=[], match=[])
     first = None
     for c in ESTIMATE_CASES:
         T = ref.estimate_maps_transforms(maps, oracle_py.default_params(**c["params"]))
@@ -72,6 +82,12 @@ def main():
         r = ref.compose_maps(maps[:3], c["T"], c["res"])
         out["compose"].append(dict(name=c["name"], res=c["res"], T_bits=bits(c["T"]), n=int(len(r)), checksum=int(np.bitwise_xor.reduce(r.view(np.uint32).reshape(-1).astype(np.uint64) * np.arange(1, r.size + 1, dtype=np.uint64) % np.uint64(2**61 - 1))),
                                    head_bits=bits(r[:8])))
+    # findFeatureCorrespondences (the reference's own reciprocal k-NN cross-match) on seeded descriptor sets
+    out["match"] = []
+    for name, ds, dt in match_cases():
+        for k in (1, 5, 8):
+            p, d = ref.match(ds, dt, k)
+            out["match"].append(dict(name=name, k=k, pairs=p.reshape(-1).tolist(), dist_bits=bits(d)))
     for argv in COMMAND_LINES:
         out["command_lines"].append(dict(argv=argv, text=ref.params_text(argv)))
     with open(os.path.join(ROOT, "tests", "golden", "mapmerging_ref.json"), "w") as fh:
