@@ -1,6 +1,7 @@
-// Stand-in for the reference's <map_merge_3d/typedefs.h> (which needs PCL) so that the REFERENCE's own public headers, its
-// map_merging.cpp and its matching.cpp compile here unmodified (see ../params_ref_shim.cpp, ../mapmerging_ref_shim.cpp).
-// Plain containers with the few members that code touches.  Test infrastructure only.
+// Stand-in for the reference's <map_merge_3d/typedefs.h> (which needs PCL) so that the REFERENCE's own public headers and
+// its features.cpp, matching.cpp and map_merging.cpp compile here unmodified (see ../params_ref_shim.cpp,
+// ../mapmerging_ref_shim.cpp).  Same typedef names over the stand-in containers of <pcl/stub_types.h>.
+// Test infrastructure only.
 #ifndef MAP_MERGE_TYPEDEFS_H_
 #define MAP_MERGE_TYPEDEFS_H_
 #include <cstddef>
@@ -15,29 +16,14 @@
 
 namespace map_merge_3d
 {
-struct PointT {
-  float x, y, z;
-  uint32_t rgba;
-};
-struct NormalT {
-  float normal_x, normal_y, normal_z, curvature;
-};
-struct PointCloud {
-  std::vector<PointT> points;
-  size_t size() const { return points.size(); }
-  PointCloud& operator+=(const PointCloud& o)
-  {
-    points.insert(points.end(), o.points.begin(), o.points.end());
-    return *this;
-  }
-};
-typedef std::shared_ptr<PointCloud> PointCloudPtr;
-typedef std::shared_ptr<const PointCloud> PointCloudConstPtr;
-struct SurfaceNormals {
-  std::vector<float> v;  // n x (nx, ny, nz, curvature)
-};
-typedef std::shared_ptr<SurfaceNormals> SurfaceNormalsPtr;
-typedef std::shared_ptr<const SurfaceNormals> SurfaceNormalsConstPtr;
+typedef pcl::PointXYZRGB PointT;
+typedef pcl::PointCloud<PointT> PointCloud;
+typedef pcl::PointCloud<PointT>::Ptr PointCloudPtr;
+typedef pcl::PointCloud<PointT>::ConstPtr PointCloudConstPtr;
+typedef pcl::Normal NormalT;
+typedef pcl::PointCloud<NormalT> SurfaceNormals;
+typedef pcl::PointCloud<NormalT>::Ptr SurfaceNormalsPtr;
+typedef pcl::PointCloud<NormalT>::ConstPtr SurfaceNormalsConstPtr;
 struct PCLPointField {
   std::string name;
 };

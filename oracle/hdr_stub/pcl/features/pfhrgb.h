@@ -1,3 +1,3 @@
-// Stand-in: the estimator templates are declared in <pcl/stub_types.h>.
+// Stand-in: see <pcl/stub_features.h>.
 #pragma once
-#include <pcl/stub_types.h>
+#include <pcl/stub_features.h>

@@ -4,6 +4,7 @@
 // pcl::KdTreeFLANN).  Test infrastructure only.
 #pragma once
 #include <algorithm>
+#include <cstdint>
 #include <cstring>
 #include <memory>
 #include <utility>
@@ -26,12 +27,14 @@ template <> struct desc_dim<PrincipalRadiiRSD> { static const int value = 2; };
 template <> struct desc_dim<SHOT1344> { static const int value = 1344; };
 template <> struct desc_dim<ShapeContext1980> { static const int value = 1980; };
 
-template <typename In, typename N, typename Out> class PFHEstimation;
-template <typename In, typename N, typename Out> class PFHRGBEstimation;
-template <typename In, typename N, typename Out> class FPFHEstimation;
-template <typename In, typename N, typename Out> class RSDEstimation;
-template <typename In, typename N, typename Out> class SHOTColorEstimation;
-template <typename In, typename N, typename Out> class ShapeContext3DEstimation;
+// PointCloud2 field name of each descriptor type (what pcl::toPCLPointCloud2 writes as fields[0].name)
+template <typename T> struct desc_field;
+template <> struct desc_field<PFHSignature125> { static const char* name() { return "pfh"; } };
+template <> struct desc_field<PFHRGBSignature250> { static const char* name() { return "pfhrgb"; } };
+template <> struct desc_field<FPFHSignature33> { static const char* name() { return "fpfh"; } };
+template <> struct desc_field<PrincipalRadiiRSD> { static const char* name() { return "r_min"; } };
+template <> struct desc_field<SHOT1344> { static const char* name() { return "shot"; } };
+template <> struct desc_field<ShapeContext1980> { static const char* name() { return "shape_context"; } };
 
 template <typename T>
 struct PointCloud {
@@ -39,6 +42,31 @@ struct PointCloud {
   typedef std::shared_ptr<PointCloud<T>> Ptr;
   typedef std::shared_ptr<const PointCloud<T>> ConstPtr;
   size_t size() const { return points.size(); }
+  typename std::vector<T>::iterator begin() { return points.begin(); }
+  typename std::vector<T>::iterator end() { return points.end(); }
+  typename std::vector<T>::const_iterator begin() const { return points.begin(); }
+  typename std::vector<T>::const_iterator end() const { return points.end(); }
+  PointCloud& operator+=(const PointCloud& o)
+  {
+    points.insert(points.end(), o.points.begin(), o.points.end());
+    return *this;
+  }
+};
+typedef std::shared_ptr<std::vector<int>> IndicesPtr;
+
+// the point types of the path (layouts: x, y, z, packed colour / normal + curvature — 16 bytes like the CPU checker's)
+struct PointXYZRGB {
+  float x, y, z;
+  uint32_t rgba;
+};
+struct Normal {
+  float normal_x, normal_y, normal_z, curvature;
+};
+struct PointWithScale {
+  float x, y, z, scale;
+};
+struct PointXYZI {
+  float x, y, z, intensity;
 };
 
 struct Correspondence {

@@ -1,13 +1,17 @@
-// The REFERENCE's own driver — src/map_merging.cpp (estimateMapsTransforms, computeGlobalTransforms, composeMaps,
-// MapMergingParams::fromCommandLine, operator<<), src/matching.cpp (findFeatureCorrespondences with its reciprocal
+// The REFERENCE's own code — src/features.cpp (downSample, removeOutliers, detectKeypoints, computeLocalDescriptors with its
+// invalid-descriptor filtering, computeSurfaceNormals), src/map_merging.cpp (estimateMapsTransforms, computeGlobalTransforms,
+// composeMaps, MapMergingParams::fromCommandLine, operator<<), src/matching.cpp (findFeatureCorrespondences with its reciprocal
 // cross-match, estimateTransformFromCorrespondences, estimateTransformFromDescriptorsSets, estimateTransformICP,
 // estimateTransform, transformScore) and src/graph.cpp — compiled unmodified where it lies under /root/reference, on top of
 // the CPU checker's stage functions.  PCL / Eigen / ROS are replaced by the stand-in headers of hdr_stub/ and
 // eigen_stub/; this file supplies what those headers only declare:
-//   * map_merge_3d::downSample ... computeSurfaceNormals  (features.h)          -> the checker's restatements
+//   * the PCL filter / keypoint / feature classes features.cpp configures (VoxelGrid, RadiusOutlierRemoval,
+//     NormalEstimation, SIFTKeypoint, HarrisKeypoint3D, the six descriptor estimators)                     -> the checker
 //   * the PCL registration classes matching.cpp configures (RANSAC rejector, SVD, SAC-IA, ICP, validation) -> the checker
 //   * Eigen::Matrix4f arithmetic, pcl::transformPointCloud                      -> the checker's 4x4 routines
-// So the control flow (stage order, pair generation, the k-NN cross-match, which parameter configures which PCL object, the
+// So the control flow (stage order, how features.cpp configures every PCL object — leaf sizes, SIFT scales, Harris flags,
+// search surface vs. input cloud — the NaN filtering of descriptors and keypoints, pair generation, the k-NN cross-match,
+// which parameter configures which PCL registration object, the
 // "identity means RANSAC failed" rule, final * initial_guess, confidence = 1 / score, pose graph, chaining with inverses,
 // the composeMaps skip / exception rules, the command-line flag table and the params printout) is the reference's own
 // code, and only the PCL-internal arithmetic underneath is restated.  Output: oracle/_ref/libmapmerging_ref.so, and (with
@@ -131,59 +135,77 @@ Eigen::Matrix4f sac_ia_run(const map_merge_3d::PointCloud& skp, const float* sde
 }  // namespace stub
 }  // namespace pcl
 
-// ---- features.h on the checker (matching.h comes from the reference's matching.cpp) ----------------------------------------------
-namespace map_merge_3d
+// ---- the PCL filter / keypoint / feature classes features.cpp drives ---------------------------------------------------------
+#include <pcl/stub_features.h>
+namespace pcl
 {
-PointCloudPtr downSample(const PointCloudConstPtr& input, double resolution)
+namespace stub
 {
-  return from_orc_cloud(orc::voxel_grid(to_orc_cloud(*input), (float)resolution));
-}
-PointCloudPtr removeOutliers(const PointCloudConstPtr& input, double radius, int min_neighbours)
+static orc::Normals to_orc_normals(const Normals& n)
 {
-  return from_orc_cloud(orc::radius_outlier_removal(to_orc_cloud(*input), radius, min_neighbours, nullptr, nullptr));
-}
-static orc::Normals to_orc_normals(const SurfaceNormals& n)
-{
-  orc::Normals o(n.v.size() / 4);
-  if (!o.empty()) memcpy(o.data(), n.v.data(), n.v.size() * 4);
+  orc::Normals o(n.points.size());
+  static_assert(sizeof(pcl::Normal) == sizeof(orc::N4), "normal layouts differ");
+  if (!o.empty()) memcpy(o.data(), n.points.data(), o.size() * sizeof(orc::N4));
   return o;
 }
-SurfaceNormalsPtr computeSurfaceNormals(const PointCloudConstPtr& input, double radius)
+void voxel_grid(const Cloud& in, float lx, float ly, float lz, Cloud& out)
 {
-  const orc::Normals n = orc::surface_normals(to_orc_cloud(*input), radius);
-  SurfaceNormalsPtr p(new SurfaceNormals);
-  p->v.resize(n.size() * 4);
-  if (!n.empty()) memcpy(p->v.data(), n.data(), n.size() * sizeof(orc::N4));
-  return p;
+  if (lx != ly || lx != lz) throw std::runtime_error("stub VoxelGrid: cubic leaves only");
+  out.points = from_orc_cloud(orc::voxel_grid(to_orc_cloud(in), lx))->points;
 }
-PointCloudPtr detectKeypoints(const PointCloudConstPtr& points, const SurfaceNormalsPtr& normals, Keypoint type, double threshold, double radius,
-                              double resolution)
+void radius_outlier_removal(const Cloud& in, double radius, int min_neighbours, Cloud& out)
 {
-  const orc::Cloud c = to_orc_cloud(*points);
-  if (type == Keypoint::HARRIS) return from_orc_cloud(orc::harris_keypoints(c, to_orc_normals(*normals), (float)threshold, (float)radius));
-  return from_orc_cloud(orc::sift_keypoints(c, (float)resolution, 3, 3, (float)threshold, 0));
+  out.points = from_orc_cloud(orc::radius_outlier_removal(to_orc_cloud(in), radius, min_neighbours, nullptr, nullptr))->points;
 }
-LocalDescriptorsPtr computeLocalDescriptors(const PointCloudConstPtr& points, const SurfaceNormalsPtr& normals, const PointCloudPtr& keypoints,
-                                            Descriptor descriptor, double feature_radius)
+void normal_estimation(const Cloud& in, double radius, Normals& out)
 {
-  const orc::Cloud c = to_orc_cloud(*points);
-  const orc::Normals n = to_orc_normals(*normals);
-  orc::Cloud kp = to_orc_cloud(*keypoints);
-  LocalDescriptorsPtr d(new LocalDescriptors);
-  const char* field = "";  // the PointCloud2 field name dispatch_descriptors.h:38-48 gives each descriptor type
-  switch (descriptor) {
-    case Descriptor::PFH: d->v = orc::pfh_descriptors(c, n, kp, feature_radius); d->dim = 125; field = "pfh"; break;
-    case Descriptor::PFHRGB: d->v = orc::pfhrgb_descriptors(c, n, kp, feature_radius); d->dim = 250; field = "pfhrgb"; break;
-    case Descriptor::FPFH: d->v = orc::fpfh_descriptors(c, n, kp, feature_radius); d->dim = 33; field = "fpfh"; break;
-    case Descriptor::RSD: d->v = orc::rsd_descriptors(c, n, kp, feature_radius); d->dim = 2; field = "r_min"; break;
-    case Descriptor::SHOT: d->v = orc::shot_descriptors(c, n, kp, feature_radius); d->dim = 1344; field = "shot"; break;
-    case Descriptor::SC3D: d->v = orc::sc3d_descriptors(c, n, kp, feature_radius); d->dim = 1980; field = "shape_context"; break;
+  const orc::Normals n = orc::surface_normals(to_orc_cloud(in), radius);
+  out.points.resize(n.size());
+  if (!n.empty()) memcpy(out.points.data(), n.data(), n.size() * sizeof(orc::N4));
+}
+void sift_keypoints(const Cloud& in, float min_scale, int nr_octaves, int nr_scales_per_octave, float min_contrast, PointCloud<PointWithScale>& out)
+{
+  std::vector<float> scales;
+  const orc::Cloud k = orc::sift_keypoints(to_orc_cloud(in), min_scale, nr_octaves, nr_scales_per_octave, min_contrast, 0, nullptr, &scales);
+  out.points.resize(k.size());
+  for (size_t i = 0; i < k.size(); ++i) out.points[i] = PointWithScale{k[i].x, k[i].y, k[i].z, i < scales.size() ? scales[i] : 0.f};
+}
+void harris_keypoints(const Cloud& in, const Normals& normals, bool non_max, bool refine, float threshold, float radius, PointCloud<PointXYZI>& out)
+{
+  if (!non_max || !refine) throw std::runtime_error("stub HarrisKeypoint3D: only the configuration features.cpp uses (NMS + refine)");
+  const orc::Cloud k = orc::harris_keypoints(to_orc_cloud(in), to_orc_normals(normals), threshold, radius);
+  out.points.resize(k.size());
+  for (size_t i = 0; i < k.size(); ++i) out.points[i] = PointXYZI{k[i].x, k[i].y, k[i].z, 0.f};
+}
+void descriptors(int kind, const Cloud& surface, const Normals& normals, const Cloud& keypoints, double radius, int dim, std::vector<float>& out)
+{
+  const orc::Cloud c = to_orc_cloud(surface);
+  const orc::Normals n = to_orc_normals(normals);
+  orc::Cloud kp = to_orc_cloud(keypoints);  // the checker drops the keypoints PCL marks invalid (NaN rows) ...
+  std::vector<float> v;
+  switch (kind) {
+    case 0: v = orc::pfh_descriptors(c, n, kp, radius); break;
+    case 1: v = orc::pfhrgb_descriptors(c, n, kp, radius); break;
+    case 2: v = orc::fpfh_descriptors(c, n, kp, radius); break;
+    case 3: v = orc::rsd_descriptors(c, n, kp, radius); break;
+    case 4: v = orc::shot_descriptors(c, n, kp, radius); break;
+    default: v = orc::sc3d_descriptors(c, n, kp, radius); break;
   }
-  d->fields.push_back(PCLPointField{field});
-  keypoints->points = from_orc_cloud(kp)->points;  // the reference filters the keypoints in place (features.cpp:137-141)
-  return d;
+  // ... so they are put back as NaN rows here, and the REFERENCE's own filtering (features.cpp:119-141) removes them
+  const size_t nk = keypoints.points.size();
+  out.assign(nk * (size_t)dim, std::numeric_limits<float>::quiet_NaN());
+  size_t j = 0;
+  for (size_t i = 0; i < nk && j < kp.size(); ++i) {
+    const PointXYZRGB& p = keypoints.points[i];
+    if (memcmp(&p, &kp[j], sizeof(orc::P4)) == 0) {  // kept keypoints are a subsequence of the input
+      memcpy(&out[i * (size_t)dim], &v[j * (size_t)dim], sizeof(float) * (size_t)dim);
+      ++j;
+    }
+  }
+  if (j != kp.size()) throw std::runtime_error("stub descriptors: kept keypoints are not a subsequence of the input");
 }
-}  // namespace map_merge_3d
+}  // namespace stub
+}  // namespace pcl
 
 // ---- C entry points -----------------------------------------------------------------------------------------------------------
 static map_merge_3d::MapMergingParams to_ref_params(const Params& p)

@@ -1,6 +1,6 @@
-"""Generates tests/golden/mapmerging_ref.json by running the REFERENCE's own driver code — src/map_merging.cpp and
-src/graph.cpp compiled unmodified into oracle/_ref/libmapmerging_ref.so (`make -C oracle ref`) on top of the CPU checker's
-stage functions — on seeded inputs: estimateMapsTransforms and composeMaps results (float bits) and the text that
+"""Generates tests/golden/mapmerging_ref.json by running the REFERENCE's own code — src/features.cpp, src/matching.cpp,
+src/map_merging.cpp and src/graph.cpp compiled unmodified into oracle/_ref/libmapmerging_ref.so (`make -C oracle ref`), with
+the PCL classes they drive replaced by stand-ins over the CPU checker's stage functions — on seeded inputs: estimateMapsTransforms and composeMaps results (float bits) and the text that
 MapMergingParams::fromCommandLine + operator<< print for a set of command lines.  Run in the build container only:
 /root/reference does not exist on the GPU box, which is why the outputs are committed."""
 import importlib
@@ -22,6 +22,10 @@ ESTIMATE_CASES = [
     dict(name="sac_ia_no_refine", params=dict(estimation_method=1, refine_transform=0, max_iterations=60)),
     dict(name="threshold_disconnects", params=dict(confidence_threshold=1e9)),
     dict(name="rsd", params=dict(descriptor_type=3)),
+    dict(name="pfh_default_descriptor", params=dict(descriptor_type=0)),
+    dict(name="pfhrgb", params=dict(descriptor_type=1)),
+    dict(name="shot", params=dict(descriptor_type=4)),
+    dict(name="sc3d", params=dict(descriptor_type=5)),
 ]
 COMMAND_LINES = [
     [],
