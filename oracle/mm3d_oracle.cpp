@@ -14,10 +14,12 @@
 // reference's call sites ("[REF file:line]").  What IS pinned by reference code
 // compiled here (oracle/_ref, `make ref`; outputs committed under tests/golden/):
 //   * the pose-graph step: the reference's graph.cpp unmodified (libgraph_ref.so);
-//   * the DRIVER and the pair-level glue: the reference's map_merging.cpp, matching.cpp
-//     and graph.cpp unmodified, running on this file's stage functions
+//   * ALL of the reference's own sources: features.cpp, map_merging.cpp, matching.cpp
+//     and graph.cpp unmodified, with stand-ins for the PCL classes they drive that
+//     hand the work to this file's stage functions
 //     (libmapmerging_ref.so, mapmerging_ref_shim.cpp) — estimateMapsTransforms /
-//     computeGlobalTransforms / composeMaps control flow, findFeatureCorrespondences
+//     computeGlobalTransforms / composeMaps control flow, how features.cpp configures
+//     each PCL object and filters invalid descriptors, findFeatureCorrespondences
 //     (the reciprocal k-NN cross-match), how matching.cpp configures RANSAC / SAC-IA /
 //     ICP / validation, the command-line flag table and the params printout;
 //   * MapMergingParams defaults and the enum layer: the reference's public headers
