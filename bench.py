@@ -400,7 +400,7 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": job.world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {M} maps x {cfg['n_points']} pts, SIFT+FPFH, MATCHING+ICP, {P} pairs", "seed": cfg["seed"],
-                   "l2": "256 MiB memset between steps (inputs are 64 MB < L2)",
+                   "l2": f"256 MiB memset between steps (inputs are {M * cfg['n_points'] * 16 // 1000000} MB)",
                    "parallelism": "single GPU" if job.world == 1 else f"maps and pairs sharded over {job.world} ranks, NCCL all_gather of features"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(job.h2d_bytes), "d2h_bytes_per_step": int(M * 64),
                 "ms_per_step": ms_e2e / args.steps},
