@@ -33,6 +33,9 @@ class Params(C.Structure):
 
 
 def default_params(**kw) -> Params:
+    """MapMergingParams() of the reference, EXCEPT descriptor_type, which defaults to FPFH (2) here because the O(K n^2) PFH of
+    the reference's default makes CPU tests slow; pass descriptor_type=0 for the reference's own default.  The product's
+    mm3d_params_default is pinned to the reference header (tests/golden/params_ref.json)."""
     # dependent defaults are frozen at resolution 0.1 (map_merging.h:29-39)
     p = Params(0.1, 0.1 * 8.0, 50, 0.1 * 6.0, 0, 5.0, 2, 0, 1, 0.1 * 5.0, 0.1 * 5.0 * 2.0, 500, 5, 1e-2, 0.0, 0.05)
     for k, v in kw.items():
