@@ -135,7 +135,9 @@ int mm3d_icp(mm3d_ctx* ctx, const float* src, uint64_t n_src, const float* tgt, 
 int mm3d_score(mm3d_ctx* ctx, const float* src, uint64_t n_src, const float* tgt, uint64_t n_tgt, const float* transform,
                double max_distance, double index_leaf, double* score);
 /* computeGlobalTransforms (src/map_merging.cpp:153-186) on the host: st = int32[n][2] (source, target).
- * out has room for max-index+1 matrices.  Optional outputs for parity with src/graph.cpp. */
+ * With nodes = max index + 1: out has room for nodes matrices.  Optional outputs for parity with src/graph.cpp:
+ * in_component n_pairs ints, tree_edges 4 x nodes ints (every tree edge is listed from both ends), centers nodes ints (a node without edges has eccentricity 0, so every
+ * isolated node below the max index is reported as a centre). */
 int mm3d_global_transforms(int n_pairs, const int32_t* st, const float* transforms, const double* confidences, double confidence_threshold,
                            float* out, int* n_out, int* reference_frame, int32_t* in_component, int32_t* tree_edges, int* n_tree_edges,
                            int32_t* centers, int* n_centers);
@@ -170,10 +172,10 @@ int mm3d_register_pairs(mm3d_ctx* ctx, const mm3d_features* f, int n_pairs, cons
  * pcl::VoxelGrid's overflow guard fires: the result is then the plain concatenation) -> all-reduce, pick splitters
  * (splitters[r] <= bucket < splitters[r+1] goes to rank r) -> partition (stable; points_dev receives the points grouped by
  * destination rank) -> all-to-all -> mm3d_downsample_dev on the received points.  Concatenating the ranks' outputs in rank
- * order gives exactly mm3d_compose_maps' output. */
+ * order gives exactly mm3d_compose_maps' output.  begin returns MM3D_ERR_ARG when n_maps != n_transforms (the reference throws). */
 typedef struct mm3d_shard mm3d_shard;
-int mm3d_compose_shard_begin(mm3d_ctx* ctx, int n_maps, const float* const* clouds, const uint64_t* n_points, const float* transforms,
-                             float* bbox, mm3d_shard** shard);
+int mm3d_compose_shard_begin(mm3d_ctx* ctx, int n_maps, const float* const* clouds, const uint64_t* n_points, int n_transforms,
+                             const float* transforms, float* bbox, mm3d_shard** shard);
 int mm3d_compose_shard_size(const mm3d_shard* shard, uint64_t* n);
 int mm3d_compose_shard_histogram(mm3d_ctx* ctx, const mm3d_shard* shard, const float* global_bbox, double resolution, int n_buckets,
                                  uint64_t* hist);

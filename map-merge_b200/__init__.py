@@ -303,7 +303,8 @@ class Context:
         T = np.asarray(transforms, np.float32).reshape(-1, 4, 4)
         Tc = np.ascontiguousarray(T.transpose(0, 2, 1)) if len(T) else np.zeros((1, 16), np.float32)
         bbox = np.zeros(6, np.float32); h = C.c_void_p()
-        self._check(self.L.mm3d_compose_shard_begin(self.h, len(clouds), ptrs, ns, Tc.ctypes.data_as(f32p), bbox.ctypes.data_as(f32p), C.byref(h)))
+        self._check(self.L.mm3d_compose_shard_begin(self.h, len(clouds), ptrs, ns, len(T), Tc.ctypes.data_as(f32p), bbox.ctypes.data_as(f32p),
+                                                    C.byref(h)))
         n = C.c_uint64()
         self.L.mm3d_compose_shard_size(h, C.byref(n))
         return bbox, h, int(n.value)
@@ -382,7 +383,8 @@ def global_transforms(st, transforms, conf, thr, debug=False):
     Tc = np.ascontiguousarray(np.asarray(transforms, np.float32).reshape(-1, 4, 4).transpose(0, 2, 1)) if n else np.zeros((1, 16), np.float32)
     nodes = int(st.max()) + 1 if n else 0
     out = np.zeros((max(nodes, 1), 16), np.float32); no = C.c_int(); ref = C.c_int()
-    inc = np.zeros(max(n, 1), np.int32); te = np.zeros((4 * n + 4, 2), np.int32); nte = C.c_int(); cen = np.zeros(n + 2, np.int32); nc = C.c_int()
+    # capacities per include/mm3d.h: tree edges (listed from both ends) < 2 x nodes, centres <= nodes (every isolated node below the max index is a centre)
+    inc = np.zeros(max(n, 1), np.int32); te = np.zeros((2 * nodes + 2, 2), np.int32); nte = C.c_int(); cen = np.zeros(nodes + 1, np.int32); nc = C.c_int()
     rc = L.mm3d_global_transforms(n, st.ctypes.data_as(i32p), Tc.ctypes.data_as(f32p), conf.ctypes.data_as(f64p), C.c_double(thr),
                                   out.ctypes.data_as(f32p), C.byref(no), C.byref(ref), inc.ctypes.data_as(i32p), te.ctypes.data_as(i32p),
                                   C.byref(nte), cen.ctypes.data_as(i32p), C.byref(nc))

@@ -105,9 +105,9 @@ double auto_leaf(double index_leaf, double radius, double ratio)
 
 void check_supported(const mm3d_params& p)
 {
-  if (p.keypoint_type != MM3D_KP_SIFT && p.keypoint_type != MM3D_KP_HARRIS) throw std::runtime_error("unsupported: unknown keypoint_type");
-  if (p.descriptor_type < MM3D_DESC_PFH || p.descriptor_type > MM3D_DESC_SC3D) throw std::runtime_error("unsupported: unknown descriptor_type");
-  if (p.estimation_method != MM3D_EST_MATCHING && p.estimation_method != MM3D_EST_SAC_IA) throw std::runtime_error("unsupported: unknown estimation_method");
+  if (p.keypoint_type != MM3D_KP_SIFT && p.keypoint_type != MM3D_KP_HARRIS) throw UnsupportedError("unsupported: unknown keypoint_type");
+  if (p.descriptor_type < MM3D_DESC_PFH || p.descriptor_type > MM3D_DESC_SC3D) throw UnsupportedError("unsupported: unknown descriptor_type");
+  if (p.estimation_method != MM3D_EST_MATCHING && p.estimation_method != MM3D_EST_SAC_IA) throw UnsupportedError("unsupported: unknown estimation_method");
 }
 
 // src/map_merging.cpp:212-242, stage-major over all maps
@@ -324,11 +324,16 @@ int estimate_from_views(Ctx& c, const std::vector<CloudView>& raw, const mm3d_pa
   try { \
     MM_CUDA(cudaSetDevice(c.device));
 #define MM_CATCH \
+  } catch (const UnsupportedError& e) { \
+    c.err = e.what(); \
+    return MM3D_ERR_UNSUPPORTED; \
+  } catch (const CudaError& e) { \
+    c.err = e.what(); \
+    cudaGetLastError(); \
+    return MM3D_ERR_CUDA; \
   } catch (const std::exception& e) { \
     c.err = e.what(); \
     cudaGetLastError(); \
-    if (c.err.find("unsupported") != std::string::npos) return MM3D_ERR_UNSUPPORTED; \
-    if (c.err.find("CUDA") != std::string::npos) return MM3D_ERR_CUDA; \
     return MM3D_ERR; \
   } \
   return MM3D_OK;
@@ -523,7 +528,7 @@ int mm3d_keypoints(mm3d_ctx* ctx, const float* pts, uint64_t n, const float* nor
 {
   if (!keypoints || !n_keypoints) return MM3D_ERR_ARG;
   MM_TRY(ctx)
-  if (type != MM3D_KP_SIFT && type != MM3D_KP_HARRIS) throw std::runtime_error("unsupported: unknown keypoint_type");
+  if (type != MM3D_KP_SIFT && type != MM3D_KP_HARRIS) throw UnsupportedError("unsupported: unknown keypoint_type");
   DCloud d = upload_cloud(c, pts, n);
   std::vector<DCloud> kp;
   std::vector<DBuf<float>> dog;
@@ -562,7 +567,7 @@ int mm3d_descriptors(mm3d_ctx* ctx, const float* pts, uint64_t n, const float* n
 {
   if (!keypoints_out || !n_out || !descriptors) return MM3D_ERR_ARG;
   MM_TRY(ctx)
-  if (type < MM3D_DESC_PFH || type > MM3D_DESC_SC3D) throw std::runtime_error("unsupported: unknown descriptor_type");
+  if (type < MM3D_DESC_PFH || type > MM3D_DESC_SC3D) throw UnsupportedError("unsupported: unknown descriptor_type");
   DCloud d = upload_cloud(c, pts, n);
   DBuf<float4> nm(c, d.n);
   if (d.n) MM_CUDA(cudaMemcpyAsync(nm.p, normals, (size_t)d.n * sizeof(float4), cudaMemcpyHostToDevice, c.stream));
@@ -796,11 +801,15 @@ int mm3d_profile_end(mm3d_ctx* ctx, char** json)
 
 // ---- composeMaps sharded over ranks --------------------------------------------
 
-int mm3d_compose_shard_begin(mm3d_ctx* ctx, int n_maps, const float* const* clouds, const uint64_t* n_points, const float* transforms,
-                             float* bbox, mm3d_shard** shard)
+int mm3d_compose_shard_begin(mm3d_ctx* ctx, int n_maps, const float* const* clouds, const uint64_t* n_points, int n_transforms,
+                             const float* transforms, float* bbox, mm3d_shard** shard)
 {
   if (!bbox || !shard) return MM3D_ERR_ARG;
   *shard = nullptr;
+  if (n_maps != n_transforms) {
+    if (ctx) ctx->c.err = "composeMaps: clouds and transforms size must be the same.";
+    return MM3D_ERR_ARG;
+  }
   MM_TRY(ctx)
   std::vector<DCloud> d;
   std::vector<std::vector<float>> tr;

@@ -288,7 +288,9 @@ void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<D
     memset(&hst[a], 0, sizeof(IcpState));
     for (int k = 0; k < 16; ++k) hst[a].final_t[k] = hst[a].step[k] = (k % 5 == 0) ? 1.f : 0.f;
     hst[a].prev_mse = 1.7976931348623157e308;
-    hst[a].active = 1;
+    // an empty source launches no block, so nothing would ever retire the pair: it starts out finished and not converged
+    // ("Not enough correspondences found", the transform stays the initial guess)
+    hst[a].active = clouds[jobs[act[a]].a].n > 0 ? 1 : 0;
   }
   DBuf<IcpState> dst = to_device(c, hst);
   std::vector<IcpJob> ij(A);
@@ -310,7 +312,8 @@ void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<D
   }
   DBuf<IcpJob> dij = to_device(c, ij);
   DBuf<int> dn_active(c, 1);
-  int n_active = A;
+  int n_active = 0;
+  for (int a = 0; a < A; ++a) n_active += hst[a].active;
   dn_active.upload(c, &n_active, 1);
   const int iblocks = std::max(1, std::min((mx + 255) / 256, 148 * 8));
   MM_LAUNCH(c, icp_init_kernel, dim3(iblocks, A), 256, 0, dij.p);

@@ -635,7 +635,7 @@ EncodeTiledFn encode_tiled()
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     MM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
-    if (!p || q != cudaDriverEntryPointSuccess) throw std::runtime_error("CUDA error: cuTensorMapEncodeTiled is not available");
+    if (!p || q != cudaDriverEntryPointSuccess) throw CudaError("CUDA error: cuTensorMapEncodeTiled is not available");
     fn = (EncodeTiledFn)p;
   }
   return fn;
@@ -651,7 +651,7 @@ CUtensorMap make_map(float* base, int rows, int Kp)
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) throw std::runtime_error("CUDA error: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  if (r != CUDA_SUCCESS) throw CudaError("CUDA error: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
   return m;
 }
 

@@ -173,6 +173,43 @@ __global__ void __launch_bounds__(128) knn_generic_kernel(const KnnJob* __restri
     }
 }
 
+// Any k (matching_k > 16): the reference hands matching_k straight to nearestKSearch (matching.cpp:45-60), so large values
+// must work.  One thread per query row, the sorted top-k list lives in the output arrays themselves (global memory);
+// same arithmetic and tie order as the kernels above.  A fallback, not a fast path.
+__global__ void __launch_bounds__(128) knn_anyk_kernel(const KnnJob* __restrict__ jobs, int D)
+{
+  const KnnJob j = jobs[blockIdx.y];
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= j.na) return;
+  const int k = j.k;
+  const float* a = j.A + (size_t)row * D;
+  float* bd = j.dist + (size_t)row * k;
+  int* bi = j.idx + (size_t)row * k;
+  int cnt = 0;
+  for (int r = 0; r < j.nb; ++r) {
+    const float* b = j.B + (size_t)r * D;
+    float v = 0.f;
+    for (int t = 0; t < D; ++t) {
+      const float diff = a[t] - __ldg(&b[t]);
+      v += diff * diff;
+    }
+    if (cnt == k && !(v < bd[k - 1])) continue;
+    int pos = (cnt < k) ? cnt : k - 1;
+    while (pos > 0 && v < bd[pos - 1]) {
+      bd[pos] = bd[pos - 1];
+      bi[pos] = bi[pos - 1];
+      --pos;
+    }
+    bd[pos] = v;
+    bi[pos] = r;
+    if (cnt < k) ++cnt;
+  }
+  for (int t = cnt; t < k; ++t) {
+    bd[t] = 0.f;
+    bi[t] = -1;
+  }
+}
+
 struct CrossJob {
   const int* fwd_idx;
   const float* fwd_dist;
@@ -599,7 +636,6 @@ void match_batch(Ctx& c, const std::vector<const float*>& desc, const std::vecto
   corr.clear();
   corr.resize(P);
   if (P == 0) return;
-  if (k_in > (size_t)KMAX) throw std::runtime_error("match_batch: matching_k > 16 is not supported");
   // forward and backward k-NN problems, 2 per pair
   std::vector<KnnJob> kj(2 * P);
   std::vector<DBuf<int>> idxb(2 * P);
@@ -637,6 +673,8 @@ void match_batch(Ctx& c, const std::vector<const float*>& desc, const std::vecto
       if (kj[2 * p + 1].na > 0) probs.push_back(KnnProblem{b, a, kj[2 * p + 1].na, kj[2 * p + 1].k, kj[2 * p + 1].idx, kj[2 * p + 1].dist});
     }
     knn_tc_batch(c, desc, nk, dim, probs);
+  } else if (max_rows > 0 && !k_fits) {
+    MM_LAUNCH(c, knn_anyk_kernel, dim3((max_rows + 127) / 128, 2 * P), 128, 0, dkj.p, dim);
   } else if (max_rows > 0) {
     // the register kernel needs one k for the whole batch (k is clamped per job only when a set is smaller than k)
     bool uniform_k = true;

@@ -20,12 +20,20 @@
 
 namespace mm3d {
 
+// Typed errors: the C ABI maps them to MM3D_ERR_CUDA / MM3D_ERR_UNSUPPORTED (anything else is MM3D_ERR).
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+struct UnsupportedError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
 #define MM_CUDA(expr)                                                                                   \
   do {                                                                                                  \
     cudaError_t _e = (expr);                                                                            \
     if (_e != cudaSuccess)                                                                              \
-      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " __FILE__ ":" + \
-                               std::to_string(__LINE__) + " (" #expr ")");                              \
+      throw mm3d::CudaError(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " __FILE__ ":" + \
+                            std::to_string(__LINE__) + " (" #expr ")");                                 \
   } while (0)
 
 // Optional per-kernel timing: one CUDA event pair around every launch, recorded on
@@ -153,6 +161,7 @@ struct VoxGeom {
   int div_b[3];
   int passthrough;  // overflow guard hit: output = input
   int nbits;        // bits needed for a voxel key
+  int nonfinite;    // points with a NaN / Inf coordinate (left out of the box; the voxel grid drops them)
 };
 
 // Neighbour index over one cloud.

@@ -30,30 +30,48 @@ __host__ __device__ __forceinline__ float ord2f(uint32_t u)
 #endif
 }
 
-// bbox[map][6] = ordered-uint min x,y,z then max x,y,z
+// bbox[map][8] = ordered-uint min x,y,z, max x,y,z, number of non-finite points, pad.  Non-finite points are left out
+// of the box, as pcl::getMinMax3D does for clouds that are not dense [PCL-recall pcl/common/impl/common.hpp].
+// Block-level reduction (warp shuffles, then shared memory): seven atomics per BLOCK.
+constexpr int BBOX_STRIDE = 8;
 __global__ void __launch_bounds__(256) bbox_kernel(const CloudView* __restrict__ clouds, uint32_t* __restrict__ bbox)
 {
   const CloudView cv = clouds[blockIdx.y];
-  uint32_t mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
+  if ((int)(blockIdx.x * blockDim.x) >= cv.n) return;  // block-uniform
+  uint32_t mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u}, bad = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cv.n; i += gridDim.x * blockDim.x) {
-    const float4 p = cv.pts[i];
+    const float4 p = __ldg(&cv.pts[i]);
+    if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) {
+      ++bad;
+      continue;
+    }
     const uint32_t a = f2ord(p.x), b = f2ord(p.y), c = f2ord(p.z);
     mn[0] = min(mn[0], a); mx[0] = max(mx[0], a);
     mn[1] = min(mn[1], b); mx[1] = max(mx[1], b);
     mn[2] = min(mn[2], c); mx[2] = max(mx[2], c);
   }
+  __shared__ uint32_t sh[8][7];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     mn[k] = __reduce_min_sync(0xffffffffu, mn[k]);
     mx[k] = __reduce_max_sync(0xffffffffu, mx[k]);
   }
-  if ((threadIdx.x & 31) == 0 && blockIdx.x * blockDim.x < cv.n + (int)blockDim.x) {
-    uint32_t* bb = bbox + blockIdx.y * 6;
+  bad = __reduce_add_sync(0xffffffffu, bad);
+  if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      atomicMin(&bb[k], mn[k]);
-      atomicMax(&bb[3 + k], mx[k]);
-    }
+    for (int k = 0; k < 3; ++k) { sh[w][k] = mn[k]; sh[w][3 + k] = mx[k]; }
+    sh[w][6] = bad;
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) {
+    const int k = threadIdx.x;
+    uint32_t v = sh[0][k];
+    for (int ww = 1; ww < 8; ++ww) v = k < 3 ? min(v, sh[ww][k]) : (k < 6 ? max(v, sh[ww][k]) : v + sh[ww][k]);
+    uint32_t* bb = bbox + blockIdx.y * BBOX_STRIDE;
+    if (k < 3) atomicMin(&bb[k], v);
+    else if (k < 6) atomicMax(&bb[k], v);
+    else if (v) atomicAdd(&bb[6], v);
   }
 }
 
@@ -67,12 +85,13 @@ __global__ void geom_kernel(const CloudView* __restrict__ clouds, const uint32_t
   for (int k = 0; k < 3; ++k) { g.min_b[k] = 0; g.div_b[k] = 0; }
   g.passthrough = 0;
   g.nbits = 0;
-  if (clouds[m].n > 0) {
+  g.nonfinite = clouds[m].n > 0 ? (int)bbox[m * BBOX_STRIDE + 6] : 0;
+  if (clouds[m].n > g.nonfinite) {
     const float inv = 1.0f / leaf;
     float mn[3], mx[3];
     for (int k = 0; k < 3; ++k) {
-      mn[k] = ord2f(bbox[m * 6 + k]);
-      mx[k] = ord2f(bbox[m * 6 + 3 + k]);
+      mn[k] = ord2f(bbox[m * BBOX_STRIDE + k]);
+      mx[k] = ord2f(bbox[m * BBOX_STRIDE + 3 + k]);
     }
     bool pass = !(leaf > 0.0f);
     if (!pass) {
@@ -172,6 +191,30 @@ __global__ void __launch_bounds__(256) centroid_kernel(const CloudView* __restri
   const uint32_t rgba = ((uint32_t)(sa / n) << 24) | ((uint32_t)(sr / n) << 16) | ((uint32_t)(sgc / n) << 8) | (uint32_t)(sb / n);
   o.w = __uint_as_float(rgba);
   out[v] = o;
+}
+
+// ---- non-finite points (pcl::VoxelGrid skips them when the cloud is not dense) -------------------------------------
+struct FiniteJob {
+  const float4* src;
+  float4* dst;
+  int n;
+  int off;  // offset of this cloud in the concatenated flag / position arrays
+};
+__global__ void __launch_bounds__(256) finite_flag_kernel(const FiniteJob* __restrict__ jobs, uint32_t* __restrict__ flags)
+{
+  const FiniteJob j = jobs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= j.n) return;
+  const float4 p = j.src[i];
+  flags[j.off + i] = (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) finite_compact_kernel(const FiniteJob* __restrict__ jobs, const uint32_t* __restrict__ flags,
+                                                            const uint32_t* __restrict__ pos)
+{
+  const FiniteJob j = jobs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= j.n) return;
+  if (flags[j.off + i]) j.dst[pos[j.off + i]] = j.src[i];
 }
 
 // ---- index build ------------------------------------------------------------
@@ -288,9 +331,9 @@ static void compute_geom(Ctx& c, const std::vector<CloudView>& in, const DBuf<Cl
                          DBuf<VoxGeom>& dgeom)
 {
   const int M = (int)in.size();
-  std::vector<uint32_t> init(M * 6);
+  std::vector<uint32_t> init(M * BBOX_STRIDE);
   for (int m = 0; m < M; ++m)
-    for (int k = 0; k < 6; ++k) init[m * 6 + k] = k < 3 ? 0xffffffffu : 0u;
+    for (int k = 0; k < BBOX_STRIDE; ++k) init[m * BBOX_STRIDE + k] = k < 3 ? 0xffffffffu : 0u;
   DBuf<uint32_t> bbox = to_device(c, init);
   const int mx = max_n(in);
   const int blocks = std::max(1, std::min((mx + 255) / 256, 148 * 4));
@@ -304,24 +347,60 @@ static void compute_geom(Ctx& c, const std::vector<CloudView>& in, const DBuf<Cl
 
 }  // namespace
 
-void voxel_downsample_batch(Ctx& c, const std::vector<CloudView>& in, float leaf, std::vector<DCloud>& out, std::vector<VoxGeom>* geom_out)
+void voxel_downsample_batch(Ctx& c, const std::vector<CloudView>& in_arg, float leaf, std::vector<DCloud>& out, std::vector<VoxGeom>* geom_out)
 {
-  const int M = (int)in.size();
+  const int M = (int)in_arg.size();
   out.clear();
   out.resize(M);
   if (M == 0) return;
   int total = 0;
-  std::vector<Seg> segs = make_segs(in, &total);
+  std::vector<Seg> segs = make_segs(in_arg, &total);
   std::vector<VoxGeom> geom(M);
   if (total == 0) {
     for (auto& g : geom) memset(&g, 0, sizeof(g));
     if (geom_out) *geom_out = geom;
     return;
   }
-  DBuf<CloudView> dviews = to_device(c, in);
+  DBuf<CloudView> dviews = to_device(c, in_arg);
   DBuf<VoxGeom> dgeom;
-  compute_geom(c, in, dviews, leaf, geom, dgeom);
+  compute_geom(c, in_arg, dviews, leaf, geom, dgeom);
   if (geom_out) *geom_out = geom;
+  // Clouds with NaN / Inf coordinates (organised RGB-D clouds, is_dense == false): pcl::VoxelGrid leaves such points out of
+  // the bounding box and out of the voxels.  Rare, so the common case pays only the count that rides on the bbox pass.
+  std::vector<CloudView> in = in_arg;
+  std::vector<DBuf<float4>> finite_copy;
+  {
+    std::vector<FiniteJob> fj;
+    std::vector<Seg> fsegs;
+    std::vector<int> fmap;
+    int foff = 0, fmx = 0;
+    for (int m = 0; m < M; ++m)
+      if (geom[m].nonfinite > 0 && !geom[m].passthrough) {  // the overflow guard returns the input as it is, NaNs included
+        fj.push_back(FiniteJob{in[m].pts, nullptr, in[m].n, foff});
+        fsegs.push_back(Seg{foff, in[m].n});
+        fmap.push_back(m);
+        foff += in[m].n;
+        fmx = std::max(fmx, in[m].n);
+      }
+    if (!fj.empty()) {
+      DBuf<uint32_t> fflags(c, foff), fpos(c, foff);
+      finite_copy.resize(fj.size());
+      for (size_t t = 0; t < fj.size(); ++t) {
+        finite_copy[t].alloc(c, (size_t)(fj[t].n - geom[fmap[t]].nonfinite) + 1);
+        fj[t].dst = finite_copy[t].p;
+      }
+      DBuf<FiniteJob> dfj = to_device(c, fj);
+      const dim3 fgrid((fmx + 255) / 256, (unsigned)fj.size());
+      MM_LAUNCH(c, finite_flag_kernel, fgrid, 256, 0, dfj.p, fflags.p);
+      std::vector<int> ftotals;
+      scan_flags_batch(c, fflags.p, fpos.p, fsegs, ftotals);
+      MM_LAUNCH(c, finite_compact_kernel, fgrid, 256, 0, dfj.p, fflags.p, fpos.p);
+      for (size_t t = 0; t < fj.size(); ++t) in[fmap[t]] = CloudView{finite_copy[t].p, ftotals[t]};
+      segs = make_segs(in, &total);
+      dviews = to_device(c, in);
+      if (total == 0) return;
+    }
+  }
   int nbits = 0;
   for (const VoxGeom& g : geom) nbits = std::max(nbits, g.nbits);
   DBuf<Seg> dsegs = to_device(c, segs);

@@ -34,7 +34,13 @@ int main(int argc, char** argv)
   std::vector<PointCloudConstPtr> clouds;
   for (int idx : pcd_file_indices) {
     PointCloudPtr cloud(new PointCloud);
-    if (mm3d_io::loadPCDFile(argv[idx], *cloud) < 0) {
+    int rc = -1;
+    try {
+      rc = mm3d_io::loadPCDFile(argv[idx], *cloud);
+    } catch (const std::exception& e) {  // corrupt file: same exit as an unreadable one (map_merge_tool.cpp:27-31)
+      std::cerr << e.what() << "\n";
+    }
+    if (rc < 0) {
       std::cerr << "Error loading pointcloud file " << argv[idx] << ". Aborting.\n";
       return -1;
     }
@@ -51,9 +57,15 @@ int main(int argc, char** argv)
   std::cout << "> Estimated transforms:\n";
   for (const auto& transform : transforms) std::cout << transform << std::endl;
   std::cout << "> Compositing clouds and writing to output.pcd\n";
-  // map_merge_node.cpp:116 resizes the cloud list to the transform count; the tool passes both as they are
-  clouds.resize(transforms.size());
-  PointCloudPtr result = composeMaps(clouds, transforms, params.output_resolution);
+  // clouds and transforms are passed as they are (map_merge_tool.cpp:49-50): when trailing maps have no keypoints the
+  // transform list is shorter and composeMaps throws, as in the reference (which lets the exception terminate the tool)
+  PointCloudPtr result;
+  try {
+    result = composeMaps(clouds, transforms, params.output_resolution);
+  } catch (const std::exception& e) {
+    std::cerr << e.what() << "\n";
+    return -3;
+  }
   if (!result) return -3;
   return mm3d_io::savePCDFileBinary(output_name, *result);
 }

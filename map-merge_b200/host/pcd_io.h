@@ -27,7 +27,7 @@ inline bool lzf_decompress(const uint8_t* in, size_t in_len, uint8_t* out, size_
     unsigned ctrl = *ip++;
     if (ctrl < (1u << 5)) {  // literal run
       ++ctrl;
-      if (op + ctrl > out_end || ip + ctrl > in_end) return false;
+      if (ctrl > (size_t)(out_end - op) || ctrl > (size_t)(in_end - ip)) return false;
       std::memcpy(op, ip, ctrl);
       op += ctrl;
       ip += ctrl;
@@ -38,8 +38,9 @@ inline bool lzf_decompress(const uint8_t* in, size_t in_len, uint8_t* out, size_
         len += *ip++;
         if (ip >= in_end) return false;
       }
-      const uint8_t* ref = op - ((ctrl & 0x1f) << 8) - 1 - *ip++;
-      if (ref < out || op + len + 2 > out_end) return false;
+      const size_t back = ((size_t)(ctrl & 0x1f) << 8) + 1 + *ip++;  // distance of the reference, checked before a pointer is formed
+      if (back > (size_t)(op - out) || (size_t)len + 2 > (size_t)(out_end - op)) return false;
+      const uint8_t* ref = op - back;
       len += 2;
       while (len--) *op++ = *ref++;
     }
@@ -108,6 +109,16 @@ inline int loadPCDFile(const std::string& path, map_merge_3d::PointCloud& cloud)
     if (fields[i].name == "rgb" || fields[i].name == "rgba") ic = (int)i;
   }
   if (ix < 0 || iy < 0 || iz < 0) return -1;
+  // the payload cannot be larger than what is left of the file: refuse headers that claim more (corrupt or truncated files)
+  const std::streampos data_pos = f.tellg();
+  f.seekg(0, std::ios::end);
+  const std::streampos end_pos = f.tellg();
+  f.seekg(data_pos);
+  if (data_pos < 0 || end_pos < data_pos || step <= 0) return -1;
+  const size_t remaining = (size_t)(end_pos - data_pos);
+  if (data_mode == "ascii" && points > remaining) return -1;  // at least one byte per point
+  if (data_mode == "binary" && points > remaining / (size_t)step) return -1;
+  if (data_mode == "binary_compressed" && points > (size_t)0xffffffffu / (size_t)step) return -1;
   cloud.points.assign(points, map_merge_3d::PointT());
   auto read_float = [](const uint8_t* p, const Field& fd) -> float {
     if (fd.type == 'F' && fd.size == 4) { float v; std::memcpy(&v, p, 4); return v; }
@@ -143,10 +154,13 @@ inline int loadPCDFile(const std::string& path, map_merge_3d::PointCloud& cloud)
     } else if (data_mode == "binary_compressed") {
       uint32_t comp = 0, uncomp = 0;
       f.read((char*)&comp, 4);
+      if (f.gcount() != 4) return -1;
       f.read((char*)&uncomp, 4);
-      if (uncomp != raw.size()) return -1;
+      if (f.gcount() != 4) return -1;
+      if (uncomp != raw.size() || remaining < 8 || comp > remaining - 8) return -1;
       std::vector<uint8_t> cbuf(comp), soa(uncomp);
       f.read((char*)cbuf.data(), comp);
+      if ((size_t)f.gcount() != (size_t)comp) return -1;
       if (!lzf_decompress(cbuf.data(), comp, soa.data(), uncomp)) return -1;
       // compressed files store field after field (SoA); rebuild the AoS rows
       size_t off = 0;

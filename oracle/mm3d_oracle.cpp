@@ -366,10 +366,20 @@ static Cloud voxel_grid(const Cloud& in, float leaf, VoxelInfo* info = nullptr, 
   }
   const float inv = 1.0f / leaf;  // Eigen::Array4f::Ones() / leaf_size_.array()
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  // Every input is treated as !is_dense: getMinMax3D and the filter loop skip points with a non-finite coordinate
+  // [PCL-recall pcl/common/impl/common.hpp, pcl/filters/impl/voxel_grid.hpp].
+  auto finite = [](const P4& p) { return std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z); };
+  size_t n_finite = 0;
   for (const P4& p : in) {  // getMinMax3D
+    if (!finite(p)) continue;
+    ++n_finite;
     mn[0] = std::min(mn[0], p.x); mx[0] = std::max(mx[0], p.x);
     mn[1] = std::min(mn[1], p.y); mx[1] = std::max(mx[1], p.y);
     mn[2] = std::min(mn[2], p.z); mx[2] = std::max(mx[2], p.z);
+  }
+  if (n_finite == 0) {
+    if (info) *info = vi;
+    return out;
   }
   bool pass = !(leaf > 0.0f);
   if (!pass) {
@@ -392,13 +402,14 @@ static Cloud voxel_grid(const Cloud& in, float leaf, VoxelInfo* info = nullptr, 
     vi.div_b[a] = div_b[a];
   }
   const int mul1 = div_b[0], mul2 = div_b[0] * div_b[1];
-  std::vector<std::pair<uint32_t, uint32_t>> iv(in.size());
+  std::vector<std::pair<uint32_t, uint32_t>> iv;
+  iv.reserve(n_finite);
   for (size_t i = 0; i < in.size(); ++i) {
+    if (!finite(in[i])) continue;
     const int i0 = (int)(std::floor(in[i].x * inv) - (float)min_b[0]);
     const int i1 = (int)(std::floor(in[i].y * inv) - (float)min_b[1]);
     const int i2 = (int)(std::floor(in[i].z * inv) - (float)min_b[2]);
-    iv[i].first = (uint32_t)(i0 + i1 * mul1 + i2 * mul2);
-    iv[i].second = (uint32_t)i;
+    iv.emplace_back((uint32_t)(i0 + i1 * mul1 + i2 * mul2), (uint32_t)i);
   }
   std::sort(iv.begin(), iv.end());  // canonical: ties by ascending point index
   size_t k = 0;

@@ -245,7 +245,8 @@ class Oracle:
     def graph(self, st, conf, thr):
         st = np.ascontiguousarray(st, np.int32); conf = np.ascontiguousarray(conf, np.float64)
         n = len(st)
-        inc = np.zeros(n, np.int32); te = np.zeros((4 * n + 4, 2), np.int32); nte = C.c_int(); cen = np.zeros(n + 2, np.int32); nc = C.c_int()
+        nodes = int(st.max()) + 1 if n else 0  # outputs are sized by node count: every isolated node is a centre
+        inc = np.zeros(n, np.int32); te = np.zeros((2 * nodes + 2, 2), np.int32); nte = C.c_int(); cen = np.zeros(nodes + 1, np.int32); nc = C.c_int()
         self.lib.orc_graph(n, st.ctypes.data_as(i32p), conf.ctypes.data_as(f64p), C.c_double(thr), inc.ctypes.data_as(i32p),
                            te.ctypes.data_as(i32p), C.byref(nte), cen.ctypes.data_as(i32p), C.byref(nc))
         return inc, te[:nte.value].copy(), cen[:nc.value].copy()
@@ -307,7 +308,8 @@ class GraphRef:
     def graph(self, st, conf, thr):
         st = np.ascontiguousarray(st, np.int32); conf = np.ascontiguousarray(conf, np.float64)
         n = len(st)
-        inc = np.zeros(n, np.int32); te = np.zeros((4 * n + 4, 2), np.int32); nte = C.c_int(); cen = np.zeros(n + 2, np.int32)
+        nodes = int(st.max()) + 1 if n else 0
+        inc = np.zeros(n, np.int32); te = np.zeros((2 * nodes + 2, 2), np.int32); nte = C.c_int(); cen = np.zeros(nodes + 1, np.int32)
         nc = C.c_int(); nn = C.c_int()
         self.lib.ref_graph(n, st.ctypes.data_as(i32p), conf.ctypes.data_as(f64p), C.c_double(thr), inc.ctypes.data_as(i32p),
                            te.ctypes.data_as(i32p), C.byref(nte), cen.ctypes.data_as(i32p), C.byref(nc), C.byref(nn))

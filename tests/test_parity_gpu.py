@@ -55,6 +55,33 @@ def test_downsample_edge_cases(ctx, oracle):
     assert_same_bits(ctx.downsample(pts, 0.25), oracle.downsample(pts, 0.25)[0], "dense voxels")
 
 
+def test_downsample_non_finite_points(ctx, oracle, tiny_maps):
+    """NaN / Inf coordinates (organised RGB-D clouds, is_dense == false) are dropped like pcl::VoxelGrid drops them; the same
+    through composeMaps, whose transform keeps them non-finite."""
+    maps, _ = tiny_maps
+    rng = np.random.default_rng(4)
+    pts = maps[0].copy()
+    bad = rng.choice(len(pts), 500, replace=False)
+    pts[bad[:200], 0] = np.nan
+    pts[bad[200:350], 1] = np.inf
+    pts[bad[350:], 2] = -np.inf
+    want, _ = oracle.downsample(pts, 0.1)
+    clean, _ = oracle.downsample(np.delete(pts, bad, axis=0), 0.1)
+    assert_same_bits(want, clean, "oracle: dirty == clean")
+    assert_same_bits(ctx.downsample(pts, 0.1), want, "downsample with non-finite points")
+    assert np.isfinite(ctx.downsample(pts, 0.1)[:, :3]).all()
+    assert ctx.downsample(np.full((64, 4), np.nan, np.float32), 0.1).shape == (0, 4)
+    T = np.stack([np.eye(4, dtype=np.float32)] * 2)
+    got = ctx.compose_maps([pts, maps[1]], T, 0.05)
+    assert_same_bits(got, oracle.compose_maps([pts, maps[1]], T, 0.05), "composeMaps with non-finite points")
+    # a batch where only one map is dirty, through the whole path
+    import oracle_py
+    mm = __import__("mm3d_pkg").load()
+    G = ctx.estimate_maps_transforms([pts, maps[1]], mm.default_params(descriptor_type="FPFH"))
+    W = oracle.estimate_maps_transforms([pts, maps[1]], oracle_py.default_params(descriptor_type=2))["transforms"]
+    np.testing.assert_allclose(G, W, rtol=0, atol=1e-5)
+
+
 def test_downsample_idempotent_full_size(ctx, synth):
     """Size-independent property at BASELINE scale: voxelising a voxelised cloud at the same leaf keeps it."""
     maps, _ = synth.make_maps(seed=5, n_maps=1, n_points=500_000, size_x=28.0, size_y=20.0, rooms_x=2, rooms_y=2)
@@ -390,6 +417,14 @@ def test_match_small_sets_and_generic_dim(ctx, oracle):
         assert np.array_equal(gp, wp), f"dim {dim}"
         assert_same_bits(gd, wd, f"distances dim {dim}")
     assert ctx.match(np.zeros((0, 33), np.float32), b, 5)[0].shape == (0, 2)
+    # any matching_k: the reference passes it straight to nearestKSearch (k = 20 and a k larger than the target set)
+    s = rng.uniform(0, 100, size=(300, 33)).astype(np.float32)
+    t = rng.uniform(0, 100, size=(260, 33)).astype(np.float32)
+    for k in (17, 20, 300):
+        wp, wd = oracle.match(s, t, k)
+        gp, gd = ctx.match(s, t, k)
+        assert np.array_equal(gp, wp), f"k {k}"
+        assert_same_bits(gd, wd, f"distances k {k}")
 
 
 # ---------------------------------------------------------------- K10 RANSAC

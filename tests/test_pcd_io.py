@@ -69,3 +69,30 @@ def test_pcd_round_trips(tmp_path):
     open(p, "wb").write(hdr2.encode() + b"binary\n" + rows.tobytes())
     assert np.array_equal(back(p).view(np.uint32), pts.view(np.uint32))
     assert subprocess.call([exe, str(tmp_path / "missing.pcd"), str(tmp_path / "o.pcd")]) == 2
+
+
+def test_pcd_corrupt_files_are_rejected(tmp_path):
+    """Truncated / lying headers must fail like an unreadable file (exit 2), not allocate gigabytes or read out of bounds."""
+    exe = str(tmp_path / "pcd_rt")
+    (tmp_path / "rt.cpp").write_text(SRC)
+    subprocess.check_call(["g++", "-O1", "-std=c++17", f"-I{ROOT}/include", f"-I{PKG}/host", "-o", exe, str(tmp_path / "rt.cpp")])
+    n = 64
+    pts = np.arange(n * 4, dtype=np.float32).reshape(n, 4)
+    hdr = ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z rgb\nSIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 1\n"
+           "WIDTH {n}\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS {n}\nDATA ")
+    soa = b"".join(pts[:, k].tobytes() for k in range(4))
+    comp = lzf_literal(soa)
+    cases = {
+        "huge_points.pcd": hdr.format(n=10 ** 12).encode() + b"binary\n" + pts.tobytes(),
+        "truncated_bin.pcd": hdr.format(n=n).encode() + b"binary\n" + pts.tobytes()[:100],
+        "comp_no_sizes.pcd": hdr.format(n=n).encode() + b"binary_compressed\n" + b"\x01\x02",
+        "comp_huge.pcd": hdr.format(n=n).encode() + b"binary_compressed\n" + struct.pack("<II", 0xFFFFFFF0, len(soa)) + comp,
+        "comp_truncated.pcd": hdr.format(n=n).encode() + b"binary_compressed\n" + struct.pack("<II", len(comp), len(soa)) + comp[:50],
+        # a back reference that points before the start of the output buffer
+        "comp_bad_ref.pcd": hdr.format(n=n).encode() + b"binary_compressed\n" + struct.pack("<II", 2, len(soa)) + bytes([0x3F, 0xFF]),
+        "ascii_short.pcd": hdr.format(n=n).encode() + b"ascii\n" + b"1 2 3 4\n",
+    }
+    for name, data in cases.items():
+        p = str(tmp_path / name)
+        open(p, "wb").write(data)
+        assert subprocess.call([exe, p, str(tmp_path / "o.pcd")]) == 2, name
