@@ -193,6 +193,52 @@ int mm3d_downsample_dev(mm3d_ctx* ctx, const void* points_dev, uint64_t n, doubl
 int mm3d_estimate_resident(mm3d_ctx* ctx, const mm3d_maps* maps, const mm3d_params* params, float* out_transforms, int* n_out,
                            float* stage_ms);
 
+/* ---- multi-GPU interface (csrc/dist.cu) -------------------------------------------------------------
+ * estimateMapsTransforms (src/map_merging.cpp:188-275) and composeMaps (:277-305) with the maps spread over several
+ * GPUs: rank r owns the contiguous block of maps mm3d_dist_block(r, world, n_maps) for the per-map stages, features are
+ * exchanged with NCCL, the row-major pair list is dealt out by mm3d_dist_plan, results come back in the reference's pair
+ * order.  The transforms are bit-identical to a single-GPU run.  Two ways to form the ranks: */
+
+/* (1) one process, several GPUs: devices = CUDA device ordinals (NULL / 0 = every visible device).  The returned context
+ * works with every call of this header; mm3d_estimate_maps_transforms and mm3d_compose_maps fan out over all its devices
+ * (one host thread per device, NCCL between them), the other calls run on the first device. */
+int mm3d_create_multi(mm3d_ctx** ctx, const int* devices, int n_devices);
+/* devices behind a context (1 for mm3d_create) */
+int mm3d_device_count(const mm3d_ctx* ctx);
+
+/* (2) one process per GPU: rank 0 fills id (MM3D_COMM_ID_BYTES bytes, an ncclUniqueId) and hands it to every rank through
+ * the launcher's own channel; every rank then creates its communicator on its context's device (collective call). */
+#define MM3D_COMM_ID_BYTES 128
+typedef struct mm3d_comm mm3d_comm;
+int mm3d_comm_id(void* id);
+int mm3d_comm_create(mm3d_ctx* ctx, int rank, int world, const void* id, mm3d_comm** comm);
+void mm3d_comm_destroy(mm3d_comm* comm);
+int mm3d_comm_rank(const mm3d_comm* comm);
+int mm3d_comm_size(const mm3d_comm* comm);
+
+/* the block of maps a rank owns: [first, first + count) */
+int mm3d_dist_block(int rank, int world, int n_maps, int* first, int* count);
+/* the pair list (row-major i < j over maps that have keypoints, src/map_merging.cpp:246-254) and the rank that registers
+ * each pair (longest-processing-time-first on an estimated cost; deterministic, host only).  pairs = int32[n][2] and owner =
+ * int32[n] have room for n_maps (n_maps - 1) / 2 entries; either may be NULL. */
+int mm3d_dist_plan(int n_maps, const int32_t* n_points, const int32_t* n_keypoints, int dim, int world, int32_t* pairs, int32_t* owner,
+                   int* n_pairs);
+
+/* estimateMapsTransforms, collective over comm (comm = NULL: single rank).  clouds / n_points describe ALL n_maps maps; a
+ * rank reads only the host buffers of its own block, the other entries may be NULL.  Every rank receives all transforms. */
+int mm3d_estimate_maps_transforms_dist(mm3d_ctx* ctx, mm3d_comm* comm, int n_maps, const float* const* clouds, const uint64_t* n_points,
+                                       const mm3d_params* params, float* out_transforms, int* n_out);
+/* the same on resident clouds: local_maps = this rank's block (mm3d_maps_upload of exactly those maps).  phase_ms (optional,
+ * 5 floats; synchronises between phases, diagnostic only) = features, feature exchange, pair registration, result exchange, graph. */
+int mm3d_estimate_resident_dist(mm3d_ctx* ctx, mm3d_comm* comm, int n_maps, const mm3d_maps* local_maps, const mm3d_params* params,
+                                float* out_transforms, int* n_out, float* phase_ms);
+/* composeMaps, collective over comm: clouds / transforms = this rank's n_local maps (rank order = map order).  *out = this
+ * rank's slice of the composed map (mm3d_free); the slices concatenated in rank order are exactly mm3d_compose_maps' output. */
+int mm3d_compose_maps_dist(mm3d_ctx* ctx, mm3d_comm* comm, int n_local, const float* const* clouds, const uint64_t* n_points,
+                           int n_transforms, const float* transforms, double resolution, float** out, uint64_t* n_out);
+int mm3d_compose_resident_dist(mm3d_ctx* ctx, mm3d_comm* comm, const mm3d_maps* local_maps, int n_transforms, const float* transforms,
+                               double resolution, float** out, uint64_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,7 +41,11 @@ SYMBOLS = [
     "mm3d_features_export_dev", "mm3d_features_import_dev", "mm3d_features_export_host", "mm3d_features_free",
     "mm3d_register_pairs", "mm3d_estimate_resident", "mm3d_profile_begin", "mm3d_profile_end", "mm3d_sac_ia", "mm3d_knn_stats", "mm3d_compose_shard_begin", "mm3d_compose_shard_size",
     "mm3d_compose_shard_histogram", "mm3d_compose_shard_partition", "mm3d_compose_shard_points", "mm3d_shard_free", "mm3d_downsample_dev",
+    "mm3d_create_multi", "mm3d_device_count", "mm3d_comm_id", "mm3d_comm_create", "mm3d_comm_destroy", "mm3d_comm_rank", "mm3d_comm_size",
+    "mm3d_dist_block", "mm3d_dist_plan", "mm3d_estimate_maps_transforms_dist", "mm3d_estimate_resident_dist", "mm3d_compose_maps_dist",
+    "mm3d_compose_resident_dist",
 ]
+COMM_ID_BYTES = 128
 
 
 class Params(C.Structure):
@@ -85,6 +89,8 @@ def lib():
         L.mm3d_features_count.argtypes = [C.c_void_p]
         L.mm3d_shard_free.argtypes = [C.c_void_p]
         L.mm3d_compose_shard_size.argtypes = [C.c_void_p, u64p]
+        L.mm3d_comm_destroy.argtypes = [C.c_void_p]
+        L.mm3d_device_count.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -121,12 +127,24 @@ def _T_out(buf):
 class Context:
     """One mm3d_ctx: a device plus a stream.  ``stream`` is a raw cudaStream_t (int) or None."""
 
-    def __init__(self, device: int = 0, stream: int | None = None):
+    def __init__(self, device: int = 0, stream: int | None = None, devices=None):
+        """devices: a list of CUDA ordinals (or "all") -> mm3d_create_multi: the high-level calls use all of them."""
         self.L = lib()
         self.h = C.c_void_p()
+        if devices is not None:
+            devs = [] if devices == "all" else [int(d) for d in devices]
+            arr = (C.c_int * max(len(devs), 1))(*devs)
+            rc = self.L.mm3d_create_multi(C.byref(self.h), arr if devs else None, len(devs))
+            if rc != 0:
+                raise MM3DError(f"mm3d_create_multi failed ({rc}) for devices {devices}; libmm3d has no CPU fallback")
+            return
         rc = self.L.mm3d_create(C.byref(self.h), int(device), C.c_void_p(stream) if stream else None)
         if rc != 0:
             raise MM3DError(f"mm3d_create failed ({rc}): no usable CUDA device {device}; libmm3d has no CPU fallback")
+
+    @property
+    def device_count(self) -> int:
+        return int(self.L.mm3d_device_count(self.h))
 
     def close(self):
         if self.h:
@@ -297,6 +315,52 @@ class Context:
         self._check(rc)
         return self._take(out, n.value * 4, np.float32, (-1, 4))
 
+    # ---- multi-GPU interface (one process per GPU) -------------------------------
+    def comm_create(self, rank: int, world: int, comm_id: bytes) -> "Comm":
+        h = C.c_void_p()
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(bytes(comm_id)[:COMM_ID_BYTES].ljust(COMM_ID_BYTES, b"\0"))
+        self._check(self.L.mm3d_comm_create(self.h, int(rank), int(world), buf, C.byref(h)))
+        return Comm(self, h, rank, world)
+
+    def estimate_maps_transforms_dist(self, comm, clouds, params: Params):
+        """clouds: ALL maps of the job (entries outside this rank's block may be None)."""
+        arrs, ptrs, ns = self._cloud_args(clouds)
+        m = len(clouds)
+        out = np.zeros((max(m, 1), 16), np.float32); no = C.c_int()
+        self._check(self.L.mm3d_estimate_maps_transforms_dist(self.h, comm.h if comm else None, m, ptrs, ns, C.byref(params),
+                                                              out.ctypes.data_as(f32p), C.byref(no)))
+        return out[:no.value].reshape(-1, 4, 4).transpose(0, 2, 1).copy()
+
+    def estimate_resident_dist(self, comm, n_maps: int, local_maps: "Maps", params: Params, phases=False):
+        out = np.zeros((max(n_maps, 1), 16), np.float32); no = C.c_int(); ph = np.zeros(5, np.float32)
+        self._check(self.L.mm3d_estimate_resident_dist(self.h, comm.h if comm else None, int(n_maps), local_maps.h, C.byref(params),
+                                                       out.ctypes.data_as(f32p), C.byref(no), ph.ctypes.data_as(f32p) if phases else None))
+        T = out[:no.value].reshape(-1, 4, 4).transpose(0, 2, 1).copy()
+        return (T, dict(zip(DIST_PHASES, ph.tolist()))) if phases else T
+
+    def compose_maps_dist(self, comm, clouds_local, transforms_local, resolution):
+        arrs, ptrs, ns = self._cloud_args(clouds_local)
+        T = np.asarray(transforms_local, np.float32).reshape(-1, 4, 4)
+        Tc = np.ascontiguousarray(T.transpose(0, 2, 1)) if len(T) else np.zeros((1, 16), np.float32)
+        out = f32p(); n = C.c_uint64()
+        rc = self.L.mm3d_compose_maps_dist(self.h, comm.h if comm else None, len(clouds_local), ptrs, ns, len(T), Tc.ctypes.data_as(f32p),
+                                           C.c_double(resolution), C.byref(out), C.byref(n))
+        if rc == -3:
+            raise MM3DError("composeMaps: clouds and transforms size must be the same.")
+        self._check(rc)
+        return self._take(out, n.value * 4, np.float32, (-1, 4))
+
+    def compose_resident_dist(self, comm, local_maps: "Maps", transforms_local, resolution):
+        T = np.asarray(transforms_local, np.float32).reshape(-1, 4, 4)
+        Tc = np.ascontiguousarray(T.transpose(0, 2, 1)) if len(T) else np.zeros((1, 16), np.float32)
+        out = f32p(); n = C.c_uint64()
+        rc = self.L.mm3d_compose_resident_dist(self.h, comm.h if comm else None, local_maps.h, len(T), Tc.ctypes.data_as(f32p),
+                                               C.c_double(resolution), C.byref(out), C.byref(n))
+        if rc == -3:
+            raise MM3DError("composeMaps: clouds and transforms size must be the same.")
+        self._check(rc)
+        return self._take(out, n.value * 4, np.float32, (-1, 4))
+
     # ---- composeMaps sharded over ranks ----------------------------------------
     def compose_shard_begin(self, clouds, transforms):
         arrs, ptrs, ns = self._cloud_args(clouds)
@@ -372,6 +436,47 @@ class Context:
         self._check(self.L.mm3d_register_pairs(self.h, feats.h, P, ij.ctypes.data_as(i32p), C.byref(params), T.ctypes.data_as(f32p),
                                                conf.ctypes.data_as(f64p), stats.ctypes.data_as(i32p)))
         return T[:P].reshape(-1, 4, 4).transpose(0, 2, 1).copy(), conf[:P].copy(), stats[:P].copy()
+
+
+DIST_PHASES = ["features", "feature exchange", "pair registration", "result exchange", "graph"]
+
+
+def comm_id() -> bytes:
+    """rank 0: an ncclUniqueId to hand to every rank (mm3d_comm_id)."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    rc = lib().mm3d_comm_id(buf)
+    if rc != 0:
+        raise MM3DError(f"mm3d_comm_id failed ({rc}): NCCL is not available")
+    return bytes(buf)
+
+
+def dist_block(rank: int, world: int, n_maps: int):
+    first = C.c_int(); count = C.c_int()
+    if lib().mm3d_dist_block(int(rank), int(world), int(n_maps), C.byref(first), C.byref(count)) != 0:
+        raise MM3DError("mm3d_dist_block: bad arguments")
+    return first.value, count.value
+
+
+def dist_plan(n_points, n_keypoints, dim: int, world: int):
+    """(pairs int32[n, 2], owner int32[n]): the row-major pair list and the rank that registers each pair."""
+    npt = np.ascontiguousarray(n_points, np.int32); nk = np.ascontiguousarray(n_keypoints, np.int32)
+    m = len(npt)
+    cap = max(m * (m - 1) // 2, 1)
+    pairs = np.zeros((cap, 2), np.int32); owner = np.zeros(cap, np.int32); n = C.c_int()
+    if lib().mm3d_dist_plan(m, npt.ctypes.data_as(i32p), nk.ctypes.data_as(i32p), int(dim), int(world), pairs.ctypes.data_as(i32p),
+                            owner.ctypes.data_as(i32p), C.byref(n)) != 0:
+        raise MM3DError("mm3d_dist_plan: bad arguments")
+    return pairs[:n.value].copy(), owner[:n.value].copy()
+
+
+class Comm:
+    def __init__(self, ctx, h, rank, world):
+        self.ctx, self.h, self.rank, self.world = ctx, h, rank, world
+
+    def free(self):
+        if self.h:
+            self.ctx.L.mm3d_comm_destroy(self.h)
+            self.h = C.c_void_p()
 
 
 def global_transforms(st, transforms, conf, thr, debug=False):

@@ -9,30 +9,9 @@
 
 #include "../../include/mm3d.h"
 #include "mm3d_internal.cuh"
+#include "pipeline.cuh"
 
 using namespace mm3d;
-
-struct mm3d_ctx {
-  Ctx c;
-};
-
-struct mm3d_maps {
-  std::vector<DCloud> clouds;
-};
-
-struct mm3d_shard {
-  DCloud cloud;  // this rank's transformed points in (map, point) order
-};
-
-struct MapFeat {
-  DCloud cloud;     // downsampled + outlier-filtered cloud (clouds_resized[i])
-  DCloud keypoints;
-  DBuf<float> desc;
-};
-struct mm3d_features {
-  std::vector<MapFeat> maps;
-  int dim = 33;
-};
 
 namespace {
 
@@ -69,26 +48,6 @@ struct StageTimer {
   }
 };
 
-void to_colmajor(const float* rm, float* cm)
-{
-  for (int r = 0; r < 4; ++r)
-    for (int c = 0; c < 4; ++c) cm[c * 4 + r] = rm[r * 4 + c];
-}
-void from_colmajor(const float* cm, float* rm)
-{
-  for (int r = 0; r < 4; ++r)
-    for (int c = 0; c < 4; ++c) rm[r * 4 + c] = cm[c * 4 + r];
-}
-
-DCloud upload_cloud(Ctx& c, const float* pts, uint64_t n)
-{
-  DCloud d;
-  d.n = (pts ? (int)n : 0);
-  d.pts.alloc(c, d.n);
-  if (d.n) MM_CUDA(cudaMemcpyAsync(d.pts.p, pts, (size_t)d.n * sizeof(float4), cudaMemcpyHostToDevice, c.stream));
-  return d;
-}
-
 template <typename T>
 T* host_copy(Ctx& c, const T* dev, size_t count)
 {
@@ -108,6 +67,30 @@ void check_supported(const mm3d_params& p)
   if (p.keypoint_type != MM3D_KP_SIFT && p.keypoint_type != MM3D_KP_HARRIS) throw UnsupportedError("unsupported: unknown keypoint_type");
   if (p.descriptor_type < MM3D_DESC_PFH || p.descriptor_type > MM3D_DESC_SC3D) throw UnsupportedError("unsupported: unknown descriptor_type");
   if (p.estimation_method != MM3D_EST_MATCHING && p.estimation_method != MM3D_EST_SAC_IA) throw UnsupportedError("unsupported: unknown estimation_method");
+}
+
+}  // namespace
+
+namespace mm3d {
+
+void to_colmajor(const float* rm, float* cm)
+{
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) cm[c * 4 + r] = rm[r * 4 + c];
+}
+void from_colmajor(const float* cm, float* rm)
+{
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) rm[r * 4 + c] = cm[c * 4 + r];
+}
+
+DCloud upload_cloud(Ctx& c, const float* pts, uint64_t n)
+{
+  DCloud d;
+  d.n = (pts ? (int)n : 0);
+  d.pts.alloc(c, d.n);
+  if (d.n) MM_CUDA(cudaMemcpyAsync(d.pts.p, pts, (size_t)d.n * sizeof(float4), cudaMemcpyHostToDevice, c.stream));
+  return d;
 }
 
 // src/map_merging.cpp:212-242, stage-major over all maps
@@ -174,14 +157,8 @@ void compute_features(Ctx& c, const std::vector<CloudView>& raw, const mm3d_para
   c.sync();
 }
 
-struct PairOut {
-  float T[16];  // row-major
-  double confidence;
-  int n_corr, n_inliers, icp_iterations, icp_converged;
-};
-
 // src/map_merging.cpp:256-269 + src/matching.cpp:223-257 for a list of pairs
-void register_pairs(Ctx& c, const std::vector<MapFeat>& f, int dim, const std::vector<PairJob>& jobs, const mm3d_params& p,
+void register_pairs(Ctx& c, const std::vector<FeatView>& f, int dim, const std::vector<PairJob>& jobs, const mm3d_params& p,
                     std::vector<PairOut>& out, float* stage_ms)
 {
   check_supported(p);
@@ -194,9 +171,9 @@ void register_pairs(Ctx& c, const std::vector<MapFeat>& f, int dim, const std::v
   std::vector<const float*> desc(M);
   std::vector<int> nk(M);
   for (int m = 0; m < M; ++m) {
-    clouds[m] = f[m].cloud.view();
-    kps[m] = f[m].keypoints.view();
-    desc[m] = f[m].desc.p;
+    clouds[m] = f[m].cloud;
+    kps[m] = f[m].keypoints;
+    desc[m] = f[m].desc;
     nk[m] = f[m].keypoints.n;
   }
   std::vector<DCorr> corr(P);
@@ -274,7 +251,6 @@ void register_pairs(Ctx& c, const std::vector<MapFeat>& f, int dim, const std::v
   c.sync();
 }
 
-// returns number of transforms written
 int desc_dim(const mm3d_params& p)
 {
   switch (p.descriptor_type) {
@@ -287,6 +263,18 @@ int desc_dim(const mm3d_params& p)
   }
 }
 
+std::vector<FeatView> feat_views(const std::vector<MapFeat>& f)
+{
+  std::vector<FeatView> v(f.size());
+  for (size_t m = 0; m < f.size(); ++m) v[m] = FeatView{f[m].cloud.view(), f[m].keypoints.view(), f[m].desc.p};
+  return v;
+}
+
+}  // namespace mm3d
+
+namespace {
+
+// returns number of transforms written
 int estimate_from_views(Ctx& c, const std::vector<CloudView>& raw, const mm3d_params& p, float* out_transforms, float* stage_ms)
 {
   const int M = (int)raw.size();
@@ -303,7 +291,7 @@ int estimate_from_views(Ctx& c, const std::vector<CloudView>& raw, const mm3d_pa
     for (int j = i + 1; j < M; ++j)
       if (f[i].keypoints.n > 0 && f[j].keypoints.n > 0) jobs.push_back(PairJob{i, j});
   std::vector<PairOut> po;
-  register_pairs(c, f, desc_dim(p), jobs, p, po, stage_ms);
+  register_pairs(c, feat_views(f), desc_dim(p), jobs, p, po, stage_ms);
   std::vector<HostEstimate> est(jobs.size());
   for (size_t k = 0; k < jobs.size(); ++k) {
     est[k].source_idx = (size_t)jobs[k].a;
@@ -419,6 +407,10 @@ int mm3d_estimate_maps_transforms(mm3d_ctx* ctx, int n_maps, const float* const*
     return MM3D_OK;
   }
   MM_TRY(ctx)
+  if (ctx->team) {  // mm3d_create_multi: maps and pairs sharded over the context's devices (dist.cu)
+    *n_out = team_estimate(ctx, n_maps, clouds, n_points, *params, out_transforms);
+    return MM3D_OK;
+  }
   std::vector<DCloud> d(n_maps);
   std::vector<CloudView> v(n_maps);
   for (int m = 0; m < n_maps; ++m) {
@@ -450,6 +442,10 @@ int mm3d_compose_maps(mm3d_ctx* ctx, int n_maps, const float* const* clouds, con
     return MM3D_OK;
   }
   MM_TRY(ctx)
+  if (ctx->team) {
+    team_compose(ctx, n_maps, clouds, n_points, transforms, resolution, out, n_out);
+    return MM3D_OK;
+  }
   std::vector<DCloud> d;
   std::vector<CloudView> v;
   std::vector<std::vector<float>> tr;
@@ -1005,7 +1001,7 @@ int mm3d_register_pairs(mm3d_ctx* ctx, const mm3d_features* f, int n_pairs, cons
       throw std::runtime_error("register_pairs: pair index out of range");
   }
   std::vector<PairOut> po;
-  register_pairs(c, f->maps, f->dim, jobs, *params, po, nullptr);
+  register_pairs(c, feat_views(f->maps), f->dim, jobs, *params, po, nullptr);
   for (int k = 0; k < n_pairs; ++k) {
     to_colmajor(po[k].T, transforms + 16 * k);
     confidences[k] = po[k].confidence;

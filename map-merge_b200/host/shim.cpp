@@ -28,10 +28,27 @@ mm3d_ctx* context()
   };
   static thread_local Holder h;
   if (!h.c) {
-    int dev = 0;
-    if (const char* e = std::getenv("MM3D_DEVICE")) dev = std::atoi(e);
-    if (mm3d_create(&h.c, dev, nullptr) != MM3D_OK)
-      throw std::runtime_error("libmm3d: no usable CUDA device (the registration path has no CPU fallback)");
+    // MM3D_DEVICE=n: that device only.  MM3D_DEVICES=0,2,3: those devices.  Neither: every visible device —
+    // estimateMapsTransforms and composeMaps shard their maps and pairs over all of them (include/mm3d.h, multi-GPU interface).
+    int rc;
+    if (const char* e = std::getenv("MM3D_DEVICE")) {
+      rc = mm3d_create(&h.c, std::atoi(e), nullptr);
+    } else {
+      std::vector<int> devs;
+      if (const char* l = std::getenv("MM3D_DEVICES")) {
+        const char* p = l;
+        while (*p) {
+          char* end = nullptr;
+          const long v = std::strtol(p, &end, 10);
+          if (end == p) break;
+          devs.push_back((int)v);
+          p = (*end == ',') ? end + 1 : end;
+        }
+      }
+      rc = mm3d_create_multi(&h.c, devs.empty() ? nullptr : devs.data(), (int)devs.size());
+      if (rc == MM3D_ERR_UNSUPPORTED) rc = mm3d_create(&h.c, devs.empty() ? 0 : devs[0], nullptr);  // no NCCL on this machine: one GPU
+    }
+    if (rc != MM3D_OK) throw std::runtime_error("libmm3d: no usable CUDA device (the registration path has no CPU fallback)");
   }
   return h.c;
 }

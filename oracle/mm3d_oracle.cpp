@@ -39,6 +39,9 @@
 //
 // Build: see oracle/Makefile (g++ -O2 -ffp-contract=off, no -march, no deps).
 #include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <cfloat>
 #include <chrono>
 #include <climits>
@@ -449,9 +452,15 @@ static Cloud radius_outlier_removal(const Cloud& in, double radius, int min_nb, 
   Cloud out;
   if (kept) kept->clear();
   if (counts) counts->assign(in.size(), 0);
-  for (size_t i = 0; i < in.size(); ++i) {
+  std::vector<int> cnt(in.size(), 0);
+#pragma omp parallel for schedule(dynamic, 512)
+  for (long long i = 0; i < (long long)in.size(); ++i) {
     int k = 0;
     g.for_radius(in[i].x, in[i].y, in[i].z, (float)radius, r2, [&](int, float) { ++k; });
+    cnt[i] = k;
+  }
+  for (size_t i = 0; i < in.size(); ++i) {
+    const int k = cnt[i];
     if (counts) (*counts)[i] = k;
     if (k <= min_nb) continue;  // "k <= min_pts_radius_" -> outlier
     out.push_back(in[i]);
@@ -590,10 +599,13 @@ static Normals surface_normals(const Cloud& in, double radius)
   Grid g;
   g.build(in, (float)radius);
   Normals out(in.size());
+  const float nanv = std::numeric_limits<float>::quiet_NaN();
+#pragma omp parallel
+  {
   std::vector<int> idx;
   std::vector<float> dist;
-  const float nanv = std::numeric_limits<float>::quiet_NaN();
-  for (size_t i = 0; i < in.size(); ++i) {
+#pragma omp for schedule(dynamic, 512)
+  for (long long i = 0; i < (long long)in.size(); ++i) {
     g.radius_sorted(in[i].x, in[i].y, in[i].z, radius, idx, dist);
     if (idx.size() < 3) {
       out[i].nx = out[i].ny = out[i].nz = out[i].curv = nanv;
@@ -611,6 +623,7 @@ static Normals surface_normals(const Cloud& in, double radius)
     const float cos_theta = (vx * nx + vy * ny + vz * nz);
     if (cos_theta < 0) { nx *= -1; ny *= -1; nz *= -1; }
     out[i].nx = nx; out[i].ny = ny; out[i].nz = nz; out[i].curv = curv;
+  }
   }
   return out;
 }
@@ -657,11 +670,14 @@ static Cloud sift_keypoints(const Cloud& input, float min_scale, int nr_octaves,
     const int nd = nscales - 1;
     std::vector<float> dog(n * nd);
     const float max_radius = 3.0f * scales.back();
-    std::vector<int> nn_idx;
-    std::vector<float> nn_dist;
     std::vector<float> sigma_sqr(nscales);
     for (int i = 0; i < nscales; ++i) sigma_sqr[i] = powf(scales[i], 2.0f);
-    for (size_t ip = 0; ip < n; ++ip) {
+#pragma omp parallel
+    {
+    std::vector<int> nn_idx;
+    std::vector<float> nn_dist;
+#pragma omp for schedule(dynamic, 256)
+    for (long long ip = 0; ip < (long long)n; ++ip) {
       tree.radius_sorted(cloud[ip].x, cloud[ip].y, cloud[ip].z, (double)max_radius, nn_idx, nn_dist);
       if (order_mode == 1) {
         std::vector<std::pair<float, int>> tmp(nn_idx.size());
@@ -699,22 +715,32 @@ static Cloud sift_keypoints(const Cloud& input, float min_scale, int nr_octaves,
         if (i_scale > 0) dog[ip * nd + (i_scale - 1)] = filter_response - previous_filter_response;
       }
     }
+    }
     if (dbg && i_octave == 0) dbg->dog = dog;
-    // findScaleSpaceExtrema
+    // findScaleSpaceExtrema (the per-point min / max tables in parallel, the emission loop below in point order)
     const int k = 25;
+    std::vector<float> all_min(n * nd), all_max(n * nd);
+#pragma omp parallel
+    {
     std::vector<std::pair<float, int>> nn;
-    std::vector<float> min_val(nd), max_val(nd);
-    for (size_t ip = 0; ip < n; ++ip) {
+#pragma omp for schedule(dynamic, 256)
+    for (long long ip = 0; ip < (long long)n; ++ip) {
       tree.knn(cloud[ip].x, cloud[ip].y, cloud[ip].z, k, nn);
       for (int is = 0; is < nd; ++is) {
-        min_val[is] = FLT_MAX;
-        max_val[is] = -FLT_MAX;
+        float mnv = FLT_MAX, mxv = -FLT_MAX;
         for (size_t t = 0; t < nn.size(); ++t) {
           const float d = dog[(size_t)nn[t].second * nd + is];
-          min_val[is] = std::min(min_val[is], d);
-          max_val[is] = std::max(max_val[is], d);
+          mnv = std::min(mnv, d);
+          mxv = std::max(mxv, d);
         }
+        all_min[ip * nd + is] = mnv;
+        all_max[ip * nd + is] = mxv;
       }
+    }
+    }
+    for (size_t ip = 0; ip < n; ++ip) {
+      const float* min_val = &all_min[ip * nd];
+      const float* max_val = &all_max[ip * nd];
       for (int is = 1; is < nd - 1; ++is) {
         const float val = dog[ip * nd + is];
         if (std::fabs(val) >= min_contrast) {
@@ -929,13 +955,24 @@ static std::vector<float> fpfh_descriptors(const Cloud& surface, const Normals& 
   std::vector<float> nn_dist;
   // computeSPFHSignatures: union of the keypoints' neighbours
   std::vector<char> need(N, 0);
-  for (size_t k = 0; k < K; ++k) {
+#pragma omp parallel
+  {
+  std::vector<int> nn_idx;
+  std::vector<float> nn_dist;
+#pragma omp for schedule(dynamic, 64)
+  for (long long k = 0; k < (long long)K; ++k) {
     tree.radius_sorted(keypoints[k].x, keypoints[k].y, keypoints[k].z, radius, nn_idx, nn_dist);
-    for (int i : nn_idx) need[i] = 1;
+    for (int i : nn_idx) need[i] = 1;  // every writer stores the same value
+  }
   }
   std::vector<float> hist(N * 33, 0.0f);  // rows at the surface index (lookup = identity on needed rows)
   const float d_pi = 1.0f / (2.0f * (float)M_PI);
-  for (size_t p = 0; p < N; ++p) {
+#pragma omp parallel
+  {
+  std::vector<int> nn_idx;
+  std::vector<float> nn_dist;
+#pragma omp for schedule(dynamic, 256)
+  for (long long p = 0; p < (long long)N; ++p) {
     if (!need[p]) continue;
     tree.radius_sorted(surface[p].x, surface[p].y, surface[p].z, radius, nn_idx, nn_dist);
     if (nn_idx.empty()) continue;
@@ -952,6 +989,7 @@ static std::vector<float> fpfh_descriptors(const Cloud& surface, const Normals& 
       hi = (int)std::floor(NB * ((f3 + 1.0) * 0.5));
       h[2 * NB + clampbin(hi, NB)] += hist_incr;
     }
+  }
   }
   if (spfh_dbg) *spfh_dbg = hist;
   std::vector<float> desc;
@@ -1607,8 +1645,11 @@ static void knn_bruteforce(const float* A, size_t na, const float* B, size_t nb,
   // for each row of A: k nearest rows of B, sorted by (distance, index)
   idx.assign(na * k, -1);
   dist.assign(na * k, 0.f);
+#pragma omp parallel
+  {
   std::vector<std::pair<float, int>> best;
-  for (size_t i = 0; i < na; ++i) {
+#pragma omp for schedule(dynamic, 32)
+  for (long long i = 0; i < (long long)na; ++i) {
     best.clear();
     const float* a = A + i * D;
     for (size_t j = 0; j < nb; ++j) {
@@ -1629,6 +1670,7 @@ static void knn_bruteforce(const float* A, size_t na, const float* B, size_t nb,
       idx[i * k + t] = best[t].second;
       dist[i * k + t] = best[t].first;
     }
+  }
   }
 }
 
@@ -2022,7 +2064,9 @@ static Mat4 icp_refine(const Cloud& source, const Cloud& target, const Mat4& ini
   const double translation_threshold = transformation_epsilon;
   do {
     long long cnt = 0, Sp[3] = {0, 0, 0}, Sq[3] = {0, 0, 0}, Sqp[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, Sd = 0;
-    for (size_t i = 0; i < source.size(); ++i) {
+    // integer (fixed-point) sums: order-free, so the loop may run on all host threads
+#pragma omp parallel for schedule(dynamic, 1024) reduction(+ : cnt, Sp[:3], Sq[:3], Sqp[:9], Sd)
+    for (long long i = 0; i < (long long)source.size(); ++i) {
       int j;
       float dd;
       const float px = pts[i * 3], py = pts[i * 3 + 1], pz = pts[i * 3 + 2];
@@ -2100,7 +2144,8 @@ static double transform_score(const Cloud& source, const Cloud& target, const Ma
   Grid tree;
   tree.build(target, (float)std::max(std::sqrt(std::max(max_range, 0.0)) * 0.25, 1e-3));
   long long Sd = 0, nr = 0;
-  for (size_t i = 0; i < source.size(); ++i) {
+#pragma omp parallel for schedule(dynamic, 1024) reduction(+ : Sd, nr)
+  for (long long i = 0; i < (long long)source.size(); ++i) {
     float x, y, z;
     xform(t, source[i].x, source[i].y, source[i].z, x, y, z);
     int j;
@@ -2397,6 +2442,19 @@ static Mat4 from_colmajor(const float* in)
 extern "C" {
 
 void orc_free(void* p) { free(p); }
+
+// host threads the per-point loops use (OpenMP); results do not depend on it.  n <= 0: all cores.  Returns the setting.
+int orc_set_threads(int n)
+{
+#ifdef _OPENMP
+  if (n <= 0) n = omp_get_num_procs();
+  omp_set_num_threads(n);
+  return n;
+#else
+  (void)n;
+  return 1;
+#endif
+}
 
 int orc_uses_libm()
 {

@@ -82,6 +82,11 @@ class Oracle:
     def _free(self, p):
         self.lib.orc_free(C.cast(p, C.c_void_p))
 
+    def set_threads(self, n: int = 0) -> int:
+        """Host threads for the per-point loops (OpenMP; 0 = all cores).  Results do not depend on it.  Returns the setting
+        (1 when the checker was built without OpenMP)."""
+        return int(self.lib.orc_set_threads(int(n)))
+
     # -- stages -----------------------------------------------------------
     def downsample(self, pts, resolution, with_keys=False):
         a, ap = _f(pts)
