@@ -115,6 +115,10 @@ int mm3d_descriptors(mm3d_ctx* ctx, const float* pts, uint64_t n, const float* n
 /* findFeatureCorrespondences (src/matching.cpp:96-108): pairs = int32[nc][2] (source, target) */
 int mm3d_match(mm3d_ctx* ctx, const float* desc_src, uint64_t n_src, const float* desc_tgt, uint64_t n_tgt, int dim, uint64_t k,
                int32_t** pairs, float** distances, uint64_t* n_corr);
+/* the k-nearest-neighbour search inside findFeatureCorrespondences (src/matching.cpp:45-60, pcl::search::KdTree<DescriptorT>::
+ * nearestKSearch under flann::L2_Simple): for every row of a, the k nearest rows of b sorted by (distance, index);
+ * idx = int32[na][k], dist = float[na][k] (squared L2), k is clamped to nb; unused slots hold -1 / 0. */
+int mm3d_knn(mm3d_ctx* ctx, const float* a, uint64_t na, const float* b, uint64_t nb, int dim, uint64_t k, int32_t* idx, float* dist);
 /* estimateTransformFromCorrespondences (src/matching.cpp:110-140); inliers = positions in pairs.
  * dbg (optional, 2 ints) = RANSAC iterations, best inlier count; dbg_d (optional) = sample distance threshold */
 int mm3d_ransac(mm3d_ctx* ctx, const float* kp_src, uint64_t n_src, const float* kp_tgt, uint64_t n_tgt, const int32_t* pairs,

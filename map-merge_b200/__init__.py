@@ -41,7 +41,7 @@ SYMBOLS = [
     "mm3d_features_export_dev", "mm3d_features_import_dev", "mm3d_features_export_host", "mm3d_features_free",
     "mm3d_register_pairs", "mm3d_estimate_resident", "mm3d_profile_begin", "mm3d_profile_end", "mm3d_sac_ia", "mm3d_knn_stats", "mm3d_compose_shard_begin", "mm3d_compose_shard_size",
     "mm3d_compose_shard_histogram", "mm3d_compose_shard_partition", "mm3d_compose_shard_points", "mm3d_shard_free", "mm3d_downsample_dev",
-    "mm3d_create_multi", "mm3d_device_count", "mm3d_comm_id", "mm3d_comm_create", "mm3d_comm_destroy", "mm3d_comm_rank", "mm3d_comm_size",
+    "mm3d_knn", "mm3d_create_multi", "mm3d_device_count", "mm3d_comm_id", "mm3d_comm_create", "mm3d_comm_destroy", "mm3d_comm_rank", "mm3d_comm_size",
     "mm3d_dist_block", "mm3d_dist_plan", "mm3d_estimate_maps_transforms_dist", "mm3d_estimate_resident_dist", "mm3d_compose_maps_dist",
     "mm3d_compose_resident_dist",
 ]
@@ -246,6 +246,15 @@ class Context:
         self._check(self.L.mm3d_match(self.h, ap, C.c_uint64(len(a)), bp, C.c_uint64(len(b)), dim, C.c_uint64(k), C.byref(pairs),
                                       C.byref(dist), C.byref(nc)))
         return self._take(pairs, nc.value * 2, np.int32, (-1, 2)), self._take(dist, nc.value, np.float32)
+
+    def knn(self, a, b, k=5):
+        """(idx int32[na, k], dist float32[na, k]): per row of a, its k nearest rows of b by (squared L2, index)."""
+        a, ap = _f(a); b, bp = _f(b)
+        dim = a.shape[1] if a.ndim == 2 and a.size else (b.shape[1] if b.ndim == 2 and b.size else 33)
+        idx = np.full((max(len(a), 1), int(k)), -1, np.int32); dist = np.zeros((max(len(a), 1), int(k)), np.float32)
+        self._check(self.L.mm3d_knn(self.h, ap, C.c_uint64(len(a)), bp, C.c_uint64(len(b)), dim, C.c_uint64(int(k)), idx.ctypes.data_as(i32p),
+                                    dist.ctypes.data_as(f32p)))
+        return idx[:len(a)], dist[:len(a)]
 
     def ransac(self, kps, kpt, pairs, inlier_threshold):
         s, sp = _f(kps, 4); t, tp = _f(kpt, 4)

@@ -608,6 +608,31 @@ int mm3d_match(mm3d_ctx* ctx, const float* desc_src, uint64_t n_src, const float
   MM_CATCH
 }
 
+int mm3d_knn(mm3d_ctx* ctx, const float* a, uint64_t na, const float* b, uint64_t nb, int dim, uint64_t k, int32_t* idx, float* dist)
+{
+  if (!idx || !dist || dim <= 0) return MM3D_ERR_ARG;
+  MM_TRY(ctx)
+  const int kk = (int)std::min<uint64_t>(k, nb);
+  if (na == 0 || kk == 0) return MM3D_OK;
+  DBuf<float> da(c, na * dim), db(c, nb * dim);
+  da.upload(c, a, na * dim);
+  db.upload(c, b, nb * dim);
+  DBuf<int> di(c, na * kk);
+  DBuf<float> dd(c, na * kk);
+  knn_problems(c, {da.p, db.p}, {(int)na, (int)nb}, dim, {KnnProblem{0, 1, (int)na, kk, di.p, dd.p}});
+  std::vector<int> hi(na * kk);
+  std::vector<float> hd(na * kk);
+  di.download(c, hi.data(), hi.size());
+  dd.download(c, hd.data(), hd.size());
+  c.sync();
+  for (uint64_t r = 0; r < na; ++r)
+    for (uint64_t t = 0; t < k; ++t) {
+      idx[r * k + t] = t < (uint64_t)kk ? hi[r * kk + t] : -1;
+      dist[r * k + t] = t < (uint64_t)kk ? hd[r * kk + t] : 0.f;
+    }
+  MM_CATCH
+}
+
 int mm3d_ransac(mm3d_ctx* ctx, const float* kp_src, uint64_t n_src, const float* kp_tgt, uint64_t n_tgt, const int32_t* pairs,
                 uint64_t n_corr, double inlier_threshold, float* transform, int32_t** inliers, uint64_t* n_inliers, int32_t* dbg,
                 double* dbg_d, float* best_model)

@@ -629,6 +629,51 @@ __global__ void __launch_bounds__(128) sac_hypothesis_kernel(const SacJob* __res
 
 }  // namespace
 
+// Exact k-NN for a list of (query map, target map) problems: per row of desc[a] (the first na rows), the k nearest rows of
+// desc[b], sorted by (distance, index); k <= number of rows of b.
+//   * 33-dimensional descriptors (FPFH, the BASELINE configs): tcgen05 distance GEMM as a filter + exact FP32 re-rank
+//     (knn_tc.cu) — bit-identical to the FP32 scan and faster;
+//   * other dimensions default to the FP32 scan kernels; any k above 16 to the any-k fallback.
+// MM3D_KNN=tc forces the tensor-core path for every dimension, MM3D_KNN=exact the scan.
+void knn_problems(Ctx& c, const std::vector<const float*>& desc, const std::vector<int>& nk, int dim, const std::vector<KnnProblem>& probs)
+{
+  if (probs.empty()) return;
+  std::vector<KnnJob> kj;
+  int max_rows = 0, kmax = 0;
+  bool uniform_k = true;
+  for (const KnnProblem& q : probs) {
+    if (q.na <= 0) continue;
+    kj.push_back(KnnJob{desc[q.a], q.na, desc[q.b], nk[q.b], q.k, q.idx, q.dist});
+    max_rows = std::max(max_rows, q.na);
+    kmax = std::max(kmax, q.k);
+    if (q.k != probs[0].k) uniform_k = false;
+  }
+  if (kj.empty() || max_rows == 0) return;
+  const char* knn_env = std::getenv("MM3D_KNN");
+  const std::string knn_mode = knn_env ? knn_env : "";
+  const bool k_fits = kmax <= KMAX;  // == KMAXTC
+  const bool use_tc = k_fits && (knn_mode == "tc" || (knn_mode != "exact" && dim == 33));
+  if (use_tc) {
+    knn_tc_batch(c, desc, nk, dim, probs);
+    return;
+  }
+  DBuf<KnnJob> dkj = to_device(c, kj);
+  { double b = 0; for (const KnnJob& q : kj) b += 4.0 * dim * ((double)q.na + q.nb) + 8.0 * q.k * q.na; MM_BYTES(c, b); }
+  const unsigned nj = (unsigned)kj.size();
+  if (!k_fits) {
+    MM_LAUNCH(c, knn_anyk_kernel, dim3((max_rows + 127) / 128, nj), 128, 0, dkj.p, dim);
+  } else if (dim == 33 && uniform_k && (kmax == 5 || kmax == 1 || kmax == 8 || kmax == 10)) {
+    // the register kernels need one k for the whole batch (k is clamped per problem only when a set is smaller than k)
+    const dim3 grid((max_rows + 127) / 128, nj);
+    if (kmax == 5) MM_LAUNCH(c, (knn_small_kernel<33, 5>), grid, 128, 0, dkj.p);
+    else if (kmax == 1) MM_LAUNCH(c, (knn_small_kernel<33, 1>), grid, 128, 0, dkj.p);
+    else if (kmax == 8) MM_LAUNCH(c, (knn_small_kernel<33, 8>), grid, 128, 0, dkj.p);
+    else MM_LAUNCH(c, (knn_small_kernel<33, 10>), grid, 128, 0, dkj.p);
+  } else {
+    MM_LAUNCH(c, knn_generic_kernel, dim3((max_rows + 63) / 64, nj), 128, 0, dkj.p, dim);
+  }
+}
+
 void match_batch(Ctx& c, const std::vector<const float*>& desc, const std::vector<int>& nk, int dim, const std::vector<PairJob>& jobs,
                  size_t k_in, std::vector<DCorr>& corr)
 {
@@ -654,43 +699,13 @@ void match_batch(Ctx& c, const std::vector<const float*>& desc, const std::vecto
     max_rows = std::max(max_rows, std::max(kj[2 * p].na, kj[2 * p + 1].na));
     max_ns = std::max(max_ns, ns);
   }
-  DBuf<KnnJob> dkj = to_device(c, kj);
-  // 33-dimensional descriptors (FPFH, the BASELINE configs): tcgen05 distance GEMM as a filter + exact re-rank, tie-heavy
-  // rows handed to an exact scan (knn_tc.cu) — bit-identical to the FP32 scan below and faster (config 3: 197 vs 294 ms).
-  // Other dimensions default to the scan (the filter's exact evaluations still run in the epilogue there).
-  // MM3D_KNN=tc forces the tensor-core path for every dimension, MM3D_KNN=exact the scan.
-  const char* knn_env = std::getenv("MM3D_KNN");
-  const std::string knn_mode = knn_env ? knn_env : "";
-  bool k_fits = true;
-  for (const KnnJob& q : kj)
-    if (q.na > 0 && q.k > 16) k_fits = false;  // KMAXTC
-  const bool use_tc = k_fits && (knn_mode == "tc" || (knn_mode != "exact" && dim == 33));
-  if (max_rows > 0 && use_tc) {
-    std::vector<KnnProblem> probs;
-    for (int p = 0; p < P; ++p) {
-      const int a = jobs[p].a, b = jobs[p].b;
-      if (kj[2 * p].na > 0) probs.push_back(KnnProblem{a, b, kj[2 * p].na, kj[2 * p].k, kj[2 * p].idx, kj[2 * p].dist});
-      if (kj[2 * p + 1].na > 0) probs.push_back(KnnProblem{b, a, kj[2 * p + 1].na, kj[2 * p + 1].k, kj[2 * p + 1].idx, kj[2 * p + 1].dist});
-    }
-    knn_tc_batch(c, desc, nk, dim, probs);
-  } else if (max_rows > 0 && !k_fits) {
-    MM_LAUNCH(c, knn_anyk_kernel, dim3((max_rows + 127) / 128, 2 * P), 128, 0, dkj.p, dim);
-  } else if (max_rows > 0) {
-    // the register kernel needs one k for the whole batch (k is clamped per job only when a set is smaller than k)
-    bool uniform_k = true;
-    for (const KnnJob& q : kj)
-      if (q.na > 0 && q.k != (int)k_in) uniform_k = false;
-    if (dim == 33 && uniform_k && (k_in == 5 || k_in == 1 || k_in == 8)) {
-      { double b = 0; for (const KnnJob& q : kj) b += 4.0 * dim * ((double)q.na + q.nb) + 8.0 * q.k * q.na; MM_BYTES(c, b); }
-      const dim3 grid((max_rows + 127) / 128, 2 * P);
-      if (k_in == 5) MM_LAUNCH(c, (knn_small_kernel<33, 5>), grid, 128, 0, dkj.p);
-      else if (k_in == 1) MM_LAUNCH(c, (knn_small_kernel<33, 1>), grid, 128, 0, dkj.p);
-      else MM_LAUNCH(c, (knn_small_kernel<33, 8>), grid, 128, 0, dkj.p);
-    } else {
-      { double b = 0; for (const KnnJob& q : kj) b += 4.0 * dim * ((double)q.na + q.nb) + 8.0 * q.k * q.na; MM_BYTES(c, b); }
-      MM_LAUNCH(c, knn_generic_kernel, dim3((max_rows + 63) / 64, 2 * P), 128, 0, dkj.p, dim);
-    }
+  std::vector<KnnProblem> probs;
+  for (int p = 0; p < P; ++p) {
+    const int a = jobs[p].a, b = jobs[p].b;
+    if (kj[2 * p].na > 0) probs.push_back(KnnProblem{a, b, kj[2 * p].na, kj[2 * p].k, kj[2 * p].idx, kj[2 * p].dist});
+    if (kj[2 * p + 1].na > 0) probs.push_back(KnnProblem{b, a, kj[2 * p + 1].na, kj[2 * p + 1].k, kj[2 * p + 1].idx, kj[2 * p + 1].dist});
   }
+  knn_problems(c, desc, nk, dim, probs);
   std::vector<int> nss(P);
   for (int p = 0; p < P; ++p) nss[p] = (k_in > 0 && nk[jobs[p].b] > 0) ? nk[jobs[p].a] : 0;
   std::vector<Seg> segs(P);

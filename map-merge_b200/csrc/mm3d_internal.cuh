@@ -584,6 +584,8 @@ struct KnnProblem {
   float* dist;  // na x k
 };
 void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vector<int>& n_rows, int D, const std::vector<KnnProblem>& probs);
+// matching.cu: picks the tensor-core filter or an exact FP32 scan per descriptor width / k / MM3D_KNN
+void knn_problems(Ctx& c, const std::vector<const float*>& desc, const std::vector<int>& n_rows, int D, const std::vector<KnnProblem>& probs);
 
 // matching.cu — K9, K10
 struct PairJob {

@@ -157,12 +157,19 @@ def _rot(yaw, pitch, roll):
 
 
 def make_maps(seed: int, n_maps: int, n_points: int, size_x: float, size_y: float, rooms_x: int, rooms_y: int,
-              window_frac: float = 0.6, layout: str = "chain"):
-    """Returns (maps, truth): maps[i] float32[n_points, 4]; truth[i] float64 4x4 map_i -> world."""
+              window_frac: float = 0.6, layout: str = "chain", only=None):
+    """Returns (maps, truth): maps[i] float32[n_points, 4]; truth[i] float64 4x4 map_i -> world.
+    only: iterable of map indices to generate (the others come back as None; every map has its own random stream, so a
+    rank that generates just its block gets the same points as a full run)."""
     world = World(seed, size_x, size_y, rooms_x, rooms_y)
     maps, truth = [], []
     wx = size_x * window_frac
+    only = None if only is None else set(int(i) for i in only)
     for i in range(n_maps):
+        if only is not None and i not in only:
+            maps.append(None)
+            truth.append(None)
+            continue
         rng = np.random.default_rng(seed * 1000 + i)
         # windows slide along x so neighbours overlap >= 50 %, second neighbours >= 25 %
         if n_maps > 1:
@@ -196,6 +203,10 @@ CONFIGS = {
     "c1": dict(seed=1, n_maps=2, n_points=200_000, size_x=8.0, size_y=6.0, rooms_x=1, rooms_y=1, window_frac=0.8),
     "c2": dict(seed=2, n_maps=8, n_points=500_000, size_x=28.0, size_y=20.0, rooms_x=2, rooms_y=2, window_frac=0.6),
     "c3": dict(seed=3, n_maps=32, n_points=1_000_000, size_x=40.0, size_y=30.0, rooms_x=4, rooms_y=3, window_frac=0.6),
+    # configs[3]: Harris3D + SHOT variant, 16 maps, tight inlier_threshold (bench.py sets the parameters)
+    "c4": dict(seed=4, n_maps=16, n_points=500_000, size_x=36.0, size_y=24.0, rooms_x=3, rooms_y=2, window_frac=0.6),
+    # configs[4]: 4 maps at 10M points for output_resolution composeMaps
+    "c5": dict(seed=5, n_maps=4, n_points=10_000_000, size_x=40.0, size_y=30.0, rooms_x=4, rooms_y=3, window_frac=0.6),
     "tiny": dict(seed=11, n_maps=2, n_points=40_000, size_x=6.0, size_y=5.0, rooms_x=1, rooms_y=1, window_frac=0.85),
     "small": dict(seed=12, n_maps=3, n_points=60_000, size_x=9.0, size_y=6.0, rooms_x=1, rooms_y=1, window_frac=0.75),
 }

@@ -1,12 +1,184 @@
-"""BASELINE-sized inputs on the GPU, checked through size-independent properties (the CPU oracle would take minutes here):
-ground-truth recovery, cycle consistency of the pairwise transforms, idempotence and point conservation of the voxel grid,
-agreement between the resident path, the host-buffer path and a sharded run."""
+"""BASELINE-sized inputs on the GPU.
+
+Against the CPU oracle (all host threads) wherever it finishes in seconds: maps 0-1 of configs 2 and 3, config 1 in full
+through map_merge_tool, config 4 in miniature (2 x 500k, Harris + SHOT, inlier_threshold 0.2), composeMaps of 4 x 2M
+points; the tensor-core k-NN against the exact scan on every pair of config 2 and 66 pairs of config 3.
+Through size-independent properties where the oracle would take minutes (all 28 pairs of config 2): ground-truth
+recovery, cycle consistency, idempotence and point conservation of the voxel grid, agreement between the resident path,
+the host-buffer path and a sharded run."""
+import os
+import re
+import subprocess
+
 import numpy as np
 import pytest
 
 from conftest import rot_err
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "map-merge_b200")
+
+
+def _bits_equal(a, b):
+    a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint32 if a.dtype.itemsize == 4 else np.uint64),
+                                                 b.view(np.uint32 if b.dtype.itemsize == 4 else np.uint64))
+
+
+def _pairs_against_oracle(ctx, oracle, maps, p_gpu, p_cpu, what):
+    """Whole path on `maps`: per-pair transform and confidence bit for bit, correspondence / inlier counts equal, the stage
+    outputs the oracle exposes (filtered cloud, keypoints, descriptors) bit for bit, global transforms within 1e-5."""
+    oracle.set_threads(0)
+    want = oracle.estimate_maps_transforms(maps, p_cpu)
+    dm = ctx.maps_upload(maps)
+    f = ctx.features_compute(dm, 0, len(maps), p_gpu)
+    npt, nk, dim = f.sizes()
+    ij = np.array([(i, j) for i in range(len(maps) - 1) for j in range(i + 1, len(maps)) if nk[i] > 0 and nk[j] > 0], np.int32).reshape(-1, 2)
+    assert ij.tolist() == want["pairs"][:, :2].tolist(), what
+    T, conf, stats = ctx.register_pairs(f, ij, p_gpu)
+    assert stats[:, 0].tolist() == want["pairs"][:, 2].tolist(), f"{what}: correspondence counts {stats[:, 0]} vs {want['pairs'][:, 2]}"
+    assert stats[:, 1].tolist() == want["pairs"][:, 3].tolist(), f"{what}: RANSAC inlier counts {stats[:, 1]} vs {want['pairs'][:, 3]}"
+    assert _bits_equal(T, want["pair_T"]), f"{what}: pairwise transforms differ\n{T}\n{want['pair_T']}"
+    assert _bits_equal(conf, want["pair_conf"]), f"{what}: confidences {conf} vs {want['pair_conf']}"
+    G = ctx.estimate_resident(dm, p_gpu)
+    np.testing.assert_allclose(G, want["transforms"], rtol=0, atol=1e-5)
+    out = dict(features=f, n_points=npt, n_keypoints=nk, stats=stats, T=T)
+    dm.free()
+    return out
+
+
+def test_config2_maps01_against_oracle(ctx, mm, oracle, synth):
+    """configs[1] (8 x 500k, FPFH): maps 0-1 through the whole path against the oracle, every stage output bit for bit."""
+    import oracle_py
+    cfg = dict(synth.CONFIGS["c2"])
+    maps, _ = synth.make_maps(**cfg, only=[0, 1])
+    r = _pairs_against_oracle(ctx, oracle, maps[:2], mm.default_params(descriptor_type="FPFH"), oracle_py.default_params(descriptor_type=2), "c2")
+    assert (r["n_points"] > 50_000).all() and (r["n_keypoints"] > 500).all() and r["stats"][0, 0] > 100
+    # stage outputs of map 0
+    p = oracle_py.default_params(descriptor_type=2)
+    ds, _ = oracle.downsample(maps[0], p.resolution)
+    fo, _, _ = oracle.remove_outliers(ds, p.descriptor_radius, p.outliers_min_neighbours)
+    nm = oracle.normals(fo, p.normal_radius)
+    kp = oracle.sift(fo, p.resolution, p.keypoint_threshold)
+    kp, desc = oracle.fpfh(fo, nm, kp, p.descriptor_radius)
+    pts, gkp, gdesc = r["features"].export_host(0)
+    assert _bits_equal(pts, fo) and _bits_equal(gkp, kp) and _bits_equal(gdesc, desc)
+    r["features"].free()
+
+
+def test_config3_maps01_against_oracle(ctx, mm, oracle, synth):
+    """configs[2] (32 x 1M, FPFH, the headline workload): maps 0-1 against the oracle."""
+    import oracle_py
+    cfg = dict(synth.CONFIGS["c3"])
+    maps, _ = synth.make_maps(**cfg, only=[0, 1])
+    r = _pairs_against_oracle(ctx, oracle, maps[:2], mm.default_params(descriptor_type="FPFH"), oracle_py.default_params(descriptor_type=2), "c3")
+    assert (r["n_points"] > 150_000).all() and (r["n_keypoints"] > 2000).all() and r["stats"][0, 0] > 500
+    r["features"].free()
+
+
+def test_config4_mini_against_oracle(ctx, mm, oracle, synth):
+    """configs[3] in miniature: 2 x 500k points, Harris3D + SHOT-1344, inlier_threshold 0.2."""
+    import oracle_py
+    cfg = dict(synth.CONFIGS["c4"])
+    maps, _ = synth.make_maps(**cfg, only=[0, 1])
+    pg = mm.default_params(keypoint_type="HARRIS", keypoint_threshold=0.0, descriptor_type="SHOT", inlier_threshold=0.2)
+    pc = oracle_py.default_params(keypoint_type=1, keypoint_threshold=0.0, descriptor_type=4, inlier_threshold=0.2)
+    r = _pairs_against_oracle(ctx, oracle, maps[:2], pg, pc, "c4")
+    assert (r["n_keypoints"] > 20).all()
+    r["features"].free()
+
+
+def write_pcd(path, pts):
+    n = len(pts)
+    hdr = ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z rgb\nSIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 1\n"
+           f"WIDTH {n}\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS {n}\nDATA binary\n")
+    with open(path, "wb") as f:
+        f.write(hdr.encode())
+        f.write(np.ascontiguousarray(pts, np.float32).tobytes())
+
+
+def test_config1_cli_against_oracle(tmp_path, mm, oracle, synth):
+    """configs[0] in full: map_merge_tool on two 200k-point room scans (SIFT + FPFH, RANSAC + ICP) against the oracle: the
+    printed transforms to print precision, output.pcd bit for bit."""
+    import oracle_py
+    subprocess.check_call(["make", "-C", PKG, "tools"], stdout=subprocess.DEVNULL)
+    maps, _ = synth.make_maps(**synth.CONFIGS["c1"])
+    a, b = str(tmp_path / "a.pcd"), str(tmp_path / "b.pcd")
+    write_pcd(a, maps[0]); write_pcd(b, maps[1])
+    r = subprocess.run([os.path.join(PKG, "map_merge_tool"), a, b, "--descriptor_type", "FPFH"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    nums = re.findall(r"[-+]?\d*\.?\d+(?:[eE][-+]?\d+)?", r.stdout.split("Estimated transforms:")[1].split("> Compositing")[0])
+    T = np.array(nums, np.float64).reshape(-1, 4, 4)
+    oracle.set_threads(0)
+    want = oracle.estimate_maps_transforms(maps, oracle_py.default_params(descriptor_type=2))["transforms"]
+    np.testing.assert_allclose(T, want, atol=2e-5, rtol=1e-5)  # printed with 6 significant digits
+    raw = open(tmp_path / "output.pcd", "rb").read()
+    k = raw.index(b"DATA binary\n") + len(b"DATA binary\n")
+    out = np.frombuffer(raw[k:], np.float32).reshape(-1, 4)
+    comp = oracle.compose_maps(maps, want, 0.05)
+    assert _bits_equal(out, comp)
+
+
+def test_compose_large_against_oracle(ctx, oracle, synth):
+    """composeMaps of 4 x 2M points at output_resolution 0.05 (config 5 in miniature) against the oracle, bit for bit; one map
+    carries a zero transform and is skipped (map_merging.cpp:293-295)."""
+    maps, truth = synth.make_maps(seed=5, n_maps=4, n_points=2_000_000, size_x=28.0, size_y=20.0, rooms_x=2, rooms_y=2)
+    T = np.stack([np.linalg.inv(truth[0]) @ t for t in truth]).astype(np.float32)
+    got = ctx.compose_maps(maps, T, 0.05)
+    want = oracle.compose_maps(maps, T, 0.05)
+    assert _bits_equal(got, want)
+    T[2] = 0
+    assert _bits_equal(ctx.compose_maps(maps, T, 0.05), oracle.compose_maps(maps, T, 0.05))
+
+
+def _knn_modes(ctx, monkeypatch, a, b, k=5):
+    monkeypatch.setenv("MM3D_KNN", "exact")
+    ie, de = ctx.knn(a, b, k)
+    monkeypatch.setenv("MM3D_KNN", "tc")
+    it, dt = ctx.knn(a, b, k)
+    monkeypatch.delenv("MM3D_KNN")
+    return ie, de, it, dt
+
+
+def test_tensor_core_knn_against_exact_scan_config2(ctx, mm, synth, monkeypatch):
+    """The tcgen05 filter + exact re-rank against the FP32 scan where its error bound is under stress: the clustered FPFH
+    descriptors of config 2 — indices and distance bits of both directions of all 28 pairs."""
+    maps, _ = synth.make_maps(**synth.CONFIGS["c2"])
+    p = mm.default_params(descriptor_type="FPFH")
+    dm = ctx.maps_upload(maps)
+    f = ctx.features_compute(dm, 0, len(maps), p)
+    desc = [f.export_host(m)[2] for m in range(len(maps))]
+    f.free(); dm.free()
+    rows = 0
+    for i in range(len(maps) - 1):
+        for j in range(i + 1, len(maps)):
+            for a, b in ((desc[i], desc[j]), (desc[j], desc[i])):
+                ie, de, it, dt = _knn_modes(ctx, monkeypatch, a, b)
+                assert np.array_equal(ie, it), f"pair ({i}, {j}): {int((ie != it).any(axis=1).sum())} rows with different neighbours"
+                assert _bits_equal(de, dt), f"pair ({i}, {j}): distances differ"
+                rows += len(a)
+    assert rows > 28 * 2 * 500
+
+
+def test_tensor_core_knn_against_exact_scan_config3(ctx, mm, synth, monkeypatch):
+    """The same on the headline workload: the first 12 maps of config 3, 66 pairs, both directions."""
+    cfg = dict(synth.CONFIGS["c3"])
+    maps, _ = synth.make_maps(**cfg, only=range(12))
+    p = mm.default_params(descriptor_type="FPFH")
+    dm = ctx.maps_upload(maps[:12])
+    f = ctx.features_compute(dm, 0, 12, p)
+    desc = [f.export_host(m)[2] for m in range(12)]
+    f.free(); dm.free()
+    n_pairs = 0
+    for i in range(11):
+        for j in range(i + 1, 12):
+            for a, b in ((desc[i], desc[j]), (desc[j], desc[i])):
+                ie, de, it, dt = _knn_modes(ctx, monkeypatch, a, b)
+                assert np.array_equal(ie, it), f"pair ({i}, {j}): {int((ie != it).any(axis=1).sum())} rows with different neighbours"
+                assert _bits_equal(de, dt), f"pair ({i}, {j}): distances differ"
+            n_pairs += 1
+    assert n_pairs == 66
 
 
 @pytest.fixture(scope="module")
