@@ -119,6 +119,11 @@ int mm3d_match(mm3d_ctx* ctx, const float* desc_src, uint64_t n_src, const float
  * nearestKSearch under flann::L2_Simple): for every row of a, the k nearest rows of b sorted by (distance, index);
  * idx = int32[na][k], dist = float[na][k] (squared L2), k is clamped to nb; unused slots hold -1 / 0. */
 int mm3d_knn(mm3d_ctx* ctx, const float* a, uint64_t na, const float* b, uint64_t nb, int dim, uint64_t k, int32_t* idx, float* dist);
+/* Test hook of the tensor-core k-NN (33-dimensional descriptors, k <= 5): the same search as mm3d_knn through the tcgen05
+ * filter, plus what the filter saw — acc = float[na][nb] raw accumulators (1 - ES) ||b'||^2 - 2 a'.b', the centred squared
+ * norms of both sides and ES.  tests/test_full_size_gpu.py checks the filter's error bound with it on BASELINE-sized data. */
+int mm3d_knn_tc_audit(mm3d_ctx* ctx, const float* a, uint64_t na, const float* b, uint64_t nb, int dim, uint64_t k, int32_t* idx, float* dist,
+                      float* acc, float* norm_a, float* norm_b, float* err_store);
 /* estimateTransformFromCorrespondences (src/matching.cpp:110-140); inliers = positions in pairs.
  * dbg (optional, 2 ints) = RANSAC iterations, best inlier count; dbg_d (optional) = sample distance threshold */
 int mm3d_ransac(mm3d_ctx* ctx, const float* kp_src, uint64_t n_src, const float* kp_tgt, uint64_t n_tgt, const int32_t* pairs,

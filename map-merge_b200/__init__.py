@@ -41,7 +41,7 @@ SYMBOLS = [
     "mm3d_features_export_dev", "mm3d_features_import_dev", "mm3d_features_export_host", "mm3d_features_free",
     "mm3d_register_pairs", "mm3d_estimate_resident", "mm3d_profile_begin", "mm3d_profile_end", "mm3d_sac_ia", "mm3d_knn_stats", "mm3d_compose_shard_begin", "mm3d_compose_shard_size",
     "mm3d_compose_shard_histogram", "mm3d_compose_shard_partition", "mm3d_compose_shard_points", "mm3d_shard_free", "mm3d_downsample_dev",
-    "mm3d_knn", "mm3d_create_multi", "mm3d_device_count", "mm3d_comm_id", "mm3d_comm_create", "mm3d_comm_destroy", "mm3d_comm_rank", "mm3d_comm_size",
+    "mm3d_knn", "mm3d_knn_tc_audit", "mm3d_create_multi", "mm3d_device_count", "mm3d_comm_id", "mm3d_comm_create", "mm3d_comm_destroy", "mm3d_comm_rank", "mm3d_comm_size",
     "mm3d_dist_block", "mm3d_dist_plan", "mm3d_estimate_maps_transforms_dist", "mm3d_estimate_resident_dist", "mm3d_compose_maps_dist",
     "mm3d_compose_resident_dist",
 ]
@@ -255,6 +255,17 @@ class Context:
         self._check(self.L.mm3d_knn(self.h, ap, C.c_uint64(len(a)), bp, C.c_uint64(len(b)), dim, C.c_uint64(int(k)), idx.ctypes.data_as(i32p),
                                     dist.ctypes.data_as(f32p)))
         return idx[:len(a)], dist[:len(a)]
+
+    def knn_tc_audit(self, a, b, k=5):
+        """The tensor-core k-NN on one problem plus what its filter saw: dict(idx, dist, acc[na, nb], norm_a, norm_b, err_store)."""
+        a, ap = _f(a); b, bp = _f(b)
+        na, nb = len(a), len(b)
+        idx = np.zeros((na, k), np.int32); dist = np.zeros((na, k), np.float32)
+        acc = np.zeros((na, nb), np.float32); n_a = np.zeros(na, np.float32); n_b = np.zeros(nb, np.float32); es = C.c_float()
+        self._check(self.L.mm3d_knn_tc_audit(self.h, ap, C.c_uint64(na), bp, C.c_uint64(nb), a.shape[1], C.c_uint64(k), idx.ctypes.data_as(i32p),
+                                             dist.ctypes.data_as(f32p), acc.ctypes.data_as(f32p), n_a.ctypes.data_as(f32p),
+                                             n_b.ctypes.data_as(f32p), C.byref(es)))
+        return dict(idx=idx, dist=dist, acc=acc, norm_a=n_a, norm_b=n_b, err_store=float(es.value))
 
     def ransac(self, kps, kpt, pairs, inlier_threshold):
         s, sp = _f(kps, 4); t, tp = _f(kpt, 4)

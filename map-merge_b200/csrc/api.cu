@@ -1,6 +1,7 @@
 // api.cu — the C ABI (include/mm3d.h) and the orchestration of the hot path:
 // stage-major per-map loops and the all-pairs loop of
 // map_merge_3d/src/map_merging.cpp:188-275, each stage one batched launch set.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -22,8 +23,12 @@ struct StageTimer {
   Ctx& c;
   float* ms;
   cudaEvent_t ev[2];
+  bool host_trace;  // MM3D_HOST_TRACE=1: host wall-clock per stage on stderr, no extra synchronisation (where does the host wait?)
+  std::chrono::steady_clock::time_point h0;
   explicit StageTimer(Ctx& ctx, float* out) : c(ctx), ms(out)
   {
+    const char* e = std::getenv("MM3D_HOST_TRACE");
+    host_trace = e && e[0] == '1';
     if (ms) {
       cudaEventCreate(&ev[0]);
       cudaEventCreate(&ev[1]);
@@ -36,9 +41,16 @@ struct StageTimer {
       cudaEventDestroy(ev[1]);
     }
   }
-  void begin() { if (ms) cudaEventRecord(ev[0], c.stream); }
+  void begin()
+  {
+    if (host_trace) h0 = std::chrono::steady_clock::now();
+    if (ms) cudaEventRecord(ev[0], c.stream);
+  }
   void end(int stage)
   {
+    if (host_trace)
+      fprintf(stderr, "[mm3d host] %-26s %8.2f ms\n", kStageNames[stage],
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());
     if (!ms) return;
     cudaEventRecord(ev[1], c.stream);
     cudaEventSynchronize(ev[1]);
@@ -72,6 +84,19 @@ void check_supported(const mm3d_params& p)
 }  // namespace
 
 namespace mm3d {
+
+HostProf& host_prof()
+{
+  static HostProf hp;
+  static bool init = false;
+  if (!init) {
+    const char* e = std::getenv("MM3D_HOST_TRACE");
+    hp.on = e && e[0] == '1';
+    init = true;
+  }
+  return hp;
+}
+double host_now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 void to_colmajor(const float* rm, float* cm)
 {
@@ -214,16 +239,24 @@ void register_pairs(Ctx& c, const std::vector<FeatView>& f, int dim, const std::
   for (const PairJob& j : jobs) tv[j.b] = clouds[j.b];
   std::vector<DIndex> tidx;
   tm.begin();
-  // cells of 4 x 2 x 2 voxels: a query visits fewer, longer rows.  (Single-voxel rows with 2-voxel cells were measured:
-  // ~10 candidates per query instead of ~100, but 20-35 % slower — the search is bound by the dependent row look-ups;
-  // 4 x 4 x 4 cells are 20 % slower as well.)
-  build_index_batch(c, tv, (float)p.resolution, 2, 1, 1, tidx);
+  // One-voxel cells: the clouds are voxel-grid outputs (at most one point per voxel), so the nearest neighbour of a query
+  // that lies on the target surface is found in the 3 x 3 x 3 voxel block around it — nine (z, y) rows whose three cells are
+  // one contiguous run each (icp.cu, nearest_block27).  The general row search remains the fallback for queries farther
+  // than one voxel from the target.  (Round 1 measured the general search alone: 4 x 2 x 2-voxel cells were its best
+  // setting because it is bound by its per-row bookkeeping; the block search has none.)
+  build_index_batch(c, tv, (float)p.resolution, 0, 0, 0, tidx);
+  // reach grids of the targets (icp.cu): queries without a target point in range are answered without a search
+  std::vector<DReach> reach;
+  {
+    const double r_icp = p.max_correspondence_distance, r_score = std::sqrt(std::max(p.max_correspondence_distance, 0.0));
+    build_reach_batch(c, tidx, (int)std::ceil(std::max(r_icp, r_score) / p.resolution) + 1, reach);
+  }
   std::vector<const float*> t0(P);
   for (int i = 0; i < P; ++i) t0[i] = rs[i].T;
   std::vector<IcpOut> icp(P);
   IcpNeighbours icp_nn;
   if (p.refine_transform) {
-    icp_batch(c, clouds, tidx, jobs, t0, p.max_correspondence_distance, p.max_iterations, p.transform_epsilon, icp, nullptr, &icp_nn);
+    icp_batch(c, clouds, tidx, reach, jobs, t0, p.max_correspondence_distance, p.max_iterations, p.transform_epsilon, icp, nullptr, &icp_nn);
   } else {
     for (int i = 0; i < P; ++i) {
       memcpy(icp[i].T, rs[i].T, sizeof(float) * 16);
@@ -237,7 +270,7 @@ void register_pairs(Ctx& c, const std::vector<FeatView>& f, int dim, const std::
   std::vector<const float*> tf(P);
   for (int i = 0; i < P; ++i) tf[i] = icp[i].T;
   std::vector<double> scores;
-  score_batch(c, clouds, tidx, jobs, tf, p.max_correspondence_distance, scores, p.refine_transform ? &icp_nn : nullptr);
+  score_batch(c, clouds, tidx, reach, jobs, tf, p.max_correspondence_distance, scores, p.refine_transform ? &icp_nn : nullptr);
   tm.end(8);
 
   for (int i = 0; i < P; ++i) {
@@ -301,6 +334,15 @@ int estimate_from_views(Ctx& c, const std::vector<CloudView>& raw, const mm3d_pa
   }
   std::vector<std::vector<float>> g = compute_global_transforms(est, p.confidence_threshold, nullptr, nullptr, nullptr, nullptr);
   for (size_t i = 0; i < g.size(); ++i) to_colmajor(g[i].data(), out_transforms + 16 * i);
+  HostProf& hp = host_prof();
+  if (hp.on) {
+    fprintf(stderr, "[mm3d host] buffer allocations %ld calls %.2f ms (%.1f MB), cudaFreeAsync %ld calls %.2f ms, sync %ld calls %.2f ms, "
+            "small copies %ld calls %.2f ms; block cache holds %.1f MB\n", hp.n_alloc, hp.alloc_ms, hp.alloc_bytes / 1e6, hp.n_free, hp.free_ms,
+            hp.n_sync, hp.sync_ms, hp.n_copy, hp.copy_ms, c.cache->held_bytes / 1e6);
+    const bool on = hp.on;
+    hp = HostProf();
+    hp.on = on;
+  }
   return (int)g.size();
 }
 
@@ -367,6 +409,8 @@ int mm3d_create(mm3d_ctx** ctx, int device, void* cuda_stream)
     if (cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking) != cudaSuccess) return MM3D_ERR_CUDA;
     h->c.own_stream = true;
   }
+  h->c.cache->device = device;
+  h->c.cache->stream = h->c.stream;
   // keep freed blocks in the pool: the path allocates and frees per stage
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -382,6 +426,8 @@ void mm3d_destroy(mm3d_ctx* ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->c.device);
   cudaStreamSynchronize(ctx->c.stream);
+  ctx->c.cache->trim();        // cached blocks go back while the stream still exists
+  ctx->c.cache->stream = nullptr;  // blocks returned by buffers that outlive the context are freed with the last reference
   if (ctx->c.knn_stats) cudaFree(ctx->c.knn_stats);
   for (cudaEvent_t e : ctx->c.event_pool) cudaEventDestroy(e);
   for (KernelSample& s : ctx->c.samples) { cudaEventDestroy(s.e0); cudaEventDestroy(s.e1); }
@@ -633,6 +679,30 @@ int mm3d_knn(mm3d_ctx* ctx, const float* a, uint64_t na, const float* b, uint64_
   MM_CATCH
 }
 
+int mm3d_knn_tc_audit(mm3d_ctx* ctx, const float* a, uint64_t na, const float* b, uint64_t nb, int dim, uint64_t k, int32_t* idx, float* dist,
+                      float* acc, float* norm_a, float* norm_b, float* err_store)
+{
+  if (!idx || !dist || !acc || !norm_a || !norm_b || !err_store) return MM3D_ERR_ARG;
+  MM_TRY(ctx)
+  if (dim != 33 || k == 0 || k > 5 || na == 0 || nb < k) throw UnsupportedError("unsupported: the audit covers 33-dimensional descriptors and k <= 5");
+  DBuf<float> da(c, na * dim), db(c, nb * dim);
+  da.upload(c, a, na * dim);
+  db.upload(c, b, nb * dim);
+  DBuf<int> di(c, na * k);
+  DBuf<float> dd(c, na * k);
+  KnnAudit au;
+  knn_tc_batch(c, {da.p, db.p}, {(int)na, (int)nb}, dim, {KnnProblem{0, 1, (int)na, (int)k, di.p, dd.p}}, &au);
+  di.download(c, idx, na * k);
+  dd.download(c, dist, na * k);
+  c.sync();
+  if (au.acc.size() != na * nb) throw std::runtime_error("knn_tc_audit: no audit data");
+  memcpy(acc, au.acc.data(), au.acc.size() * sizeof(float));
+  memcpy(norm_a, au.norm_a.data(), au.norm_a.size() * sizeof(float));
+  memcpy(norm_b, au.norm_b.data(), au.norm_b.size() * sizeof(float));
+  *err_store = au.err_store;
+  MM_CATCH
+}
+
 int mm3d_ransac(mm3d_ctx* ctx, const float* kp_src, uint64_t n_src, const float* kp_tgt, uint64_t n_tgt, const int32_t* pairs,
                 uint64_t n_corr, double inlier_threshold, float* transform, int32_t** inliers, uint64_t* n_inliers, int32_t* dbg,
                 double* dbg_d, float* best_model)
@@ -691,13 +761,16 @@ int mm3d_icp(mm3d_ctx* ctx, const float* src, uint64_t n_src, const float* tgt, 
   MM_TRY(ctx)
   DCloud s = upload_cloud(c, src, n_src), t = upload_cloud(c, tgt, n_tgt);
   std::vector<DIndex> idx;
-  build_index_batch(c, {CloudView{nullptr, 0}, t.view()}, (float)auto_leaf(index_leaf, max_correspondence_distance, 10.0), 2, 1, 1, idx);
+  const double leaf = auto_leaf(index_leaf, max_correspondence_distance, 10.0);
+  build_index_batch(c, {CloudView{nullptr, 0}, t.view()}, (float)leaf, 0, 0, 0, idx);
+  std::vector<DReach> reach;
+  build_reach_batch(c, idx, (int)std::ceil(max_correspondence_distance / leaf) + 1, reach);
   float t0[16];
   from_colmajor(initial_guess, t0);
   std::vector<IcpOut> out;
   std::vector<std::vector<long long>> sd;
-  icp_batch(c, {s.view(), t.view()}, idx, {PairJob{0, 1}}, {t0}, max_correspondence_distance, max_iterations, transformation_epsilon, out,
-            sums ? &sd : nullptr);
+  icp_batch(c, {s.view(), t.view()}, idx, reach, {PairJob{0, 1}}, {t0}, max_correspondence_distance, max_iterations, transformation_epsilon,
+            out, sums ? &sd : nullptr);
   to_colmajor(out[0].T, transform);
   if (dbg) { dbg[0] = out[0].iterations; dbg[1] = out[0].converged; }
   if (sums) {
@@ -715,12 +788,14 @@ int mm3d_score(mm3d_ctx* ctx, const float* src, uint64_t n_src, const float* tgt
   MM_TRY(ctx)
   DCloud s = upload_cloud(c, src, n_src), t = upload_cloud(c, tgt, n_tgt);
   std::vector<DIndex> idx;
-  build_index_batch(c, {CloudView{nullptr, 0}, t.view()}, (float)auto_leaf(index_leaf, std::sqrt(std::max(max_distance, 1e-12)), 10.0), 2, 1, 1,
-                    idx);
+  const double leaf = auto_leaf(index_leaf, std::sqrt(std::max(max_distance, 1e-12)), 10.0);
+  build_index_batch(c, {CloudView{nullptr, 0}, t.view()}, (float)leaf, 0, 0, 0, idx);
+  std::vector<DReach> reach;
+  build_reach_batch(c, idx, (int)std::ceil(std::sqrt(std::max(max_distance, 0.0)) / leaf) + 1, reach);
   float tr[16];
   from_colmajor(transform, tr);
   std::vector<double> sc;
-  score_batch(c, {s.view(), t.view()}, idx, {PairJob{0, 1}}, {tr}, max_distance, sc);
+  score_batch(c, {s.view(), t.view()}, idx, reach, {PairJob{0, 1}}, {tr}, max_distance, sc);
   *score = sc[0];
   MM_CATCH
 }

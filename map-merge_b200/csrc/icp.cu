@@ -1,16 +1,28 @@
-// icp.cu — K11 point-to-point ICP refine and K12 Euclidean transform score,
-// all pairs per launch (blockIdx.y = pair).
+// icp.cu — K11 point-to-point ICP refine and K12 Euclidean transform score, all pairs at once.
 //   <- map_merge_3d/src/matching.cpp:196-221 (pcl::IterativeClosestPoint, TransformationEstimationSVD,
 //      DefaultConvergenceCriteria) and :259-268 (pcl::registration::TransformationValidationEuclidean)
-// One iteration = one kernel that does the nearest-neighbour search, the distance
-// gate and the {n, sum p, sum q, sum q p^T, sum d^2} reduction for every active
-// pair, plus a one-warp-per-pair kernel that solves Umeyama (3x3 SVD), updates the
-// transform and tests convergence on the device.  Sums are fixed-point int64, so
-// the reduction is order-independent and matches the CPU checker bit for bit.
+//
+// The WHOLE ICP loop of every pair is ONE persistent cooperative kernel: per iteration the blocks pull 128-query tiles of
+// the still-active pairs from a device-side queue; a tile applies the previous iteration's step transform, finds each
+// query's nearest target point within the correspondence distance and adds its share of {n, sum p, sum q, sum q p^T,
+// sum d^2} (fixed-point int64, so the reduction is order-independent and matches the CPU checker bit for bit); the last
+// tile of a pair solves Umeyama (3x3 SVD), updates the transform and tests convergence; a grid-wide barrier ends the
+// iteration, block 0 rebuilds the tile queue from the pairs that are still active, and the loop ends on the device when
+// none is left.  The host launches once and reads the results once.
+//
+// Nearest-neighbour search: thread per query over the voxel-row index, pruned three ways — (1) the target's reach grid
+// (a lower bound of the distance to the nearest target point per voxel) answers queries that have no target point in
+// range without a search, which is most of the non-overlapping part of a pair; (2) the same bound plus the voxel
+// diagonal caps the radius for the others; (3) the previous iteration's match seeds the running best.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 #include "mm3d_internal.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace mm3d {
 
@@ -31,17 +43,263 @@ struct IcpState {
 
 struct IcpJob {
   GridView tgt;      // target index
+  ReachView reach;   // target reach grid
   const float4* src; // source cloud
   int ns;
   float4* work;      // transformed source (input_transformed)
   long long* sums;   // NSUM
   IcpState* st;
-  int* ticket;       // blocks of this pair that finished the current iteration
+  int* ticket;       // tiles of this pair that finished the current iteration
   float t0[16];      // initial guess, row-major
   long long* sums_log;  // optional max_log x NSUM
   int* nn_slot;      // per source point: the target slot matched in the previous iteration (-1 = none)
 };
 
+struct IcpLoop {
+  int n_active;     // pairs still iterating
+  int iteration;
+  int total_tiles;  // tiles of this iteration (0 = done)
+  int next_tile;    // queue head
+};
+
+// ---------------------------------------------------------------- reach grid
+struct ReachJob {
+  GridView g;
+  ReachView r;
+  unsigned char* a;  // ping
+  unsigned char* b;  // pong (final)
+};
+
+__global__ void __launch_bounds__(256) reach_mark_kernel(const ReachJob* __restrict__ jobs)
+{
+  const ReachJob& j = jobs[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.g.n; i += gridDim.x * blockDim.x) {
+    const float4 p = j.g.pts[i];
+    const int x = floor_to_int(p.x * j.g.inv_leaf) - j.g.min_b[0] - j.r.org[0];
+    const int y = floor_to_int(p.y * j.g.inv_leaf) - j.g.min_b[1] - j.r.org[1];
+    const int z = floor_to_int(p.z * j.g.inv_leaf) - j.g.min_b[2] - j.r.org[2];
+    if (x >= 0 && y >= 0 && z >= 0 && x < j.r.dim[0] && y < j.r.dim[1] && z < j.r.dim[2])
+      j.a[((size_t)z * j.r.dim[1] + y) * j.r.dim[0] + x] = 0;
+  }
+}
+
+// one axis of the min-plus transform: out(c) = min over |d| <= margin of in(c + d * stride) + max(|d| - 1, 0)^2, saturating
+__global__ void __launch_bounds__(256) reach_pass_kernel(const ReachJob* __restrict__ jobs, int axis, int margin, int from_a)
+{
+  const ReachJob& j = jobs[blockIdx.y];
+  const size_t ncell = (size_t)j.r.dim[0] * j.r.dim[1] * j.r.dim[2];
+  const unsigned char* in = from_a ? j.a : j.b;
+  unsigned char* out = from_a ? j.b : j.a;
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(c % j.r.dim[0]);
+    const int y = (int)((c / j.r.dim[0]) % j.r.dim[1]);
+    const int z = (int)(c / ((size_t)j.r.dim[0] * j.r.dim[1]));
+    const int pos = axis == 0 ? x : (axis == 1 ? y : z);
+    const int len = j.r.dim[axis];
+    const long long stride = axis == 0 ? 1 : (axis == 1 ? (long long)j.r.dim[0] : (long long)j.r.dim[0] * j.r.dim[1]);
+    const int lo = max(-margin, -pos), hi = min(margin, len - 1 - pos);
+    int best = 255;
+    for (int d = lo; d <= hi; ++d) {
+      const int f = max(abs(d) - 1, 0);
+      const int v = (int)in[(long long)c + (long long)d * stride] + f * f;
+      best = min(best, v);
+    }
+    out[c] = (unsigned char)min(best, j.r.none);
+  }
+}
+
+// lower bound (voxel units, squared) for a query; returns false when the query lies outside the grid (= farther than the margin)
+__device__ __forceinline__ bool reach_lookup(const GridView& g, const ReachView& r, float qx, float qy, float qz, int* lb2)
+{
+  const int x = floor_to_int(qx * g.inv_leaf) - g.min_b[0] - r.org[0];
+  const int y = floor_to_int(qy * g.inv_leaf) - g.min_b[1] - r.org[1];
+  const int z = floor_to_int(qz * g.inv_leaf) - g.min_b[2] - r.org[2];
+  if (x < 0 || y < 0 || z < 0 || x >= r.dim[0] || y >= r.dim[1] || z >= r.dim[2]) return false;
+  *lb2 = (int)__ldg(&r.lb2[((size_t)z * r.dim[1] + y) * r.dim[0] + x]);
+  return true;
+}
+
+// The 3 x 3 x 3 voxel block around the query in an index with one-voxel cells: nine (z, y) rows of three cells each, every
+// row one contiguous run of points.  All nine run bounds are loaded up front (independent loads), rows are skipped when
+// their slab distance already exceeds the running best.  Every point outside the block is at least one voxel away, so a
+// best closer than that is the exact nearest neighbour (*certain); otherwise the caller falls back to the general search.
+__device__ __forceinline__ bool nearest_block27(const GridView& g, float qx, float qy, float qz, double bound, int guess_slot, int* out_idx,
+                                                float* out_d2, float4* out_pt, int* out_slot, bool* certain)
+{
+  const float fx = qx * g.inv_leaf, fy = qy * g.inv_leaf, fz = qz * g.inv_leaf;
+  const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+  const int vx = (int)flx - g.min_b[0], vy = (int)fly - g.min_b[1], vz = (int)flz - g.min_b[2];
+  const float ay = fy - fly, az = fz - flz;  // position inside the voxel, voxel units
+  bool found = false;
+  float best = 0.0f;
+  int best_idx = 0x7fffffff, best_slot = -1;
+  float4 best_pt = make_float4(0.f, 0.f, 0.f, 0.f);
+  float bestv = 3.0e38f;  // best in voxel units, squared (row pruning)
+  const float inv2 = g.inv_leaf * g.inv_leaf;
+  if (guess_slot >= 0 && guess_slot < g.n) {
+    const float4 p = g.pts[guess_slot];
+    const float d2 = em::dist2_3(qx, qy, qz, p.x, p.y, p.z);
+    if ((double)d2 <= bound) {
+      found = true;
+      best = d2;
+      best_idx = g.orig ? g.orig[guess_slot] : guess_slot;
+      best_slot = guess_slot;
+      best_pt = p;
+      bestv = d2 * inv2 * 1.0001f + 1e-4f;
+    }
+  }
+  int rs[9], re[9];
+  const int xlo = max(vx - 1, 0), xhi = min(vx + 1, g.div_v[0] - 1);
+  const bool x_ok = xlo <= xhi;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int cz = vz + t / 3 - 1, cy = vy + t % 3 - 1;
+    rs[t] = 0;
+    re[t] = 0;
+    if (x_ok && cz >= 0 && cz < g.div_v[2] && cy >= 0 && cy < g.div_v[1]) {
+      const int base = (cz * g.dim[1] + cy) * g.dim[0];
+      rs[t] = __ldg(&g.cell_start[base + xlo]);
+      re[t] = __ldg(&g.cell_start[base + xhi + 1]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int dz = t / 3 - 1, dy = t % 3 - 1;
+    const float zd = dz < 0 ? az : (dz > 0 ? 1.0f - az : 0.0f);
+    const float yd = dy < 0 ? ay : (dy > 0 ? 1.0f - ay : 0.0f);
+    if (zd * zd + yd * yd > bestv) continue;
+    for (int k = rs[t]; k < re[t]; ++k) {
+      const float4 p = g.pts[k];
+      const float d2 = em::dist2_3(qx, qy, qz, p.x, p.y, p.z);
+      if ((double)d2 > bound) continue;
+      const int oi = g.orig ? g.orig[k] : k;
+      if (!found || d2 < best || (d2 == best && oi < best_idx)) {
+        found = true;
+        best = d2;
+        best_idx = oi;
+        best_slot = k;
+        best_pt = p;
+        bestv = d2 * inv2 * 1.0001f + 1e-4f;
+      }
+    }
+  }
+  *certain = found && best * inv2 < 0.999f;
+  *out_idx = best_idx;
+  *out_d2 = best;
+  *out_pt = best_pt;
+  *out_slot = found ? best_slot : -1;
+  return found;
+}
+
+// Bounded nearest neighbour for the IB queries of one tile, in three block-wide phases so that the warps stay converged:
+//   1. thread per query: the reach grid answers "nothing within the bound" for queries far from the target, the 27-voxel
+//      block answers queries that lie on the target surface (the common case once two clouds are roughly aligned);
+//   2. the queries neither could settle are compacted into a shared-memory list and served by WHOLE WARPS, one query per
+//      warp at a time: the 32 lanes resolve the (z, y) rows of the query's window in parallel and test 32 candidates per
+//      step (warp_radius_unordered), the window bounded by what phase 1 learned (reach-grid upper bound, or the best
+//      point of the block).  In the thread-per-query search these few long-running queries kept whole warps busy at
+//      6-12 active lanes of 32 (ncu, round 2);
+//   3. every thread picks up its result.
+// The result is the same as an exhaustive search: the nearest point by (d^2, original index) among those with d^2 <= bound.
+struct TileNn {
+  float4 q[IB];   // x, y, z, search radius^2 of the queries handed to phase 2
+  int todo[IB];
+  float res_d2[IB];
+  int res_slot[IB];
+  int n_todo;
+};
+
+__device__ __forceinline__ bool tile_nearest(TileNn& sh, const GridView& g, const ReachView& r, bool live, float qx, float qy, float qz,
+                                             double bound, int guess_slot, float* out_d2, float4* out_pt, int* out_slot)
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) sh.n_todo = 0;
+  __syncthreads();
+  bool hit = false, pending = false;
+  float d2 = 0.f;
+  int slot = -1;
+  float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) {
+    float r2 = (float)bound;  // radius^2 phase 2 would have to search
+    bool rejected = false, block_has_points = true;
+    if (r.lb2) {
+      int lb2 = 0;
+      const float bound_v = (float)bound * g.inv_leaf * g.inv_leaf;  // bound in voxel units, squared
+      const bool inside = reach_lookup(g, r, qx, qy, qz, &lb2);
+      // outside the grid: farther than the margin from every occupied voxel, i.e. lower bound >= none
+      const float lb = inside ? (float)lb2 : (float)r.none;
+      if (lb > bound_v * 1.001f + 0.01f) rejected = true;
+      if (inside && lb2 < r.none) {
+        const float ub = sqrtf((float)lb2) + 3.4642f;  // + twice the voxel diagonal
+        r2 = fminf(r2, (ub * ub * 1.001f + 0.01f) * g.leaf * g.leaf);
+      }
+      block_has_points = inside && lb2 == 0;  // lower bound 0 <=> an occupied voxel inside the 3 x 3 x 3 block
+    }
+    if (!rejected) {
+      bool certain = false;
+      if ((block_has_points || guess_slot >= 0) && g.shift[0] == 0 && g.shift[1] == 0 && g.shift[2] == 0) {
+        int idx;
+        hit = nearest_block27(g, qx, qy, qz, bound, guess_slot, &idx, &d2, &pt, &slot, &certain);
+        if (hit) r2 = fminf(r2, d2);  // phase 2 only has to look for something at least as close
+      }
+      if (!certain) {
+        pending = true;
+        hit = false;
+        sh.q[tid] = make_float4(qx, qy, qz, r2 * 1.00001f + 1e-12f);  // strict < inside the walk: widen by a hair
+        sh.todo[atomicAdd(&sh.n_todo, 1)] = tid;
+      }
+    }
+  }
+  __syncthreads();
+  const int n_todo = sh.n_todo;
+  for (int t = warp; t < n_todo; t += IB / 32) {
+    const int who = sh.todo[t];
+    const float4 q = sh.q[who];
+    const int rv = (int)ceilf(sqrtf(q.w) * g.inv_leaf) + 1;
+    float bd = 3.0e38f;
+    int bi = 0x7fffffff, bs = -1;
+    warp_radius_unordered(g, q.x, q.y, q.z, q.w, rv, [&](bool valid, int k, const float4&, float dd) {
+      if (valid && (double)dd <= bound) {
+        const int oi = g.orig ? g.orig[k] : k;
+        if (dd < bd || (dd == bd && oi < bi)) {
+          bd = dd;
+          bi = oi;
+          bs = k;
+        }
+      }
+    });
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+      if (od < bd || (od == bd && oi < bi)) {
+        bd = od;
+        bi = oi;
+        bs = os;
+      }
+    }
+    if (lane == 0) {
+      sh.res_d2[who] = bd;
+      sh.res_slot[who] = bs;
+    }
+  }
+  __syncthreads();
+  if (pending) {
+    slot = sh.res_slot[tid];
+    hit = slot >= 0;
+    if (hit) {
+      d2 = sh.res_d2[tid];
+      pt = g.pts[slot];
+    }
+  }
+  *out_d2 = d2;
+  *out_pt = pt;
+  *out_slot = hit ? slot : -1;
+  return hit;
+}
+
+// ---------------------------------------------------------------- ICP
 __global__ void __launch_bounds__(256) icp_init_kernel(const IcpJob* __restrict__ jobs)
 {
   const IcpJob& j = jobs[blockIdx.y];
@@ -59,6 +317,7 @@ __device__ __forceinline__ void block_accumulate(long long* vals, int nvals, lon
 {
   __shared__ long long sh[IB / 32][NSUM];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();  // the previous tile's readers are done with sh
   for (int k = 0; k < nvals; ++k) {
     const long long v = warp_sum_ll(vals[k]);
     if (lane == 0) sh[w][k] = v;
@@ -84,14 +343,14 @@ __device__ void mat4_mul(const float* a, const float* b, float* r)
 }
 
 // Umeyama from the finished reductions, transform update and pcl::registration::DefaultConvergenceCriteria for one pair;
-// runs on one thread of the LAST block of that pair to finish (so an ICP iteration is a single kernel)
+// runs on one thread of the LAST tile of that pair to finish
 __device__ void icp_solve(const IcpJob& j, int max_iterations, double rotation_threshold, double translation_threshold, int max_log,
-                          int* __restrict__ n_active)
+                          int* n_active)
 {
   IcpState& st = *j.st;
   long long s[NSUM];
   for (int k = 0; k < NSUM; ++k) {
-    s[k] = (long long)atomicExch((unsigned long long*)&j.sums[k], 0ull);  // read the other blocks' atomics, reset for the next iteration
+    s[k] = (long long)atomicExch((unsigned long long*)&j.sums[k], 0ull);  // read the other tiles' atomics, reset for the next iteration
   }
   if (j.sums_log && st.iterations < max_log)
     for (int k = 0; k < NSUM; ++k) j.sums_log[(size_t)st.iterations * NSUM + k] = s[k];
@@ -145,33 +404,39 @@ __device__ void icp_solve(const IcpJob& j, int max_iterations, double rotation_t
   }
 }
 
-// the step transform of the previous iteration is applied on the fly
-// (transformCloud(input_transformed, input_transformed, transformation_))
-__global__ void __launch_bounds__(IB) icp_iteration_kernel(const IcpJob* __restrict__ jobs, double max_dist_sqr, int rv, int apply_step,
-                                                           int max_iterations, double rotation_threshold, double translation_threshold,
-                                                           int max_log, int* __restrict__ n_active)
+// One 128-query tile of one pair in the current iteration.  Data that other blocks wrote in an earlier iteration (work,
+// nn_slot, the step transform) is read through L2 (__ldcg): L1 is not coherent between SMs.
+__device__ __forceinline__ void icp_tile(const IcpJob& j, int tile, int apply_step, double max_dist_sqr, int rv, int max_iterations,
+                                         double rotation_threshold, double translation_threshold, int max_log, int* n_active)
 {
-  const IcpJob& j = jobs[blockIdx.y];
-  if (!j.st->active) return;
-  if (blockIdx.x * IB >= j.ns) return;
+  __shared__ float s_step[16];
+  __shared__ TileNn nn;
+  __syncthreads();
+  if (threadIdx.x < 16) s_step[threadIdx.x] = __ldcg(&j.st->step[threadIdx.x]);
+  __syncthreads();
   long long v[NSUM];
 #pragma unroll
   for (int k = 0; k < NSUM; ++k) v[k] = 0;
-  const int i = blockIdx.x * IB + threadIdx.x;
-  if (i < j.ns) {
-    float4 p = j.work[i];
-    if (apply_step) {
+  const int i = tile * IB + threadIdx.x;
+  const bool live = i < j.ns;
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  int guess = -1;
+  if (live) {
+    p = __ldcg(&j.work[i]);
+    if (apply_step) {  // transformCloud(input_transformed, input_transformed, transformation_) of the previous iteration
       float4 o;
-      em::transform_point(j.st->step, p.x, p.y, p.z, &o.x, &o.y, &o.z);
+      em::transform_point(s_step, p.x, p.y, p.z, &o.x, &o.y, &o.z);
       o.w = p.w;
       p = o;
       j.work[i] = p;
     }
-    int idx;
-    float d2;
-    float4 q;
-    int slot;
-    const bool hit = nearest_bounded(j.tgt, p.x, p.y, p.z, max_dist_sqr, rv, &idx, &d2, &q, j.nn_slot[i], &slot);
+    guess = __ldcg(&j.nn_slot[i]);
+  }
+  float d2;
+  float4 q;
+  int slot;
+  const bool hit = tile_nearest(nn, j.tgt, j.reach, live, p.x, p.y, p.z, max_dist_sqr, guess, &d2, &q, &slot);
+  if (live) {
     j.nn_slot[i] = slot;  // the transform moves little between iterations: last iteration's match seeds the next search
     if (hit) {
       const double pp[3] = {(double)p.x, (double)p.y, (double)p.z};
@@ -188,15 +453,13 @@ __global__ void __launch_bounds__(IB) icp_iteration_kernel(const IcpJob* __restr
     }
   }
   block_accumulate(v, NSUM, j.sums);
-  // last block of this pair: solve + convergence test
-  __shared__ int s_last;
+  // last tile of this pair: solve + convergence test
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    const int nblocks = (j.ns + IB - 1) / IB;
+    const int ntiles = (j.ns + IB - 1) / IB;
     const int ticket = atomicAdd(j.ticket, 1);
-    s_last = (ticket == nblocks - 1) ? 1 : 0;
-    if (s_last) {
+    if (ticket == ntiles - 1) {
       *j.ticket = 0;
       __threadfence();
       icp_solve(j, max_iterations, rotation_threshold, translation_threshold, max_log, n_active);
@@ -204,9 +467,64 @@ __global__ void __launch_bounds__(IB) icp_iteration_kernel(const IcpJob* __restr
   }
 }
 
+// tile_pref[k] = first tile of the k-th active pair, tile_pair[k] = its job index, tile_pair[n_jobs] = number of active pairs
+__global__ void __launch_bounds__(IB) icp_persistent_kernel(const IcpJob* __restrict__ jobs, int n_jobs, IcpLoop* loop, int* tile_pref,
+                                                            int* tile_pair, double max_dist_sqr, int rv, int max_iterations,
+                                                            double rotation_threshold, double translation_threshold, int max_log)
+{
+  cg::grid_group grid = cg::this_grid();
+  __shared__ int s_tile, s_nact;
+  for (;;) {
+    const int total = __ldcg(&loop->total_tiles);
+    if (total == 0) break;
+    const int it = __ldcg(&loop->iteration);
+    if (threadIdx.x == 0) s_nact = __ldcg(&tile_pair[n_jobs]);
+    for (;;) {
+      __syncthreads();
+      if (threadIdx.x == 0) s_tile = atomicAdd(&loop->next_tile, 1);
+      __syncthreads();
+      const int tile = s_tile;
+      if (tile >= total) break;
+      // owner of the tile: last k with tile_pref[k] <= tile
+      int lo = 0, hi = s_nact - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldcg(&tile_pref[mid]) <= tile) lo = mid;
+        else hi = mid - 1;
+      }
+      const IcpJob& j = jobs[__ldcg(&tile_pair[lo])];
+      icp_tile(j, tile - __ldcg(&tile_pref[lo]), it > 0 ? 1 : 0, max_dist_sqr, rv, max_iterations, rotation_threshold, translation_threshold,
+               max_log, &loop->n_active);
+    }
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      // rebuild the queue from the pairs that are still active (a few hundred at most: one thread)
+      int n = 0, tiles = 0;
+      const int next_it = it + 1;
+      if (next_it < max(max_iterations, 1)) {
+        for (int a = 0; a < n_jobs; ++a)
+          if (__ldcg(&jobs[a].st->active)) {
+            tile_pref[n] = tiles;
+            tile_pair[n] = a;
+            tiles += (jobs[a].ns + IB - 1) / IB;
+            ++n;
+          }
+      }
+      tile_pref[n] = tiles;
+      tile_pair[n_jobs] = n;
+      loop->iteration = next_it;
+      loop->next_tile = 0;
+      __threadfence();
+      loop->total_tiles = tiles;
+    }
+    grid.sync();
+  }
+}
+
 // ---------------------------------------------------------------- score
 struct ScoreJob {
   GridView tgt;
+  ReachView reach;
   const float4* src;
   int ns;
   float t[16];
@@ -218,29 +536,86 @@ __global__ void __launch_bounds__(IB) score_kernel(const ScoreJob* __restrict__ 
 {
   const ScoreJob& j = jobs[blockIdx.y];
   if (blockIdx.x * IB >= j.ns) return;
+  __shared__ TileNn nn;
   long long v[2] = {0, 0};
   const int i = blockIdx.x * IB + threadIdx.x;
-  if (i < j.ns) {
+  const bool live = i < j.ns;
+  float x = 0.f, y = 0.f, z = 0.f;
+  if (live) {
     const float4 p = j.src[i];
-    float x, y, z;
     em::transform_point(j.t, p.x, p.y, p.z, &x, &y, &z);
-    int idx;
-    float d2;
-    float4 q;
-    // the reference compares the squared distance with the plain range
-    if (nearest_bounded(j.tgt, x, y, z, max_range, rv, &idx, &d2, &q, j.nn_guess ? j.nn_guess[i] : -1)) {
-      v[0] = em::to_fix((double)d2, MM3D_FIXD_SCALE);
-      v[1] = 1;
-    }
+  }
+  float d2;
+  float4 q;
+  int slot;
+  // the reference compares the squared distance with the plain range
+  if (tile_nearest(nn, j.tgt, j.reach, live, x, y, z, max_range, (live && j.nn_guess) ? j.nn_guess[i] : -1, &d2, &q, &slot)) {
+    v[0] = em::to_fix((double)d2, MM3D_FIXD_SCALE);
+    v[1] = 1;
   }
   block_accumulate(v, 2, j.sums);
 }
 
+ReachView no_reach()
+{
+  ReachView r;
+  memset(&r, 0, sizeof(r));
+  return r;
+}
+
 }  // namespace
 
-void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<PairJob>& jobs,
-               const std::vector<const float*>& T0, double max_dist, int max_it, double eps, std::vector<IcpOut>& out,
-               std::vector<std::vector<long long>>* sums_dbg, IcpNeighbours* nn_keep)
+void build_reach_batch(Ctx& c, const std::vector<DIndex>& idx, int margin, std::vector<DReach>& out)
+{
+  const int M = (int)idx.size();
+  out.clear();
+  out.resize(M);
+  margin = std::max(2, std::min(margin, 15));
+  std::vector<ReachJob> jobs;
+  std::vector<DBuf<unsigned char>> ping(M);
+  size_t max_cells = 0;
+  int max_n = 0;
+  for (int m = 0; m < M; ++m) {
+    out[m].v = no_reach();
+    const GridView& g = idx[m].v;
+    if (g.n <= 0 || g.div_v[0] <= 0) continue;
+    ReachView r = no_reach();
+    size_t cells = 1;
+    for (int k = 0; k < 3; ++k) {
+      r.org[k] = -margin;
+      r.dim[k] = g.div_v[k] + 2 * margin;
+      cells *= (size_t)r.dim[k];
+    }
+    if (cells > ((size_t)1 << 30)) continue;  // absurdly sparse cloud: search without the grid
+    r.none = std::min(255, margin * margin);
+    out[m].lb2.alloc(c, cells);
+    ping[m].alloc(c, cells);
+    MM_CUDA(cudaMemsetAsync(ping[m].p, 255, cells, c.stream));
+    r.lb2 = out[m].lb2.p;
+    out[m].v = r;
+    jobs.push_back(ReachJob{g, r, ping[m].p, out[m].lb2.p});
+    max_cells = std::max(max_cells, cells);
+    max_n = std::max(max_n, g.n);
+  }
+  if (jobs.empty()) return;
+  DBuf<ReachJob> dj = to_device(c, jobs);
+  const unsigned nj = (unsigned)jobs.size();
+  MM_LAUNCH(c, reach_mark_kernel, dim3(std::max(1, std::min((max_n + 255) / 256, 148 * 4)), nj), 256, 0, dj.p);
+  const unsigned blocks = (unsigned)std::min<size_t>((max_cells + 255) / 256, 148 * 16);
+  // x: ping -> lb2, y: lb2 -> ping, z: ping -> lb2
+  double bytes = 0;
+  for (const ReachJob& j : jobs) bytes += 2.0 * j.r.dim[0] * j.r.dim[1] * j.r.dim[2];
+  MM_BYTES(c, bytes);
+  MM_LAUNCH(c, reach_pass_kernel, dim3(blocks, nj), 256, 0, dj.p, 0, margin, 1);
+  MM_BYTES(c, bytes);
+  MM_LAUNCH(c, reach_pass_kernel, dim3(blocks, nj), 256, 0, dj.p, 1, margin, 0);
+  MM_BYTES(c, bytes);
+  MM_LAUNCH(c, reach_pass_kernel, dim3(blocks, nj), 256, 0, dj.p, 2, margin, 1);
+}
+
+void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<DReach>& reach,
+               const std::vector<PairJob>& jobs, const std::vector<const float*>& T0, double max_dist, int max_it, double eps,
+               std::vector<IcpOut>& out, std::vector<std::vector<long long>>* sums_dbg, IcpNeighbours* nn_keep)
 {
   const int P = (int)jobs.size();
   out.assign(P, IcpOut());
@@ -288,7 +663,7 @@ void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<D
     memset(&hst[a], 0, sizeof(IcpState));
     for (int k = 0; k < 16; ++k) hst[a].final_t[k] = hst[a].step[k] = (k % 5 == 0) ? 1.f : 0.f;
     hst[a].prev_mse = 1.7976931348623157e308;
-    // an empty source launches no block, so nothing would ever retire the pair: it starts out finished and not converged
+    // an empty source has no tile, so nothing would ever retire the pair: it starts out finished and not converged
     // ("Not enough correspondences found", the transform stays the initial guess)
     hst[a].active = clouds[jobs[act[a]].a].n > 0 ? 1 : 0;
   }
@@ -298,6 +673,7 @@ void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<D
   for (int a = 0; a < A; ++a) {
     const PairJob& pj = jobs[act[a]];
     ij[a].tgt = idx[pj.b].v;
+    ij[a].reach = pj.b < (int)reach.size() ? reach[pj.b].v : no_reach();
     ij[a].src = clouds[pj.a].pts;
     ij[a].ns = clouds[pj.a].n;
     ij[a].work = work.p + off;
@@ -311,23 +687,51 @@ void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<D
     off += (size_t)ij[a].ns;
   }
   DBuf<IcpJob> dij = to_device(c, ij);
-  DBuf<int> dn_active(c, 1);
-  int n_active = 0;
-  for (int a = 0; a < A; ++a) n_active += hst[a].active;
-  dn_active.upload(c, &n_active, 1);
+  // the first iteration's queue: every pair with a non-empty source
+  std::vector<int> pref(A + 1, 0), pairs(A + 1, 0);
+  IcpLoop hl;
+  memset(&hl, 0, sizeof(hl));
+  int n = 0, tiles = 0;
+  double bytes = 0;
+  for (int a = 0; a < A; ++a)
+    if (hst[a].active) {
+      pref[n] = tiles;
+      pairs[n] = a;
+      tiles += (ij[a].ns + IB - 1) / IB;
+      ++n;
+      bytes += 16.0 * (2.0 * ij[a].ns + ij[a].tgt.n);
+    }
+  pref[n] = tiles;
+  pairs[A] = n;
+  hl.n_active = n;
+  hl.total_tiles = max_it >= 1 ? tiles : 0;
+  DBuf<int> dpref = to_device(c, pref), dpairs = to_device(c, pairs);
+  DBuf<IcpLoop> dloop(c, 1);
+  dloop.upload(c, &hl, 1);
   const int iblocks = std::max(1, std::min((mx + 255) / 256, 148 * 8));
   MM_LAUNCH(c, icp_init_kernel, dim3(iblocks, A), 256, 0, dij.p);
   const double max_dist_sqr = max_dist * max_dist;
   const float leaf = idx[jobs[act[0]].b].v.leaf;
   const int rv = (int)std::ceil(max_dist / (double)leaf) + 1;
-  const dim3 grid(std::max(1, (mx + IB - 1) / IB), A);
-  int it = 0;
-  while (n_active > 0 && it < std::max(max_it, 1)) {
-    { double b = 0; for (int a = 0; a < A; ++a) b += 16.0 * ((double)ij[a].ns * (it > 0 ? 2 : 1) + ij[a].tgt.n); MM_BYTES(c, b * ((double)n_active / A)); }
-    MM_LAUNCH(c, icp_iteration_kernel, grid, IB, 0, dij.p, max_dist_sqr, rv, it > 0 ? 1 : 0, max_it, 1.0 - eps, eps, max_log, dn_active.p);
-    dn_active.download(c, &n_active, 1);
-    c.sync();
-    ++it;
+  if (hl.total_tiles > 0) {
+    // persistent cooperative launch: as many blocks as can be co-resident
+    int dev = 0, sms = 0, per_sm = 0;
+    MM_CUDA(cudaGetDevice(&dev));
+    MM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_persistent_kernel, IB, 0));
+    const int grid = std::max(1, std::min(sms * std::max(per_sm, 1), tiles));
+    const IcpJob* a_jobs = dij.p;
+    int a_n = A;
+    IcpLoop* a_loop = dloop.p;
+    int* a_pref = dpref.p;
+    int* a_pairs = dpairs.p;
+    double a_md = max_dist_sqr, a_rot = 1.0 - eps, a_tr = eps;
+    int a_rv = rv, a_mi = max_it, a_ml = max_log;
+    void* args[] = {&a_jobs, &a_n, &a_loop, &a_pref, &a_pairs, &a_md, &a_rv, &a_mi, &a_rot, &a_tr, &a_ml};
+    MM_BYTES(c, bytes);  // one sweep of every active pair; later iterations repeat it for the pairs still active
+    c.before_launch("icp_persistent_kernel");
+    MM_CUDA(cudaLaunchCooperativeKernel((const void*)icp_persistent_kernel, dim3(grid), dim3(IB), args, 0, c.stream));
+    c.after_launch();
   }
   dst.download(c, hst.data(), A);
   std::vector<long long> hlog;
@@ -358,8 +762,9 @@ void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<D
   }
 }
 
-void score_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<PairJob>& jobs,
-                 const std::vector<const float*>& T, double max_range, std::vector<double>& scores, const IcpNeighbours* nn_guess)
+void score_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<DReach>& reach,
+                 const std::vector<PairJob>& jobs, const std::vector<const float*>& T, double max_range, std::vector<double>& scores,
+                 const IcpNeighbours* nn_guess)
 {
   const int P = (int)jobs.size();
   scores.assign(P, 1.7976931348623157e308);
@@ -370,6 +775,7 @@ void score_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector
   int mx = 0;
   for (int p = 0; p < P; ++p) {
     sj[p].tgt = idx[jobs[p].b].v;
+    sj[p].reach = jobs[p].b < (int)reach.size() ? reach[jobs[p].b].v : no_reach();
     sj[p].src = clouds[jobs[p].a].pts;
     sj[p].ns = clouds[jobs[p].a].n;
     for (int k = 0; k < 16; ++k) sj[p].t[k] = T[p][k];

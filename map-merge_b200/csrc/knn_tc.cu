@@ -30,14 +30,23 @@ namespace {
 constexpr int TM = 128, TN = 128, TK = 32;  // A rows, B rows, floats per k-block (one 128-byte swizzle row = 16 dimensions, hi | lo)
 constexpr int KB_BYTES = TM * TK * 4;       // one k-block of one operand: 16 KB
 constexpr int A_RES_MAX_KB = 4;             // A stays resident in shared memory when it has at most this many k-blocks (D <= 61)
-constexpr int LIST_CAP = 64;                // candidate list entries per query row
+constexpr int LIST_CAP = 64;                // pending candidates per (query row, column half), 16-bit column indices (nb <= 65535)
+constexpr int LIST_STRIDE = LIST_CAP + 2;   // 33 words per list: appends by 32 rows (2-way) and reads of one row's 32 entries (none) stay cheap
 constexpr int KMAXTC = 16;
-constexpr int TC_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
-constexpr int LIST_BYTES = TM * LIST_CAP * 8;
-// A resident: A (<= 64 KB) + 6 B stages; otherwise 4 stages of A + B
-constexpr int STAGES_RES = 6, STAGES_STREAM = 4;
-constexpr size_t TC_SMEM_RES = (size_t)A_RES_MAX_KB * KB_BYTES + (size_t)STAGES_RES * KB_BYTES + LIST_BYTES + 1024 + 256;
-constexpr size_t TC_SMEM_STREAM = (size_t)STAGES_STREAM * 2 * KB_BYTES + LIST_BYTES + 1024 + 256;
+constexpr int EPI_WARPS = 8;                // two per scheduler: warps w and w + 4 share a TMEM lane quarter and split every tile's columns
+constexpr int TC_THREADS = 64 + EPI_WARPS * 32;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
+constexpr int LIST_BYTES = TM * 2 * LIST_STRIDE * 2;
+constexpr int PARK_BYTES = TM * KMAXTC * 8;  // the half-merge parks (distance, index) lists here: separate from the pending lists
+constexpr int APAD = 36;                    // floats per row of the shared-memory copy of the original query rows (D = 33 path)
+constexpr int AORIG_BYTES = TM * APAD * 4;
+// shared memory: [A resident (3 k-blocks for D = 33, else 4)] [B (or A + B) stages] [pending lists] [parking] [query rows] [barriers]
+__host__ __device__ constexpr int tc_a_kb(int dreg, bool a_res) { return a_res ? (dreg > 0 ? 3 : A_RES_MAX_KB) : 0; }
+__host__ __device__ constexpr int tc_stages(int dreg, bool a_res) { return a_res ? (dreg > 0 ? 6 : 5) : 4; }
+__host__ __device__ constexpr size_t tc_smem(int dreg, bool a_res)
+{
+  return (size_t)tc_a_kb(dreg, a_res) * KB_BYTES + (size_t)tc_stages(dreg, a_res) * (a_res ? 1 : 2) * KB_BYTES + LIST_BYTES + PARK_BYTES +
+         AORIG_BYTES + 1024 + 256;
+}
 
 struct TcJob {
   int a_map, b_map;  // tensor maps: A-form of a_map, B-form of b_map
@@ -47,12 +56,11 @@ struct TcJob {
   const float* origB;
   const float4* padA;  // rows padded to a multiple of 4 floats (D = 33 only), else null
   const float4* padB;
-  const float* normB;  // ||b - mean||^2
+  const float* cmaxB;  // max ||b - mean||^2 over every 32 rows of B
   int k;
-  int* dense_rows;            // rows of this job that are handed to the exact scan (D = 33 path), capacity na
-  unsigned int* dense_count;  // their number
   int* idx;     // na x k
   float* dist;  // na x k
+  float* audit; // optional na x nb: the raw accumulator (tests: error-bound audit)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------
@@ -68,12 +76,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra WAIT_DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(20000u)  // suspend-time hint (ns): the waiting thread sleeps in the barrier unit instead of spinning in the issue slots
       : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
@@ -134,60 +142,72 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t* r)
                : "memory");
 }
 
-// exact flann::L2_Simple distance on the original descriptors (sequential FP32, the order the CPU scan uses)
-template <int DREG>
-__device__ __forceinline__ float exact_dist(const float* __restrict__ a_reg, const float* __restrict__ a, const TcJob& job, int jcol, int D)
+// named barrier for the epilogue warps only (the producer / MMA warps never join it)
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
+
+__device__ __forceinline__ float fmin3(float a, float b, float c)
 {
-  float acc = 0.f;
-  if (DREG > 0) {
-    constexpr int Q = DREG > 0 ? (DREG + 3) / 4 : 1;
-    const float4* bp = job.padB + (size_t)jcol * Q;
-    float b[Q * 4];
-#pragma unroll
-    for (int t = 0; t < Q; ++t) {
-      const float4 v = __ldg(&bp[t]);
-      b[4 * t] = v.x; b[4 * t + 1] = v.y; b[4 * t + 2] = v.z; b[4 * t + 3] = v.w;
-    }
-#pragma unroll
-    for (int t = 0; t < DREG; ++t) {
-      const float diff = a_reg[t] - b[t];
-      acc += diff * diff;
-    }
-  } else {
-    const float* b = job.origB + (size_t)jcol * D;
-    for (int t = 0; t < D; ++t) {
-      const float diff = a[t] - __ldg(&b[t]);
-      acc += diff * diff;
-    }
-  }
-  return acc;
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));  // one FMNMX3 on sm_100
+  return r;
 }
 
-// One-sided bound on |approximate - exact| squared distance, relative to ||a'||^2 + ||b'||^2 of the centred descriptors:
-// dropped a_lo.b_lo and TF32 truncation of the lo parts (3 * 2^-20), FP32 accumulation inside the tensor core, FP32 norms,
-// centring; derived in DESIGN.md §3 (K9) and padded.
-constexpr float TC_ERR = 3.0e-5f;
-// The B form carries (1 - TC_ERR_STORE) ||b'||^2, so the accumulator is a LOWER bound of the exact distance minus
-// (1 - TC_ERR_STORE) ||a'||^2; TC_ERR_STORE exceeds TC_ERR by more than the rounding of that product.
-constexpr float TC_ERR_STORE = 3.1e-5f;
+// Error model of the filter (validated on the device by tests/test_full_size_gpu.py::test_tensor_core_knn_error_bound, which
+// reads the raw accumulators back through mm3d_knn_tc_audit):
+//   acc(i, j) = (1 - ES) ||b'_j||^2 - 2 a'_i . b'_j     as the tensor core delivers it (a', b' = descriptors minus the common mean)
+//   v(i, j)   = acc(i, j) + (1 - ES) ||a'_i||^2
+//   v(i, j) <= d(i, j) <= v(i, j) + 2 ES (||a'_i||^2 + ||b'_j||^2)      d = the sequential FP32 distance of the exact scan
+// The true deviation of the dot product has three parts: the dropped lo.lo products and the TF32 truncation of the lo parts
+// (|x_lo| <= 2^-11 |x|, truncated to 11 bits: <= (2^-22 + 2 * 2^-21) |a_k||b_k| per dimension, i.e. <= 1.2e-6 ||a'|| ||b'||), the
+// FP32 accumulation inside the tensor core (18 chained MMAs of 8 products; each partial sum is bounded by ||b'||^2 + 2 ||a'|| ||b'||),
+// and the FP32 rounding of the norms and of d itself (<= 35 * 2^-24 relative).  With 2 ||a'|| ||b'|| <= ||a'||^2 + ||b'||^2 the sum
+// of the three stays below EG (||a'||^2 + ||b'||^2); ES = EG + margin, so v is a lower bound and v + 2 ES (...) an upper bound.
+constexpr float TC_ERR_STORE = 3.1e-5f;  // ES
+
+// Insertion of (d, j) into a list sorted by (distance, arrival): candidates arrive in ascending column order, so a new
+// element goes behind every element with an equal distance (strict <), and from its slot on the displaced elements shift
+// down UNCONDITIONALLY — comparing them again would let a displaced element lose against an equal neighbour that sat
+// behind it (two identical descriptors: the higher column would overtake the lower one).  Result: the brute-force scan's
+// (distance, index) order.
+template <int KCAP>
+__device__ __forceinline__ void topk_insert(float (&bd)[KCAP], int (&bi)[KCAP], float cd, int ci)
+{
+  bool shifting = false;
+#pragma unroll
+  for (int u = 0; u < KCAP; ++u) {
+    if (shifting || cd < bd[u]) {
+      const float td = bd[u];
+      const int ti = bi[u];
+      bd[u] = cd;
+      bi[u] = ci;
+      cd = td;
+      ci = ti;
+      shifting = true;
+    }
+  }
+}
 
 // KCAP = capacity of the register top lists (>= k; the first k are written out); DREG = descriptor length when the query
-// row is cached in registers (and rows are read as float4 from the padded copies), 0 = scalar reads from global memory;
-// A_RES = the A tile stays in shared memory for the whole CTA (kblocks <= A_RES_MAX_KB).
-template <int KCAP, int DREG, bool A_RES>
+// rows sit in shared memory and rows are read as float4 from the padded copies, 0 = scalar reads from global memory;
+// A_RES = the A tile stays in shared memory for the whole CTA (kblocks <= A_RES_MAX_KB); AUDIT = also dump the accumulators.
+template <int KCAP, int DREG, bool A_RES, bool AUDIT>
 __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __restrict__ jobs, const CUtensorMap* __restrict__ mapsA,
                                                               const CUtensorMap* __restrict__ mapsB, int kblocks, int D,
                                                               unsigned long long* __restrict__ stats)
 {
-  constexpr int STAGES = A_RES ? STAGES_RES : STAGES_STREAM;
+  constexpr int STAGES = tc_stages(DREG, A_RES);
   constexpr int STAGE_BYTES = A_RES ? KB_BYTES : 2 * KB_BYTES;
-  constexpr int A_RES_BYTES = A_RES ? A_RES_MAX_KB * KB_BYTES : 0;
+  constexpr int A_RES_BYTES = tc_a_kb(DREG, A_RES) * KB_BYTES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* a_res = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by OFFSET, so that every pointer below stays a shared-memory pointer for the compiler (rounding the
+  // address through uintptr_t turned all list / query-row accesses into generic LD.E / ST.E)
+  uint8_t* a_res = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* tiles = a_res + A_RES_BYTES;
-  float* list_v = (float*)(tiles + (size_t)STAGES * STAGE_BYTES);  // [LIST_CAP][TM]
-  int* list_j = (int*)(list_v + TM * LIST_CAP);
-  uint64_t* full_bar = (uint64_t*)(list_j + TM * LIST_CAP);
+  unsigned short* list = (unsigned short*)(tiles + (size_t)STAGES * STAGE_BYTES);  // [TM][2][LIST_STRIDE]
+  float* park_d = (float*)(list + TM * 2 * LIST_STRIDE);                           // [TM][KCAP] distances, then indices
+  int* park_i = (int*)(park_d + TM * KMAXTC);
+  float* a_orig = (float*)(park_i + TM * KMAXTC);                                  // [TM][APAD] (D = 33 path)
+  uint64_t* full_bar = (uint64_t*)(a_orig + TM * APAD);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -207,7 +227,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty[b], EPI_WARPS);  // one arrival per epilogue warp
     }
     mbar_init(a_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -277,18 +297,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
       }
     }
   } else {
-    // ===== epilogue: one query row per thread =====
-    // The accumulator holds acc = (1 - e) ||b'||^2 - 2 a'.b' (the scaled norm rides along as three extra dimensions), a
-    // lower bound of (exact distance - (1 - e) ||a'||^2); acc + 2 e (||a'||^2 + ||b'||^2) is an upper bound.  Per row:
-    //   * t5[]: the KCAP smallest UPPER bounds seen so far; a column can be among the exact nearest only if its lower
-    //     bound acc <= t5[KCAP-1], so only those columns are appended to the row's list (the error term is per column:
-    //     a far column with a large norm does not loosen the bound for the near ones);
-    //   * the list is compacted against the (shrinking) bound when it runs low on room; if that does not help — ties:
-    //     clustered or duplicated descriptors — the row goes to the exact scan (D = 33) or the listed columns are
-    //     evaluated EXACTLY there and then ("early flush"), after which the exact k-th distance bounds acc directly;
-    //   * after the last tile the survivors are evaluated exactly, in ascending column order with strict <, which is
-    //     the brute-force scan's (distance, index) order bit for bit.
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===== epilogue: one query row per thread, two warps per TMEM lane quarter (each takes 64 of a tile's 128 columns) =====
+    // Per (row, column half):
+    //   * t5[]: the KCAP smallest UPPER bounds seen so far, fed with one value per 32-column chunk — the chunk's smallest
+    //     accumulator plus the error term of the chunk's largest norm.  Chunk minima belong to distinct columns, so their
+    //     KCAP-th smallest upper bound bounds the row's k-th nearest distance; thr = min(that, the exact k-th distance so far);
+    //   * a column can be among the exact nearest only if its lower bound acc <= thr: such columns are appended (index
+    //     only) to the row's pending list in shared memory.  The common case — no column of the chunk passes — costs the
+    //     min tree (16 three-input minima) and ten min/max for the bound, no branch per column;
+    //   * when a list holds 32 candidates the WARP evaluates them together: lane c computes the exact sequential FP32
+    //     distance of candidate c (query row broadcast from shared memory, B row as float4 loads), the few that beat the
+    //     row's current k-th distance are inserted by the owning lane in ascending column order with strict <, which is
+    //     the brute-force scan's (distance, index) order bit for bit.  Tie-heavy rows (clustered descriptors: hundreds of
+    //     columns inside the error margin of the k-th distance) therefore cost one full-warp evaluation per 32 ties
+    //     instead of diverged per-lane work or a brute-force fallback.
+    const int ew = warp - 2;
+    const int q = warp & 3;        // TMEM lane quarter this warp may access
+    const int half = ew >> 2;      // which 64 columns of every tile
     const int lrow = q * 32 + lane;
     const int row = m0 + lrow;
     const bool live = row < job.na;
@@ -299,139 +324,192 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
     int bi[KCAP];
 #pragma unroll
     for (int i = 0; i < KCAP; ++i) { t5[i] = INF; bd[i] = INF; bi[i] = -1; }
-    const float* a = job.origA + (size_t)(live ? row : 0) * D;
-    float areg[DREG > 0 ? DREG : 1];
+    // shared copy of the original query rows (D = 33 path)
     if (DREG > 0) {
-      constexpr int Q = DREG > 0 ? (DREG + 3) / 4 : 1;
-      const float4* ap = job.padA + (size_t)(live ? row : 0) * Q;
-      float tmp[Q * 4];
-#pragma unroll
-      for (int t = 0; t < Q; ++t) {
-        const float4 v = ap[t];
-        tmp[4 * t] = v.x; tmp[4 * t + 1] = v.y; tmp[4 * t + 2] = v.z; tmp[4 * t + 3] = v.w;
+      for (int e = (ew * 32 + lane); e < TM * (APAD / 4); e += EPI_WARPS * 32) {
+        const int r = e / (APAD / 4), t = e - r * (APAD / 4);
+        const float4 v = (m0 + r < job.na) ? job.padA[(size_t)(m0 + r) * (APAD / 4) + t] : make_float4(0.f, 0.f, 0.f, 0.f);
+        reinterpret_cast<float4*>(a_orig)[r * (APAD / 4) + t] = v;
       }
-#pragma unroll
-      for (int t = 0; t < DREG; ++t) areg[t] = tmp[t];
+      epi_bar_sync();
     }
-    float thr = live ? INF : -INF;   // acc-space filter bound, only ever shrinks
+    float thr = live ? INF : -INF;  // acc-space filter bound, only ever shrinks
     float thr_exact = INF;
-    bool dense = false;  // D = 33 path: the row is tie-heavy and goes to the exact scan instead
     int n = 0;
-    unsigned evals = 0, early = 0;
-    float* lv = list_v + lrow;
-    int* lj = list_j + lrow;
+    unsigned evals = 0, flushes = 0;
+    unsigned short* my_list = list + (lrow * 2 + half) * LIST_STRIDE;
+
+    // the warp evaluates up to 32 pending candidates of lane L's row exactly and merges them into L's top list
+    auto flush = [&](int L) {
+      const int nL = __shfl_sync(0xffffffffu, n, L);
+      const int cnt = min(nL, 32);
+      const int rL = q * 32 + L;
+      unsigned short* lst = list + (rL * 2 + half) * LIST_STRIDE;
+      const int jcol = lane < cnt ? (int)lst[lane] : 0;
+      float d = INF;
+      if (lane < cnt) {
+        float acc = 0.f;
+        if (DREG > 0) {
+          constexpr int Q = DREG > 0 ? (DREG + 3) / 4 : 1;
+          const float4* bp = job.padB + (size_t)jcol * Q;
+          const float4* ap = reinterpret_cast<const float4*>(a_orig + rL * APAD);
+          float a_[Q * 4], b_[Q * 4];
+#pragma unroll
+          for (int t = 0; t < Q; ++t) {
+            const float4 v = __ldg(&bp[t]);
+            b_[4 * t] = v.x; b_[4 * t + 1] = v.y; b_[4 * t + 2] = v.z; b_[4 * t + 3] = v.w;
+            const float4 w = ap[t];
+            a_[4 * t] = w.x; a_[4 * t + 1] = w.y; a_[4 * t + 2] = w.z; a_[4 * t + 3] = w.w;
+          }
+#pragma unroll
+          for (int t = 0; t < DREG; ++t) {
+            const float diff = a_[t] - b_[t];
+            acc += diff * diff;
+          }
+        } else {
+          const float* a = job.origA + (size_t)(m0 + rL) * D;
+          const float* b = job.origB + (size_t)jcol * D;
+          for (int t = 0; t < D; ++t) {
+            const float diff = __ldg(&a[t]) - __ldg(&b[t]);
+            acc += diff * diff;
+          }
+        }
+        d = acc;
+      }
+      const float kth = __shfl_sync(0xffffffffu, bd[KCAP - 1], L);
+      unsigned better = __ballot_sync(0xffffffffu, d < kth);
+      while (better) {
+        const int b = __ffs(better) - 1;
+        const float dv = __shfl_sync(0xffffffffu, d, b);
+        const int jv = __shfl_sync(0xffffffffu, jcol, b);
+        if (lane == L) topk_insert<KCAP>(bd, bi, dv, jv);
+        // the k-th distance just shrank: candidates that no longer beat it drop out (in the first flushes most of the 32 do)
+        const float kth2 = __shfl_sync(0xffffffffu, bd[KCAP - 1], L);
+        better &= __ballot_sync(0xffffffffu, d < kth2) & ~((2u << b) - 1u);
+      }
+      // the rest of the list moves to the front
+      const int rest = nL - cnt;
+      unsigned short moved = 0;
+      if (lane < rest) moved = lst[32 + lane];
+      __syncwarp();
+      if (lane < rest) lst[lane] = moved;
+      __syncwarp();
+      if (lane == L) {
+        n = rest;
+        evals += (unsigned)cnt;
+        ++flushes;
+        thr_exact = (bd[KCAP - 1] - na_low) + 1e-6f * (1.0f + fabsf(bd[KCAP - 1]) + na);  // acc <= exact k-th - na_low (+ rounding pad)
+        thr = fminf(thr, thr_exact);
+      }
+    };
 
     const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int n_chunks = n_tiles * (TN / 32);
+    const int n_chunks = n_tiles * 2;  // this warp's chunks: two per tile
     uint32_t r[32], rn[32];
-    // chunk = 32 columns of one tile; the next chunk's TMEM load is in flight while the current one is filtered
     mbar_wait(&tmem_full[0], 0);
     tc_fence_after();
-    tmem_ld_32x32_issue(tmem_row, r);
+    // Seed the running bound from tile 0 before anything is listed (otherwise the first chunk, filtered against an infinite
+    // bound, would send all its 32 columns of every row through an exact evaluation): one upper bound per 4 columns of this
+    // half's 64 = 16 bounds >= KCAP.  The main loop then skips the bound update for tile 0 (a column must not count twice).
+#pragma unroll 1
+    for (int sc = 0; sc < 2; ++sc) {
+      tmem_ld_32x32_issue(tmem_row + (uint32_t)(half * 64 + sc * 32), r);
+      tmem_ld_wait(r);
+      const int jbase = half * 64 + sc * 32;
+      const int left = job.nb - jbase;
+      if (left < 32) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c >= left) r[c] = 0x7f800000u;
+      }
+      if (left > 0) {
+        const float e = (2.0f * TC_ERR_STORE) * (na + __ldg(&job.cmaxB[jbase >> 5]));
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float m4 = fminf(fmin3(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2])),
+                                 __uint_as_float(r[4 * g + 3]));
+          float ub = m4 + (e + 1e-6f * (1.0f + fabsf(m4)));
+#pragma unroll
+          for (int t = 0; t < KCAP; ++t) {
+            const float lo_ = fminf(t5[t], ub);
+            ub = fmaxf(t5[t], ub);
+            t5[t] = lo_;
+          }
+        }
+      }
+    }
+    thr = fminf(thr, t5[KCAP - 1]);
+    tmem_ld_32x32_issue(tmem_row + (uint32_t)(half * 64), r);
     tmem_ld_wait(r);
     for (int ch = 0; ch < n_chunks; ++ch) {
-      const int nt = ch >> 2, c0 = (ch & 3) * 32;
-      const bool tile_end = (ch & 3) == 3;
+      const int nt = ch >> 1, c0 = half * 64 + (ch & 1) * 32;
+      const bool tile_end = (ch & 1) == 1;
       if (ch + 1 < n_chunks) {
-        const int nt1 = (ch + 1) >> 2, buf1 = nt1 & 1;
+        const int nt1 = (ch + 1) >> 1, buf1 = nt1 & 1;
         if (tile_end) {
           mbar_wait(&tmem_full[buf1], (uint32_t)(nt1 >> 1) & 1u);
           tc_fence_after();
         }
-        tmem_ld_32x32_issue(tmem_row + (uint32_t)(buf1 * TN + ((ch + 1) & 3) * 32), rn);
+        tmem_ld_32x32_issue(tmem_row + (uint32_t)(buf1 * TN + half * 64 + ((ch + 1) & 1) * 32), rn);
       }
-      // ---- filter: one compare per column, four independent mask chains
-      uint32_t m0_ = 0, m1_ = 0, m2_ = 0, m3_ = 0;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        m0_ |= (__uint_as_float(r[c]) <= thr) ? (1u << c) : 0u;
-        m1_ |= (__uint_as_float(r[8 + c]) <= thr) ? (1u << (8 + c)) : 0u;
-        m2_ |= (__uint_as_float(r[16 + c]) <= thr) ? (1u << (16 + c)) : 0u;
-        m3_ |= (__uint_as_float(r[24 + c]) <= thr) ? (1u << (24 + c)) : 0u;
-      }
-      uint32_t mask = (m0_ | m1_) | (m2_ | m3_);
       const int jbase = nt * TN + c0;
-      const int left = job.nb - jbase;  // columns past nb are zero rows of the B form
-      if (left < 32) mask &= left <= 0 ? 0u : ((1u << left) - 1u);
-      // (marking a row dense as soon as one chunk passes >= 8 columns was measured: no faster on config 2, and 25 % false
-      //  positives on small sets, where the bound is still loose after 128 columns)
-      while (mask) {
-        const int c = __ffs(mask) - 1;
-        mask &= mask - 1;
-        // r[c] without dynamic register indexing: a 5-level select tree
-        float s16[16], s8[8], s4[4], s2[2];
+      const int left = job.nb - jbase;  // columns past nb are zero rows of the B form: keep them out of the minimum
+      if (AUDIT) {
+        if (live) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) s16[i] = __uint_as_float((c & 1) ? r[2 * i + 1] : r[2 * i]);
+          for (int c = 0; c < 32; ++c)
+            if (c < left) job.audit[(size_t)row * job.nb + jbase + c] = __uint_as_float(r[c]);
+        }
+      }
+      if (left < 32) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s8[i] = (c & 2) ? s16[2 * i + 1] : s16[2 * i];
+        for (int c = 0; c < 32; ++c)
+          if (c >= left) r[c] = 0x7f800000u;
+      }
+      if (left > 0) {
+        // smallest accumulator of the chunk: 16 three-input minima
+        float m = fmin3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
 #pragma unroll
-        for (int i = 0; i < 4; ++i) s4[i] = (c & 4) ? s8[2 * i + 1] : s8[2 * i];
+        for (int c = 3; c < 31; c += 2) m = fmin3(m, __uint_as_float(r[c]), __uint_as_float(r[c + 1]));
+        m = fminf(m, __uint_as_float(r[31]));
+        // its upper bound in acc space (the chunk's largest norm bounds every column's error term) feeds the running bound
+        if (ch >= 2) {  // tile 0 seeded the bound already
+          const float cmax = __ldg(&job.cmaxB[jbase >> 5]);
+          float ub = m + ((2.0f * TC_ERR_STORE) * (na + cmax) + 1e-6f * (1.0f + fabsf(m)));
 #pragma unroll
-        for (int i = 0; i < 2; ++i) s2[i] = (c & 8) ? s4[2 * i + 1] : s4[2 * i];
-        const float v = (c & 16) ? s2[1] : s2[0];
-        if (v <= thr) {  // thr may have shrunk since the mask was built
-          lv[n * TM] = v;
-          lj[n * TM] = jbase + c;
-          ++n;
-          // upper bound of this column in acc space
-          const float up = v + (2.0f * TC_ERR_STORE) * (na + __ldg(&job.normB[jbase + c])) + 1e-6f;
-          if (up < t5[KCAP - 1]) {
-            float cv = up;
+          for (int t = 0; t < KCAP; ++t) {
+            const float lo_ = fminf(t5[t], ub);
+            ub = fmaxf(t5[t], ub);
+            t5[t] = lo_;
+          }
+          thr = fminf(thr, t5[KCAP - 1]);
+        }
+        if (m <= thr) {
+          // which columns pass (one compare + one bit each), then one append per set bit
+          uint32_t m0_ = 0, m1_ = 0, m2_ = 0, m3_ = 0;
 #pragma unroll
-            for (int t = 0; t < KCAP; ++t) {
-              const float lo_ = fminf(t5[t], cv);
-              cv = fmaxf(t5[t], cv);
-              t5[t] = lo_;
-            }
-            thr = fminf(t5[KCAP - 1], thr_exact);
+          for (int c = 0; c < 8; ++c) {
+            m0_ |= (__uint_as_float(r[c]) <= thr) ? (1u << c) : 0u;
+            m1_ |= (__uint_as_float(r[8 + c]) <= thr) ? (1u << (8 + c)) : 0u;
+            m2_ |= (__uint_as_float(r[16 + c]) <= thr) ? (1u << (16 + c)) : 0u;
+            m3_ |= (__uint_as_float(r[24 + c]) <= thr) ? (1u << (24 + c)) : 0u;
+          }
+          uint32_t msk = (m0_ | m1_) | (m2_ | m3_);
+          if (left < 32) msk &= (1u << left) - 1u;  // columns past nb (masked to +inf above) would still pass an infinite bound
+          while (msk) {
+            const int c = __ffs(msk) - 1;
+            msk &= msk - 1;
+            my_list[n++] = (unsigned short)(jbase + c);
           }
         }
       }
-      const bool last = ch == n_chunks - 1;
-      if (n > LIST_CAP - 32 || (last && live)) {
-        int w = 0;
-        for (int t = 0; t < n; ++t) {
-          const float v = lv[t * TM];
-          if (v <= thr) {
-            lv[w * TM] = v;
-            lj[w * TM] = lj[t * TM];
-            ++w;
-          }
-        }
-        n = w;
-        if (DREG > 0 && n > LIST_CAP - 32 && !last) {
-          // more than LIST_CAP - 32 columns tie with the k-th nearest inside the error margin (clustered descriptors):
-          // evaluating them here would stall the pipeline on a few diverged lanes — the exact scan kernel takes the row
-          dense = true;
-          ++early;
-          n = 0;
-          thr = -INF;
-        } else if (n > LIST_CAP - 32 || last) {
-          if (!last) ++early;
-          for (int t = 0; t < n; ++t) {
-            const int jcol = lj[t * TM];
-            const float d = exact_dist<DREG>(areg, a, job, jcol, D);
-            ++evals;
-            if (d < bd[KCAP - 1]) {
-              float cd = d;
-              int ci = jcol;
-#pragma unroll
-              for (int u = 0; u < KCAP; ++u) {  // strict <: an equal distance stays behind the lower column already there
-                if (cd < bd[u]) {
-                  const float td = bd[u];
-                  const int ti = bi[u];
-                  bd[u] = cd;
-                  bi[u] = ci;
-                  cd = td;
-                  ci = ti;
-                }
-              }
-            }
-          }
-          n = 0;
-          thr_exact = (bd[KCAP - 1] - na_low) + 1e-6f * (1.0f + fabsf(bd[KCAP - 1]) + na);  // acc <= exact k-th - na_low (+ rounding pad)
-          thr = fminf(thr, thr_exact);
-        }
+      __syncwarp();
+      // full lists are evaluated by the whole warp
+      unsigned full = __ballot_sync(0xffffffffu, n >= 32);
+      while (full) {
+        const int L = __ffs(full) - 1;
+        flush(L);
+        full = __ballot_sync(0xffffffffu, n >= 32);
       }
       tmem_ld_wait(rn);  // rn has landed (and, at a tile end, every read of this tile's accumulator is done)
       if (tile_end) {
@@ -442,24 +520,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
 #pragma unroll
       for (int c = 0; c < 32; ++c) r[c] = rn[c];
     }
-    if (live && dense) {
-      job.dense_rows[atomicAdd(job.dense_count, 1u)] = row;
-    } else if (live) {
-      const int k = job.k;
+    // what is still pending
+    unsigned pending = __ballot_sync(0xffffffffu, n > 0);
+    while (pending) {
+      const int L = __ffs(pending) - 1;
+      flush(L);
+      pending = __ballot_sync(0xffffffffu, n > 0);
+    }
+    // merge the two column halves of every row: half 1 parks its list in shared memory (the pending lists are empty now)
+    epi_bar_sync();
+    if (half == 1) {
 #pragma unroll
-      for (int t = 0; t < KCAP; ++t)
-        if (t < k) {
-          job.idx[(size_t)row * k + t] = bi[t];
-          job.dist[(size_t)row * k + t] = bi[t] >= 0 ? bd[t] : 0.f;
+      for (int t = 0; t < KCAP; ++t) {
+        park_d[lrow * KCAP + t] = bd[t];
+        park_i[lrow * KCAP + t] = bi[t];
+      }
+    }
+    epi_bar_sync();
+    if (half == 0 && live) {
+      const int k = job.k;
+      int ia = 0, ib = 0;
+      for (int t = 0; t < k; ++t) {
+        // the smaller (distance, index) of the two heads
+        float da = INF, db = INF;
+        int ja = -1, jb = -1;
+#pragma unroll
+        for (int u = 0; u < KCAP; ++u) {
+          if (u == ia) { da = bd[u]; ja = bi[u]; }
         }
+        if (ib < KCAP) { db = park_d[lrow * KCAP + ib]; jb = park_i[lrow * KCAP + ib]; }
+        const bool take_b = jb >= 0 && (ja < 0 || db < da || (db == da && jb < ja));
+        const float dsel = take_b ? db : da;
+        const int jsel = take_b ? jb : ja;
+        if (take_b) ++ib; else ++ia;
+        job.idx[(size_t)row * k + t] = jsel;
+        job.dist[(size_t)row * k + t] = jsel >= 0 ? dsel : 0.f;
+      }
     }
     if (stats) {
-      const unsigned rows = __reduce_add_sync(0xffffffffu, live ? 1u : 0u);
-      const unsigned ef = __reduce_add_sync(0xffffffffu, live ? early : 0u);
+      const unsigned rows = __reduce_add_sync(0xffffffffu, (live && half == 0) ? 1u : 0u);
+      const unsigned fl = __reduce_add_sync(0xffffffffu, live ? flushes : 0u);
       const unsigned ev = __reduce_add_sync(0xffffffffu, live ? evals : 0u);
       if (lane == 0) {
         atomicAdd(&stats[0], (unsigned long long)rows);
-        atomicAdd(&stats[1], (unsigned long long)ef);
+        atomicAdd(&stats[1], (unsigned long long)fl);
         atomicAdd(&stats[2], (unsigned long long)ev);
       }
     }
@@ -469,81 +573,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
-  }
-}
-
-// Exact FP32 scan of the rows the tensor-core pass handed over (same arithmetic and tie order as knn_small_kernel in
-// matching.cu): one thread per listed row, B streams through shared memory dimension-major.
-template <int D, int K>
-__global__ void __launch_bounds__(128) knn_dense_rows_kernel(const TcJob* __restrict__ jobs)
-{
-  constexpr int TB = 64;
-  __shared__ __align__(16) float sb[D * TB];
-  const TcJob j = jobs[blockIdx.y];
-  const int n_dense = (int)*j.dense_count;
-  if ((int)(blockIdx.x * blockDim.x) >= n_dense) return;
-  const int li = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = li < n_dense;
-  const int row = live ? j.dense_rows[li] : 0;
-  float a[D];
-#pragma unroll
-  for (int t = 0; t < D; ++t) a[t] = live ? j.origA[(size_t)row * D + t] : 0.f;
-  float bd[K];
-  int bi[K];
-#pragma unroll
-  for (int t = 0; t < K; ++t) {
-    bd[t] = __int_as_float(0x7f800000);
-    bi[t] = -1;
-  }
-  for (int base = 0; base < j.nb; base += TB) {
-    const int tb = min(TB, j.nb - base);
-    __syncthreads();
-    for (int e = threadIdx.x; e < TB * D; e += blockDim.x) {
-      const int r = e / D, t = e - r * D;
-      sb[t * TB + r] = (r < tb) ? j.origB[(size_t)(base + r) * D + t] : 0.f;
-    }
-    __syncthreads();
-    if (!live) continue;
-    for (int r0 = 0; r0 < tb; r0 += 4) {
-      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-#pragma unroll
-      for (int t = 0; t < D; ++t) {
-        const float4 b = *reinterpret_cast<const float4*>(&sb[t * TB + r0]);
-        const float d0 = a[t] - b.x, d1 = a[t] - b.y, d2 = a[t] - b.z, d3 = a[t] - b.w;
-        acc0 += d0 * d0;
-        acc1 += d1 * d1;
-        acc2 += d2 * d2;
-        acc3 += d3 * d3;
-      }
-      const float accs[4] = {acc0, acc1, acc2, acc3};
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float cd = accs[u];
-        if (r0 + u < tb && cd < bd[K - 1]) {
-          int ci = base + r0 + u;
-#pragma unroll
-          for (int t = 0; t < K; ++t) {  // strict <: ties keep the lower column
-            if (cd < bd[t]) {
-              const float td = bd[t];
-              const int ti = bi[t];
-              bd[t] = cd;
-              bi[t] = ci;
-              cd = td;
-              ci = ti;
-            }
-          }
-        }
-      }
-    }
-  }
-  if (live) {
-    const int k = j.k;
-#pragma unroll
-    for (int t = 0; t < K; ++t)
-      if (t < k) {
-        j.idx[(size_t)row * k + t] = bi[t];
-        j.dist[(size_t)row * k + t] = bi[t] >= 0 ? bd[t] : 0.f;
-      }
   }
 }
 
@@ -625,6 +654,23 @@ __global__ void __launch_bounds__(128) knn_tc_prep_kernel(const PrepJob* __restr
     for (int t = threadIdx.x; t < padw; t += blockDim.x) j.pad[(size_t)row * padw + t] = t < D ? a[t] : 0.f;
 }
 
+// largest centred norm of every 32 rows (one epilogue chunk): bounds the error term of all columns of the chunk
+struct CmaxJob {
+  const float* norm;
+  float* cmax;
+  int n;
+};
+__global__ void __launch_bounds__(128) knn_tc_cmax_kernel(const CmaxJob* __restrict__ jobs)
+{
+  const CmaxJob& j = jobs[blockIdx.y];
+  const int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (chunk * 32 >= j.n) return;
+  const int r = chunk * 32 + lane;
+  float v = r < j.n ? j.norm[r] : 0.f;
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (lane == 0) j.cmax[chunk] = v;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -658,30 +704,36 @@ CUtensorMap make_map(float* base, int rows, int Kp)
 }  // namespace
 
 // Same contract as the brute-force kernels: idx / dist hold, per row of A, the k nearest rows of B sorted by (distance, index).
-void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vector<int>& n_rows, int D, const std::vector<KnnProblem>& probs)
+// audit (tests only, one problem): receives the raw accumulators (na x nb), the centred norms of both sides and ES.
+void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vector<int>& n_rows, int D, const std::vector<KnnProblem>& probs,
+                  KnnAudit* audit)
 {
   if (probs.empty()) return;
   const int M = (int)desc.size();
   const int kblocks = (D + 3 + 15) / 16;
   const int Kp = kblocks * TK;
   const bool reg_path = D == 33;
-  const int padw = reg_path ? 36 : 0;
+  const int padw = reg_path ? APAD : 0;
   std::vector<char> used(M, 0);
   for (const KnnProblem& p : probs) { used[p.a] = 1; used[p.b] = 1; }
-  std::vector<DBuf<float>> formA(M), formB(M), norm(M), pad(M);
+  std::vector<DBuf<float>> formA(M), formB(M), norm(M), pad(M), cmax(M);
   std::vector<PrepJob> pj;
+  std::vector<CmaxJob> cj;
   int mxn = 0;
   for (int m = 0; m < M; ++m) {
     if (!used[m] || n_rows[m] == 0) continue;
     formA[m].alloc(c, (size_t)n_rows[m] * Kp);
     formB[m].alloc(c, (size_t)n_rows[m] * Kp);
     norm[m].alloc(c, n_rows[m]);
+    cmax[m].alloc(c, (size_t)(n_rows[m] + 31) / 32);
     if (reg_path) pad[m].alloc(c, (size_t)n_rows[m] * padw);
     pj.push_back(PrepJob{desc[m], formA[m].p, formB[m].p, norm[m].p, reg_path ? pad[m].p : nullptr, n_rows[m]});
+    cj.push_back(CmaxJob{norm[m].p, cmax[m].p, n_rows[m]});
     mxn = std::max(mxn, n_rows[m]);
   }
   if (pj.empty()) return;
   DBuf<PrepJob> dpj = to_device(c, pj);
+  DBuf<CmaxJob> dcj = to_device(c, cj);
   size_t rows_all = 0;
   for (const PrepJob& j : pj) rows_all += (size_t)j.n;
   DBuf<double> partial(c, pj.size() * MEAN_CHUNKS * (size_t)D);
@@ -689,6 +741,7 @@ void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vect
   MM_LAUNCH(c, knn_tc_mean_partial_kernel, dim3(MEAN_CHUNKS, (unsigned)pj.size()), 128, 0, dpj.p, D, partial.p);
   MM_LAUNCH(c, knn_tc_mean_kernel, (D + 127) / 128, 128, 0, partial.p, (int)pj.size() * MEAN_CHUNKS, D, 1.0 / (double)rows_all, mean.p);
   MM_LAUNCH(c, knn_tc_prep_kernel, dim3(mxn, (unsigned)pj.size()), 128, 0, dpj.p, mean.p, D, Kp, padw);
+  MM_LAUNCH(c, knn_tc_cmax_kernel, dim3((mxn + 127) / 128, (unsigned)cj.size()), 128, 0, dcj.p);
   std::vector<CUtensorMap> hA(M), hB(M);
   for (int m = 0; m < M; ++m) {
     if (!used[m] || n_rows[m] == 0) {
@@ -703,19 +756,10 @@ void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vect
   std::vector<TcJob> tj;
   int max_na = 0, kmax = 0;
   double bytes = 0;
-  size_t rows_total = 0, n_jobs = 0;
-  for (const KnnProblem& p : probs)
-    if (p.na > 0 && n_rows[p.b] > 0) { rows_total += (size_t)p.na; ++n_jobs; }
-  DBuf<int> dense_rows(c, reg_path ? rows_total : 0);
-  DBuf<unsigned int> dense_count(c, n_jobs);
-  dense_count.zero(c);
-  size_t row_off = 0;
+  DBuf<float> audit_acc;
   for (const KnnProblem& p : probs) {
     if (p.na == 0 || n_rows[p.b] == 0) continue;
     TcJob j;
-    j.dense_rows = reg_path ? dense_rows.p + row_off : nullptr;
-    j.dense_count = dense_count.p + tj.size();
-    row_off += (size_t)p.na;
     j.a_map = p.a;
     j.b_map = p.b;
     j.na = p.na;
@@ -725,16 +769,22 @@ void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vect
     j.origB = desc[p.b];
     j.padA = reg_path ? (const float4*)pad[p.a].p : nullptr;
     j.padB = reg_path ? (const float4*)pad[p.b].p : nullptr;
-    j.normB = norm[p.b].p;
+    j.cmaxB = cmax[p.b].p;
     j.k = p.k;
     j.idx = p.idx;
     j.dist = p.dist;
+    j.audit = nullptr;
     tj.push_back(j);
     max_na = std::max(max_na, p.na);
     kmax = std::max(kmax, p.k);
     bytes += 4.0 * D * ((double)j.na + j.nb) + 8.0 * j.k * j.na;
   }
   if (tj.empty()) return;
+  const bool do_audit = audit && tj.size() == 1 && reg_path && kmax <= 5;
+  if (do_audit) {
+    audit_acc.alloc(c, (size_t)tj[0].na * tj[0].nb);
+    tj[0].audit = audit_acc.p;
+  }
   DBuf<TcJob> dtj = to_device(c, tj);
   MM_BYTES(c, bytes);
   if (!c.knn_stats) {
@@ -742,32 +792,33 @@ void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vect
     MM_CUDA(cudaMemsetAsync(c.knn_stats, 0, 3 * sizeof(unsigned long long), c.stream));
   }
   const dim3 grid((max_na + TM - 1) / TM, (unsigned)tj.size());
-#define MM_TC(KCAP, DREG, RES)                                                                                                   \
-  do {                                                                                                                           \
-    const size_t smem = RES ? TC_SMEM_RES : TC_SMEM_STREAM;                                                                      \
-    /* per device and cheap: set on every call (a process may drive several GPUs) */                                            \
-    MM_CUDA(cudaFuncSetAttribute(knn_tc_kernel<KCAP, DREG, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-    MM_LAUNCH(c, (knn_tc_kernel<KCAP, DREG, RES>), grid, TC_THREADS, smem, dtj.p, dA.p, dB.p, kblocks, D, c.knn_stats);          \
+#define MM_TC(KCAP, DREG, RES, AUD)                                                                                                    \
+  do {                                                                                                                                 \
+    const size_t smem = tc_smem(DREG, RES);                                                                                            \
+    /* per device and cheap: set on every call (a process may drive several GPUs) */                                                  \
+    MM_CUDA(cudaFuncSetAttribute(knn_tc_kernel<KCAP, DREG, RES, AUD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+    MM_LAUNCH(c, (knn_tc_kernel<KCAP, DREG, RES, AUD>), grid, TC_THREADS, smem, dtj.p, dA.p, dB.p, kblocks, D, c.knn_stats);           \
   } while (0)
   const bool res = kblocks <= A_RES_MAX_KB;
-  const dim3 dgrid((max_na + 127) / 128, (unsigned)tj.size());  // blocks past a job's dense count exit at once
-  if (reg_path && kmax <= 5) {
-    MM_TC(5, 33, true);
-    MM_LAUNCH(c, (knn_dense_rows_kernel<33, 5>), dgrid, 128, 0, dtj.p);
-  } else if (reg_path && kmax <= 10) {
-    MM_TC(10, 33, true);
-    MM_LAUNCH(c, (knn_dense_rows_kernel<33, 10>), dgrid, 128, 0, dtj.p);
-  } else if (reg_path) {
-    MM_TC(KMAXTC, 33, true);
-    MM_LAUNCH(c, (knn_dense_rows_kernel<33, KMAXTC>), dgrid, 128, 0, dtj.p);
-  }
-  else if (res && kmax <= 5) MM_TC(5, 0, true);
-  else if (res) MM_TC(KMAXTC, 0, true);
-  else if (kmax <= 1) MM_TC(1, 0, false);
-  else if (kmax <= 5) MM_TC(5, 0, false);
-  else if (kmax <= 10) MM_TC(10, 0, false);
-  else MM_TC(KMAXTC, 0, false);
+  if (do_audit) MM_TC(5, 33, true, true);
+  else if (reg_path && kmax <= 5) MM_TC(5, 33, true, false);
+  else if (reg_path && kmax <= 10) MM_TC(10, 33, true, false);
+  else if (reg_path) MM_TC(KMAXTC, 33, true, false);
+  else if (res && kmax <= 5) MM_TC(5, 0, true, false);
+  else if (res) MM_TC(KMAXTC, 0, true, false);
+  else if (kmax <= 5) MM_TC(5, 0, false, false);
+  else MM_TC(KMAXTC, 0, false, false);
 #undef MM_TC
+  if (do_audit) {
+    audit->acc.resize((size_t)tj[0].na * tj[0].nb);
+    audit->norm_a.resize(tj[0].na);
+    audit->norm_b.resize(tj[0].nb);
+    audit_acc.download(c, audit->acc.data(), audit->acc.size());
+    norm[probs[0].a].download(c, audit->norm_a.data(), audit->norm_a.size());
+    norm[probs[0].b].download(c, audit->norm_b.data(), audit->norm_b.size());
+    audit->err_store = TC_ERR_STORE;
+    c.sync();
+  }
 }
 
 }  // namespace mm3d

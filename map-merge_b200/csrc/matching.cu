@@ -652,7 +652,10 @@ void knn_problems(Ctx& c, const std::vector<const float*>& desc, const std::vect
   const char* knn_env = std::getenv("MM3D_KNN");
   const std::string knn_mode = knn_env ? knn_env : "";
   const bool k_fits = kmax <= KMAX;  // == KMAXTC
-  const bool use_tc = k_fits && (knn_mode == "tc" || (knn_mode != "exact" && dim == 33));
+  bool nb_fits = true;  // the tensor-core kernel keeps 16-bit column indices in its pending lists
+  for (const KnnProblem& q : probs)
+    if (nk[q.b] > 65535) nb_fits = false;
+  const bool use_tc = k_fits && nb_fits && (knn_mode == "tc" || (knn_mode != "exact" && dim == 33));
   if (use_tc) {
     knn_tc_batch(c, desc, nk, dim, probs);
     return;

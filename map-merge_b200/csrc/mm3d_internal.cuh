@@ -12,8 +12,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "exact_math.h"
@@ -44,8 +47,89 @@ struct KernelSample {
   cudaEvent_t e0, e1;
 };
 
+// MM3D_HOST_TRACE=1: host time spent inside the CUDA runtime calls of the path (where does the host wait?)
+struct HostProf {
+  bool on = false;
+  double alloc_ms = 0, free_ms = 0, sync_ms = 0, copy_ms = 0;
+  long n_alloc = 0, n_free = 0, n_sync = 0, n_copy = 0;
+  size_t alloc_bytes = 0;
+};
+HostProf& host_prof();
+double host_now_ms();
+
+// Device-memory block cache of one context.  The path allocates and frees thousands of stage buffers per step (c3: ~4300
+// calls, ~9 GB); handing them to cudaMallocAsync / cudaFreeAsync made the step time erratic — the driver pool re-creates
+// multi-GB physical chunks whenever fragmentation defeats reuse (measured: 5 .. 560 ms per step inside cudaMallocAsync).
+// Freed blocks therefore return to size-class free lists here (8 classes per octave: <= 12.5 % slack) and are handed out
+// again without a driver call.  Everything of a context runs on ONE stream, so reuse after free is ordered by the stream,
+// exactly like the driver's stream-ordered pool.  Buffers hold a shared reference: blocks that outlive their context are
+// released with the last reference.
+struct BlockCache {
+  std::mutex mu;
+  std::unordered_map<size_t, std::vector<void*>> free_blocks;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  size_t held_bytes = 0;
+  static size_t size_class(size_t bytes)
+  {
+    if (bytes <= 4096) return (bytes + 255) & ~(size_t)255;
+    int lg = 0;
+    while (((size_t)1 << (lg + 1)) <= bytes) ++lg;
+    const size_t step = (size_t)1 << (lg - 3);
+    return (bytes + step - 1) & ~(step - 1);
+  }
+  void* get(size_t cls)
+  {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      auto it = free_blocks.find(cls);
+      if (it != free_blocks.end() && !it->second.empty()) {
+        void* p = it->second.back();
+        it->second.pop_back();
+        held_bytes -= cls;
+        return p;
+      }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, cls, stream);
+    if (e != cudaSuccess) {  // out of memory: give the cached blocks back and retry once
+      cudaGetLastError();
+      trim();
+      e = cudaMallocAsync(&p, cls, stream);
+    }
+    if (e != cudaSuccess)
+      throw CudaError(std::string("CUDA error: ") + cudaGetErrorString(e) + " allocating " + std::to_string(cls) + " bytes");
+    return p;
+  }
+  void put(void* p, size_t cls)
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    free_blocks[cls].push_back(p);
+    held_bytes += cls;
+  }
+  void trim()
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& kv : free_blocks)
+      for (void* p : kv.second) cudaFreeAsync(p, stream);
+    free_blocks.clear();
+    held_bytes = 0;
+  }
+  ~BlockCache()
+  {
+    // the context (and its stream) may be gone: plain cudaFree, which synchronises the device
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(device);
+    for (auto& kv : free_blocks)
+      for (void* p : kv.second) cudaFree(p);
+    cudaSetDevice(cur);
+  }
+};
+
 struct Ctx {
   int device = 0;
+  std::shared_ptr<BlockCache> cache = std::make_shared<BlockCache>();
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::string err;
@@ -55,7 +139,18 @@ struct Ctx {
   unsigned long long* knn_stats = nullptr;  // device: rows, rows that fell back to the exact scan, candidates re-ranked
   std::vector<KernelSample> samples;
   std::vector<cudaEvent_t> event_pool;
-  void sync() { MM_CUDA(cudaStreamSynchronize(stream)); }
+  void sync()
+  {
+    HostProf& hp = host_prof();
+    if (!hp.on) {
+      MM_CUDA(cudaStreamSynchronize(stream));
+      return;
+    }
+    const double t0 = host_now_ms();
+    MM_CUDA(cudaStreamSynchronize(stream));
+    hp.sync_ms += host_now_ms() - t0;
+    ++hp.n_sync;
+  }
   cudaEvent_t get_event()
   {
     cudaEvent_t e;
@@ -98,22 +193,23 @@ struct Ctx {
 // annotate the next launch with its algorithmic byte count
 #define MM_BYTES(ctx, b) ((ctx).next_bytes = (double)(b))
 
-// Stream-ordered device buffer.
+// Stream-ordered device buffer (blocks come from the context's BlockCache).
 template <typename T>
 struct DBuf {
   T* p = nullptr;
   size_t n = 0;
-  cudaStream_t s = nullptr;
+  size_t cls = 0;                     // size class of the block behind p
+  std::shared_ptr<BlockCache> cache;  // where the block returns to
   DBuf() {}
   DBuf(Ctx& c, size_t count) { alloc(c, count); }
   DBuf(const DBuf&) = delete;
   DBuf& operator=(const DBuf&) = delete;
-  DBuf(DBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+  DBuf(DBuf&& o) noexcept : p(o.p), n(o.n), cls(o.cls), cache(std::move(o.cache)) { o.p = nullptr; o.n = 0; }
   DBuf& operator=(DBuf&& o) noexcept
   {
     if (this != &o) {
       release();
-      p = o.p; n = o.n; s = o.s;
+      p = o.p; n = o.n; cls = o.cls; cache = std::move(o.cache);
       o.p = nullptr; o.n = 0;
     }
     return *this;
@@ -122,19 +218,43 @@ struct DBuf {
   void alloc(Ctx& c, size_t count)
   {
     release();
-    s = c.stream;
     n = count;
-    if (count) MM_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), s));
+    if (!count) return;
+    cache = c.cache;
+    cls = BlockCache::size_class(count * sizeof(T));
+    HostProf& hp = host_prof();
+    const double t0 = hp.on ? host_now_ms() : 0.0;
+    p = (T*)cache->get(cls);
+    if (hp.on) {
+      hp.alloc_ms += host_now_ms() - t0;
+      ++hp.n_alloc;
+      hp.alloc_bytes += cls;
+    }
   }
   void release()
   {
-    if (p) cudaFreeAsync(p, s);
+    if (p && cache) cache->put(p, cls);
     p = nullptr;
     n = 0;
+    cache.reset();
   }
   void zero(Ctx& c) { if (n) MM_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), c.stream)); }
-  void upload(Ctx& c, const T* h, size_t count) { if (count) MM_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, c.stream)); }
-  void download(Ctx& c, T* h, size_t count) const { if (count) MM_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, c.stream)); }
+  void upload(Ctx& c, const T* h, size_t count)
+  {
+    if (!count) return;
+    HostProf& hp = host_prof();
+    const double t0 = hp.on ? host_now_ms() : 0.0;
+    MM_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, c.stream));
+    if (hp.on) { hp.copy_ms += host_now_ms() - t0; ++hp.n_copy; }
+  }
+  void download(Ctx& c, T* h, size_t count) const
+  {
+    if (!count) return;
+    HostProf& hp = host_prof();
+    const double t0 = hp.on ? host_now_ms() : 0.0;
+    MM_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, c.stream));
+    if (hp.on) { hp.copy_ms += host_now_ms() - t0; ++hp.n_copy; }
+  }
 };
 
 template <typename T>
@@ -425,8 +545,11 @@ __device__ __forceinline__ void warp_radius_unordered(const GridView& g, float q
 // best prunes the rest.  rv = ceil(sqrt(bound) / leaf) + 1 voxels.
 // guess_slot >= 0: a slot (position in g.pts) expected to be close, e.g. the answer for a slightly different query; it
 // only seeds the running best (the search still visits everything that could beat or tie it), so the result is the same.
+// lim0_v > 0: an upper bound (voxel units, squared) on the distance to the nearest point that is known from elsewhere (the
+// reach grid); like the guess it only tightens the pruning threshold.
 __device__ __forceinline__ bool nearest_bounded(const GridView& g, float qx, float qy, float qz, double bound, int rv, int* out_idx,
-                                                float* out_d2, float4* out_pt, int guess_slot = -1, int* out_slot = nullptr)
+                                                float* out_d2, float4* out_pt, int guess_slot = -1, int* out_slot = nullptr,
+                                                float lim0_v = 0.0f)
 {
   const int vx = floor_to_int(qx * g.inv_leaf) - g.min_b[0];
   const int vy = floor_to_int(qy * g.inv_leaf) - g.min_b[1];
@@ -442,6 +565,7 @@ __device__ __forceinline__ bool nearest_bounded(const GridView& g, float qx, flo
   float4 best_pt = make_float4(0.f, 0.f, 0.f, 0.f);
   // pruning threshold in voxel units; starts at the bound
   float lim_v = (float)bound * g.inv_leaf * g.inv_leaf * 1.0001f + 1e-3f;
+  if (lim0_v > 0.0f) lim_v = fminf(lim_v, lim0_v);
   if (guess_slot >= 0 && guess_slot < g.n) {
     const float4 p = g.pts[guess_slot];
     const float d2 = em::dist2_3(qx, qy, qz, p.x, p.y, p.z);
@@ -451,7 +575,7 @@ __device__ __forceinline__ bool nearest_bounded(const GridView& g, float qx, flo
       best_idx = g.orig ? g.orig[guess_slot] : guess_slot;
       best_slot = guess_slot;
       best_pt = p;
-      lim_v = d2 * g.inv_leaf * g.inv_leaf * 1.0001f + 1e-3f;
+      lim_v = fminf(lim_v, d2 * g.inv_leaf * g.inv_leaf * 1.0001f + 1e-3f);
     }
   }
   const int nz = zhi - zlo + 1, ny = yhi - ylo + 1;
@@ -583,7 +707,12 @@ struct KnnProblem {
   int* idx;     // na x k
   float* dist;  // na x k
 };
-void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vector<int>& n_rows, int D, const std::vector<KnnProblem>& probs);
+struct KnnAudit {  // tests: what the tensor-core filter saw for one problem
+  std::vector<float> acc, norm_a, norm_b;
+  float err_store = 0.f;
+};
+void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vector<int>& n_rows, int D, const std::vector<KnnProblem>& probs,
+                  KnnAudit* audit = nullptr);
 // matching.cu: picks the tensor-core filter or an exact FP32 scan per descriptor width / k / MM3D_KNN
 void knn_problems(Ctx& c, const std::vector<const float*>& desc, const std::vector<int>& n_rows, int D, const std::vector<KnnProblem>& probs);
 
@@ -620,6 +749,22 @@ void sac_ia_batch(Ctx& c, const std::vector<CloudView>& keypoints, const std::ve
                   int max_iterations, unsigned long long rand_skip, std::vector<SacOut>& out);
 
 // icp.cu — K11, K12
+// Reach grid of a target cloud: per voxel of the (margin-extended) index grid a LOWER bound, in voxel units squared, of the
+// distance from any point inside that voxel to the nearest target point (separable min-plus transform of the occupancy with
+// the per-axis cost max(|d| - 1, 0)^2, saturating at 255).  A query whose voxel is farther than the search bound is
+// answered without a search; for the others the bound + the voxel diagonal caps the search radius.
+struct ReachView {
+  const unsigned char* lb2;  // dim[0] * dim[1] * dim[2], x fastest
+  int org[3];                // voxel coordinate (relative to the index grid's min_b) of cell 0: -margin
+  int dim[3];
+  int none;                  // value stored where no occupied voxel lies inside the margin window (= min(255, margin^2))
+};
+struct DReach {
+  ReachView v;
+  DBuf<unsigned char> lb2;
+};
+// one reach grid per index with points; margin = voxels of reach (>= ceil(search radius / leaf) + 1, capped at 15)
+void build_reach_batch(Ctx& c, const std::vector<DIndex>& idx, int margin, std::vector<DReach>& out);
 struct IcpOut {
   float T[16];  // row-major
   int iterations;
@@ -630,11 +775,11 @@ struct IcpNeighbours {
   DBuf<int> slots;
   std::vector<long long> offset;  // per pair job, -1 = not available
 };
-void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<PairJob>& jobs,
-               const std::vector<const float*>& T0_rowmajor, double max_dist, int max_it, double eps, std::vector<IcpOut>& out,
-               std::vector<std::vector<long long>>* sums_dbg, IcpNeighbours* nn_keep = nullptr);
-void score_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<PairJob>& jobs,
-                 const std::vector<const float*>& T_rowmajor, double max_range, std::vector<double>& scores,
+void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<DReach>& reach,
+               const std::vector<PairJob>& jobs, const std::vector<const float*>& T0_rowmajor, double max_dist, int max_it, double eps,
+               std::vector<IcpOut>& out, std::vector<std::vector<long long>>* sums_dbg, IcpNeighbours* nn_keep = nullptr);
+void score_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<DIndex>& idx, const std::vector<DReach>& reach,
+                 const std::vector<PairJob>& jobs, const std::vector<const float*>& T_rowmajor, double max_range, std::vector<double>& scores,
                  const IcpNeighbours* nn_guess = nullptr);
 
 // compose.cu — composeMaps sharded over ranks

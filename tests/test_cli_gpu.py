@@ -55,3 +55,55 @@ def test_map_merge_tool(tmp_path, ctx, mm, tiny_maps):
     # bad enum value -> error exit
     r = subprocess.run([os.path.join(PKG, "map_merge_tool"), a, b, "--keypoint_type", "sift"], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode != 0
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
+def test_multi_gpu_context_matches_single_gpu(mm, small_maps, tiny_maps):
+    """mm3d_create_multi: estimateMapsTransforms and composeMaps sharded over two devices inside the library (NCCL feature
+    exchange, LPT pair plan, all-to-all of points) are bit-identical to one device."""
+    maps, truth = small_maps
+    p = mm.default_params(descriptor_type="FPFH")
+    one = mm.Context(0)
+    two = mm.Context(devices=[0, 1])
+    assert two.device_count == 2 and one.device_count == 1
+    G1 = one.estimate_maps_transforms(maps, p)
+    G2 = two.estimate_maps_transforms(maps, p)
+    assert np.array_equal(G1.view(np.uint32), G2.view(np.uint32))
+    # more devices than maps with keypoints, an empty map in the middle
+    odd = [maps[0], np.zeros((0, 4), np.float32), maps[1]]
+    assert np.array_equal(one.estimate_maps_transforms(odd, p).view(np.uint32), two.estimate_maps_transforms(odd, p).view(np.uint32))
+    T = np.stack([np.linalg.inv(truth[0]) @ t for t in truth]).astype(np.float32)
+    for res in (0.05, 0.2, 1e-4):
+        c1 = one.compose_maps(maps, T, res)
+        c2 = two.compose_maps(maps, T, res)
+        assert c1.shape == c2.shape and np.array_equal(c1.view(np.uint32), c2.view(np.uint32)), res
+    T[1] = 0
+    assert np.array_equal(one.compose_maps(maps, T, 0.05).view(np.uint32), two.compose_maps(maps, T, 0.05).view(np.uint32))
+    one.close(); two.close()
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
+def test_map_merge_tool_two_gpus(tmp_path, tiny_maps):
+    """The CLI on two GPUs (MM3D_DEVICES=0,1) prints the same transforms and writes the same output.pcd as on one."""
+    subprocess.check_call(["make", "-C", PKG, "tools"], stdout=subprocess.DEVNULL)
+    maps, _ = tiny_maps
+    outs = []
+    for env_extra in ({"MM3D_DEVICE": "0"}, {"MM3D_DEVICES": "0,1"}):
+        d = tmp_path / ("run_" + "_".join(env_extra))
+        d.mkdir()
+        a, b = str(d / "a.pcd"), str(d / "b.pcd")
+        write_pcd(a, maps[0]); write_pcd(b, maps[1])
+        env = dict(os.environ); env.update(env_extra)
+        r = subprocess.run([os.path.join(PKG, "map_merge_tool"), a, b, "--descriptor_type", "FPFH"], cwd=d, capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append((r.stdout.split("Estimated transforms:")[1], open(d / "output.pcd", "rb").read()))
+    assert outs[0][0] == outs[1][0]
+    assert outs[0][1] == outs[1][1]

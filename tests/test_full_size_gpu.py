@@ -98,7 +98,7 @@ def write_pcd(path, pts):
         f.write(np.ascontiguousarray(pts, np.float32).tobytes())
 
 
-def test_config1_cli_against_oracle(tmp_path, mm, oracle, synth):
+def test_config1_cli_against_oracle(tmp_path, ctx, mm, oracle, synth):
     """configs[0] in full: map_merge_tool on two 200k-point room scans (SIFT + FPFH, RANSAC + ICP) against the oracle: the
     printed transforms to print precision, output.pcd bit for bit."""
     import oracle_py
@@ -116,7 +116,11 @@ def test_config1_cli_against_oracle(tmp_path, mm, oracle, synth):
     raw = open(tmp_path / "output.pcd", "rb").read()
     k = raw.index(b"DATA binary\n") + len(b"DATA binary\n")
     out = np.frombuffer(raw[k:], np.float32).reshape(-1, 4)
-    comp = oracle.compose_maps(maps, want, 0.05)
+    # the tool composes with ITS transforms (within 1e-5 of the oracle's: general 4x4 inverses in the graph step); the same
+    # call through the C ABI returns them with all their bits, and the oracle composes with exactly those
+    T_gpu = ctx.estimate_maps_transforms(maps, mm.default_params(descriptor_type="FPFH"))
+    np.testing.assert_allclose(T, T_gpu, atol=2e-5, rtol=1e-5)
+    comp = oracle.compose_maps(maps, T_gpu, 0.05)
     assert _bits_equal(out, comp)
 
 
@@ -139,6 +143,47 @@ def _knn_modes(ctx, monkeypatch, a, b, k=5):
     it, dt = ctx.knn(a, b, k)
     monkeypatch.delenv("MM3D_KNN")
     return ie, de, it, dt
+
+
+def _seq_fp32_dist(a, b):
+    """flann::L2_Simple as the exact scan evaluates it: float32, dimension by dimension, no contraction."""
+    acc = np.zeros((len(a), len(b)), np.float32)
+    for t in range(a.shape[1]):
+        diff = a[:, None, t] - b[None, :, t]
+        acc += diff * diff
+    return acc
+
+
+def test_tensor_core_knn_error_bound(ctx, mm, synth):
+    """The filter's error model on the headline workload's descriptors (two c3 maps, both directions):
+    v = acc + (1 - ES) ||a'||^2 must satisfy v <= d <= v + 2 ES (||a'||^2 + ||b'||^2) for EVERY pair of rows, d = the sequential
+    FP32 distance of the exact scan — with room to spare: the measured deviation of the dot product must stay below ES / 2."""
+    cfg = dict(synth.CONFIGS["c3"])
+    maps, _ = synth.make_maps(**cfg, only=[0, 1])
+    p = mm.default_params(descriptor_type="FPFH")
+    dm = ctx.maps_upload(maps[:2])
+    f = ctx.features_compute(dm, 0, 2, p)
+    desc = [f.export_host(m)[2] for m in range(2)]
+    f.free(); dm.free()
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for a, b in ((desc[0], desc[1]), (desc[1], desc[0])):
+        a = a[np.sort(rng.choice(len(a), 2048, replace=False))]
+        au = ctx.knn_tc_audit(a, b, 5)
+        es = au["err_store"]
+        d = _seq_fp32_dist(a, b).astype(np.float64)
+        na = au["norm_a"].astype(np.float64)[:, None]; nb = au["norm_b"].astype(np.float64)[None, :]
+        v = au["acc"].astype(np.float64) + (1.0 - es) * na
+        ratio = (d - v) / (na + nb + 1e-30)      # ES +- (deviation of the dot product) / (||a'||^2 + ||b'||^2)
+        assert ratio.min() >= 0.0, f"lower bound violated: min ratio {ratio.min():.3e}"
+        assert ratio.max() <= 2.0 * es, f"upper bound violated: max ratio {ratio.max():.3e} vs {2 * es:.3e}"
+        dev = np.abs(ratio - es).max()
+        worst = max(worst, dev)
+        assert dev < 0.5 * es, f"deviation {dev:.3e} leaves less than half of ES = {es:.3e} as margin"
+        # and the search itself equals numpy's (distance, index) ranking
+        order = np.lexsort((np.broadcast_to(np.arange(d.shape[1]), d.shape), d), axis=1)[:, :5]
+        assert np.array_equal(au["idx"], order)
+    print(f"tensor-core filter: worst deviation / (||a'||^2 + ||b'||^2) = {worst:.3e}, ES = {es:.3e}")
 
 
 def test_tensor_core_knn_against_exact_scan_config2(ctx, mm, synth, monkeypatch):

@@ -427,6 +427,32 @@ def test_match_small_sets_and_generic_dim(ctx, oracle):
         assert_same_bits(gd, wd, f"distances k {k}")
 
 
+def test_knn_duplicate_descriptors_keep_index_order(ctx, monkeypatch):
+    """Two identical descriptors (SIFT keypoints of different octaves at one location) tie exactly; the lower index must
+    stay first even when closer rows arrive later in the scan and push the tied pair down the list."""
+    rng = np.random.default_rng(21)
+    b = rng.uniform(0, 100, size=(700, 33)).astype(np.float32)
+    a = rng.uniform(0, 100, size=(130, 33)).astype(np.float32)
+    for r in range(len(a)):
+        # a tied pair early in the scan, three closer rows later on (both halves of a tile, several tiles)
+        near = a[r] + rng.normal(0, 3.0, 33).astype(np.float32)
+        j = 5 + 2 * r
+        b[j] = near; b[j + 1] = near
+        for t, col in enumerate((300 + r, 450 + r, 570 + r)):
+            b[col] = a[r] + rng.normal(0, 0.5 + 0.3 * t, 33).astype(np.float32)
+    d = np.zeros((len(a), len(b)), np.float32)
+    for t in range(33):
+        diff = a[:, None, t] - b[None, :, t]
+        d += diff * diff
+    want = np.lexsort((np.broadcast_to(np.arange(len(b)), d.shape), d), axis=1)[:, :5]
+    for mode in ("exact", "tc"):
+        monkeypatch.setenv("MM3D_KNN", mode)
+        idx, dist = ctx.knn(a, b, 5)
+        assert np.array_equal(idx, want), mode
+        assert_same_bits(dist, np.take_along_axis(d, want, axis=1), f"distances {mode}")
+    monkeypatch.delenv("MM3D_KNN")
+
+
 # ---------------------------------------------------------------- K10 RANSAC
 def test_ransac_bit_exact(ctx, oracle, tiny_stages):
     s, t = tiny_stages
