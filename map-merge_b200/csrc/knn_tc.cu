@@ -33,6 +33,8 @@ constexpr int A_RES_MAX_KB = 4;             // A stays resident in shared memory
 constexpr int LIST_CAP = 64;                // pending candidates per (query row, column half), 16-bit column indices (nb <= 65535)
 constexpr int LIST_STRIDE = LIST_CAP + 2;   // 33 words per list: appends by 32 rows (2-way) and reads of one row's 32 entries (none) stay cheap
 constexpr int KMAXTC = 16;
+constexpr int ACC_BUFS = 4;                 // TMEM accumulator buffers (4 x 128 columns = all 512): the epilogue warps may lag the
+                                            // MMA by three tiles, so one warp's burst of exact evaluations no longer stalls the rest
 constexpr int EPI_WARPS = 8;                // two per scheduler: warps w and w + 4 share a TMEM lane quarter and split every tile's columns
 constexpr int TC_THREADS = 64 + EPI_WARPS * 32;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
 constexpr int LIST_BYTES = TM * 2 * LIST_STRIDE * 2;
@@ -210,8 +212,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
   uint64_t* full_bar = (uint64_t*)(a_orig + TM * APAD);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* a_full = tmem_empty + 2;
+  uint64_t* tmem_empty = tmem_full + ACC_BUFS;
+  uint64_t* a_full = tmem_empty + ACC_BUFS;
   uint32_t* tmem_slot = (uint32_t*)(a_full + 1);
 
   const TcJob job = jobs[blockIdx.y];
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < ACC_BUFS; ++b) {
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], EPI_WARPS);  // one arrival per epilogue warp
     }
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(ACC_BUFS * TN)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -272,8 +274,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
       int stage = 0;
       uint32_t phase = 0;
       for (int nt = 0; nt < n_tiles; ++nt) {
-        const int buf = nt & 1;
-        const uint32_t acc_phase = (uint32_t)(nt >> 1) & 1u;
+        const int buf = nt % ACC_BUFS;
+        const uint32_t acc_phase = (uint32_t)(nt / ACC_BUFS) & 1u;
         mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TN);
@@ -445,9 +447,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
       const int nt = ch >> 1, c0 = half * 64 + (ch & 1) * 32;
       const bool tile_end = (ch & 1) == 1;
       if (ch + 1 < n_chunks) {
-        const int nt1 = (ch + 1) >> 1, buf1 = nt1 & 1;
+        const int nt1 = (ch + 1) >> 1, buf1 = nt1 % ACC_BUFS;
         if (tile_end) {
-          mbar_wait(&tmem_full[buf1], (uint32_t)(nt1 >> 1) & 1u);
+          mbar_wait(&tmem_full[buf1], (uint32_t)(nt1 / ACC_BUFS) & 1u);
           tc_fence_after();
         }
         tmem_ld_32x32_issue(tmem_row + (uint32_t)(buf1 * TN + half * 64 + ((ch + 1) & 1) * 32), rn);
@@ -515,7 +517,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
       if (tile_end) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[nt & 1]);
+        if (lane == 0) mbar_arrive(&tmem_empty[nt % ACC_BUFS]);
       }
 #pragma unroll
       for (int c = 0; c < 32; ++c) r[c] = rn[c];
@@ -572,7 +574,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(ACC_BUFS * TN)) : "memory");
   }
 }
 

@@ -230,3 +230,30 @@ def test_choose_splitters(mm):
     assert sum(loads) == 1000 and max(loads) <= 300
     assert list(sh.choose_splitters(np.zeros(8, np.int64), 2)) == [0, 0, 8]
     assert list(sh.choose_splitters(np.array([5]), 3)) == [0, 1, 1, 1]
+
+
+def test_library_pair_plan_matches_python_restatement(mm):
+    """mm3d_dist_block / mm3d_dist_plan (csrc/dist.cu, what every rank of the multi-GPU path computes for itself) against
+    the Python restatement in sharding.py: same blocks, same row-major pair list, same LPT owners."""
+    import importlib
+    sh = importlib.import_module("map_merge_b200.sharding")
+    rng = np.random.default_rng(3)
+    for n_maps, world in ((32, 8), (32, 4), (8, 2), (5, 3), (2, 2), (1, 4), (7, 16)):
+        n_pts = rng.integers(100_000, 300_000, n_maps)
+        n_kp = rng.integers(0, 9000, n_maps)
+        n_kp[rng.integers(0, n_maps)] = 0
+        pairs, owner = mm.dist_plan(n_pts, n_kp, 33, world)
+        ij = sh.pair_list(n_kp.tolist())
+        assert pairs.tolist() == [list(p) for p in ij]
+        want = sh.lpt_assign(sh.pair_costs(ij, n_pts.tolist(), n_kp.tolist(), 33), world) if ij else np.zeros(0, np.int64)
+        assert owner.tolist() == [int(x) for x in want]
+        if len(ij) >= world:
+            costs = np.array(sh.pair_costs(ij, n_pts.tolist(), n_kp.tolist(), 33))
+            loads = np.array([costs[owner == r].sum() for r in range(world)])
+            assert loads.max() <= loads.mean() + costs.max()  # LPT: no rank is more than one job above the mean
+        covered = []
+        for r in range(world):
+            first, count = mm.dist_block(r, world, n_maps)
+            assert (first, count) == sh.map_block(r, world, n_maps)[:2]
+            covered += list(range(first, first + count))
+        assert covered == list(range(n_maps))
