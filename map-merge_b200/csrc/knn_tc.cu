@@ -63,6 +63,7 @@ struct TcJob {
   int* idx;     // na x k
   float* dist;  // na x k
   float* audit; // optional na x nb: the raw accumulator (tests: error-bound audit)
+  float* thr;   // na: per row, upper bound (accumulator space) of the k-th nearest distance — written by pass 0, read by pass 1
 };
 
 // ---- PTX wrappers ------------------------------------------------------------
@@ -192,7 +193,13 @@ __device__ __forceinline__ void topk_insert(float (&bd)[KCAP], int (&bi)[KCAP], 
 // KCAP = capacity of the register top lists (>= k; the first k are written out); DREG = descriptor length when the query
 // rows sit in shared memory and rows are read as float4 from the padded copies, 0 = scalar reads from global memory;
 // A_RES = the A tile stays in shared memory for the whole CTA (kblocks <= A_RES_MAX_KB); AUDIT = also dump the accumulators.
-template <int KCAP, int DREG, bool A_RES, bool AUDIT>
+// PASS 0 = threshold pass: the same GEMM with a minimal epilogue that only derives, per row, an upper bound of the k-th nearest
+// distance (job.thr); PASS 1 = candidate pass: columns whose lower bound is within that bound are evaluated exactly.
+// Two passes instead of one running threshold: a streaming top-k meets ~k ln(n / k) record breakers per row that all need
+// an exact evaluation and a list insertion (measured: 2/3 of the single-pass epilogue's instructions); with the bound known
+// up front only the columns inside the error margin of the k-th distance are ever touched, and the tensor pipe — 5 % busy
+// in the single-pass kernel — pays for the second GEMM.
+template <int KCAP, int DREG, bool A_RES, bool AUDIT, int PASS>
 __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __restrict__ jobs, const CUtensorMap* __restrict__ mapsA,
                                                               const CUtensorMap* __restrict__ mapsB, int kblocks, int D,
                                                               unsigned long long* __restrict__ stats)
@@ -322,10 +329,84 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
     const float na = live ? job.normA[row] : 0.f;
     const float na_low = (1.0f - TC_ERR_STORE) * na;  // acc + na_low <= exact distance
     const float INF = __int_as_float(0x7f800000);
-    float t5[KCAP], bd[KCAP];
+    unsigned evals = 0, flushes = 0;
+    if constexpr (PASS == 0) {
+      // ---- threshold pass: K-th smallest upper bound over one value per 32-column chunk (chunk minima are distinct columns)
+      float t5[KCAP];
+#pragma unroll
+      for (int i = 0; i < KCAP; ++i) t5[i] = INF;
+      const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
+      const int n_chunks = n_tiles * 2;
+      uint32_t r[32], rn[32];
+      mbar_wait(&tmem_full[0], 0);
+      tc_fence_after();
+      tmem_ld_32x32_issue(tmem_row + (uint32_t)(half * 64), r);
+      tmem_ld_wait(r);
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        const int nt = ch >> 1, c0 = half * 64 + (ch & 1) * 32;
+        const bool tile_end = (ch & 1) == 1;
+        if (ch + 1 < n_chunks) {
+          const int nt1 = (ch + 1) >> 1, buf1 = nt1 % ACC_BUFS;
+          if (tile_end) {
+            mbar_wait(&tmem_full[buf1], (uint32_t)(nt1 / ACC_BUFS) & 1u);
+            tc_fence_after();
+          }
+          tmem_ld_32x32_issue(tmem_row + (uint32_t)(buf1 * TN + half * 64 + ((ch + 1) & 1) * 32), rn);
+        }
+        const int jbase = nt * TN + c0;
+        const int left = job.nb - jbase;  // columns past nb are zero rows of the B form: keep them out of the minimum
+        if (left < 32) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c >= left) r[c] = 0x7f800000u;
+        }
+        if (left > 0) {
+          float m = fmin3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
+#pragma unroll
+          for (int c = 3; c < 31; c += 2) m = fmin3(m, __uint_as_float(r[c]), __uint_as_float(r[c + 1]));
+          m = fminf(m, __uint_as_float(r[31]));
+          const float cmax = __ldg(&job.cmaxB[jbase >> 5]);
+          float ub = m + ((2.0f * TC_ERR_STORE) * (na + cmax) + 1e-6f * (1.0f + fabsf(m)));
+#pragma unroll
+          for (int t = 0; t < KCAP; ++t) {
+            const float lo_ = fminf(t5[t], ub);
+            ub = fmaxf(t5[t], ub);
+            t5[t] = lo_;
+          }
+        }
+        tmem_ld_wait(rn);
+        if (tile_end) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[nt % ACC_BUFS]);
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) r[c] = rn[c];
+      }
+      // K-th smallest of the two halves' sorted lists
+      if (half == 1) {
+#pragma unroll
+        for (int t = 0; t < KCAP; ++t) park_d[lrow * KCAP + t] = t5[t];
+      }
+      epi_bar_sync();
+      if (half == 0 && live) {
+        int ia = 0, ib = 0;
+        float kth = INF;
+        for (int t = 0; t < KCAP; ++t) {
+          float da = INF;
+#pragma unroll
+          for (int u = 0; u < KCAP; ++u)
+            if (u == ia) da = t5[u];
+          const float db = ib < KCAP ? park_d[lrow * KCAP + ib] : INF;
+          if (db < da) { kth = db; ++ib; } else { kth = da; ++ia; }
+        }
+        job.thr[row] = kth;
+      }
+    } else {
+    float bd[KCAP];
     int bi[KCAP];
 #pragma unroll
-    for (int i = 0; i < KCAP; ++i) { t5[i] = INF; bd[i] = INF; bi[i] = -1; }
+    for (int i = 0; i < KCAP; ++i) { bd[i] = INF; bi[i] = -1; }
     // shared copy of the original query rows (D = 33 path)
     if (DREG > 0) {
       for (int e = (ew * 32 + lane); e < TM * (APAD / 4); e += EPI_WARPS * 32) {
@@ -335,10 +416,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
       }
       epi_bar_sync();
     }
-    float thr = live ? INF : -INF;  // acc-space filter bound, only ever shrinks
+    float thr = live ? job.thr[row] : -INF;  // acc-space filter bound from the threshold pass, only ever shrinks
     float thr_exact = INF;
     int n = 0;
-    unsigned evals = 0, flushes = 0;
     unsigned short* my_list = list + (lrow * 2 + half) * LIST_STRIDE;
 
     // the warp evaluates up to 32 pending candidates of lane L's row exactly and merges them into L's top list
@@ -410,37 +490,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
     uint32_t r[32], rn[32];
     mbar_wait(&tmem_full[0], 0);
     tc_fence_after();
-    // Seed the running bound from tile 0 before anything is listed (otherwise the first chunk, filtered against an infinite
-    // bound, would send all its 32 columns of every row through an exact evaluation): one upper bound per 4 columns of this
-    // half's 64 = 16 bounds >= KCAP.  The main loop then skips the bound update for tile 0 (a column must not count twice).
-#pragma unroll 1
-    for (int sc = 0; sc < 2; ++sc) {
-      tmem_ld_32x32_issue(tmem_row + (uint32_t)(half * 64 + sc * 32), r);
-      tmem_ld_wait(r);
-      const int jbase = half * 64 + sc * 32;
-      const int left = job.nb - jbase;
-      if (left < 32) {
-#pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (c >= left) r[c] = 0x7f800000u;
-      }
-      if (left > 0) {
-        const float e = (2.0f * TC_ERR_STORE) * (na + __ldg(&job.cmaxB[jbase >> 5]));
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float m4 = fminf(fmin3(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2])),
-                                 __uint_as_float(r[4 * g + 3]));
-          float ub = m4 + (e + 1e-6f * (1.0f + fabsf(m4)));
-#pragma unroll
-          for (int t = 0; t < KCAP; ++t) {
-            const float lo_ = fminf(t5[t], ub);
-            ub = fmaxf(t5[t], ub);
-            t5[t] = lo_;
-          }
-        }
-      }
-    }
-    thr = fminf(thr, t5[KCAP - 1]);
     tmem_ld_32x32_issue(tmem_row + (uint32_t)(half * 64), r);
     tmem_ld_wait(r);
     for (int ch = 0; ch < n_chunks; ++ch) {
@@ -474,18 +523,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
 #pragma unroll
         for (int c = 3; c < 31; c += 2) m = fmin3(m, __uint_as_float(r[c]), __uint_as_float(r[c + 1]));
         m = fminf(m, __uint_as_float(r[31]));
-        // its upper bound in acc space (the chunk's largest norm bounds every column's error term) feeds the running bound
-        if (ch >= 2) {  // tile 0 seeded the bound already
-          const float cmax = __ldg(&job.cmaxB[jbase >> 5]);
-          float ub = m + ((2.0f * TC_ERR_STORE) * (na + cmax) + 1e-6f * (1.0f + fabsf(m)));
-#pragma unroll
-          for (int t = 0; t < KCAP; ++t) {
-            const float lo_ = fminf(t5[t], ub);
-            ub = fmaxf(t5[t], ub);
-            t5[t] = lo_;
-          }
-          thr = fminf(thr, t5[KCAP - 1]);
-        }
         if (m <= thr) {
           // which columns pass (one compare + one bit each), then one append per set bit
           uint32_t m0_ = 0, m1_ = 0, m2_ = 0, m3_ = 0;
@@ -558,6 +595,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
         job.idx[(size_t)row * k + t] = jsel;
         job.dist[(size_t)row * k + t] = jsel >= 0 ? dsel : 0.f;
       }
+    }
     }
     if (stats) {
       const unsigned rows = __reduce_add_sync(0xffffffffu, (live && half == 0) ? 1u : 0u);
@@ -759,9 +797,16 @@ void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vect
   int max_na = 0, kmax = 0;
   double bytes = 0;
   DBuf<float> audit_acc;
+  size_t rows_total = 0;
+  for (const KnnProblem& p : probs)
+    if (p.na > 0 && n_rows[p.b] > 0) rows_total += (size_t)p.na;
+  DBuf<float> thr(c, rows_total);
+  size_t row_off = 0;
   for (const KnnProblem& p : probs) {
     if (p.na == 0 || n_rows[p.b] == 0) continue;
     TcJob j;
+    j.thr = thr.p + row_off;
+    row_off += (size_t)p.na;
     j.a_map = p.a;
     j.b_map = p.b;
     j.na = p.na;
@@ -788,7 +833,6 @@ void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vect
     tj[0].audit = audit_acc.p;
   }
   DBuf<TcJob> dtj = to_device(c, tj);
-  MM_BYTES(c, bytes);
   if (!c.knn_stats) {
     MM_CUDA(cudaMalloc((void**)&c.knn_stats, 3 * sizeof(unsigned long long)));
     MM_CUDA(cudaMemsetAsync(c.knn_stats, 0, 3 * sizeof(unsigned long long), c.stream));
@@ -798,8 +842,12 @@ void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vect
   do {                                                                                                                                 \
     const size_t smem = tc_smem(DREG, RES);                                                                                            \
     /* per device and cheap: set on every call (a process may drive several GPUs) */                                                  \
-    MM_CUDA(cudaFuncSetAttribute(knn_tc_kernel<KCAP, DREG, RES, AUD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-    MM_LAUNCH(c, (knn_tc_kernel<KCAP, DREG, RES, AUD>), grid, TC_THREADS, smem, dtj.p, dA.p, dB.p, kblocks, D, c.knn_stats);           \
+    MM_CUDA(cudaFuncSetAttribute(knn_tc_kernel<KCAP, DREG, RES, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    MM_CUDA(cudaFuncSetAttribute(knn_tc_kernel<KCAP, DREG, RES, AUD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    MM_BYTES(c, bytes);                                                                                                                \
+    MM_LAUNCH(c, (knn_tc_kernel<KCAP, DREG, RES, false, 0>), grid, TC_THREADS, smem, dtj.p, dA.p, dB.p, kblocks, D, nullptr);          \
+    MM_BYTES(c, bytes);                                                                                                                \
+    MM_LAUNCH(c, (knn_tc_kernel<KCAP, DREG, RES, AUD, 1>), grid, TC_THREADS, smem, dtj.p, dA.p, dB.p, kblocks, D, c.knn_stats);        \
   } while (0)
   const bool res = kblocks <= A_RES_MAX_KB;
   if (do_audit) MM_TC(5, 33, true, true);
