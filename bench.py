@@ -72,53 +72,72 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    """SM clock + throttle reasons sampled during the timed region through NVML in a background thread (pynvml; an
+    `nvidia-smi -lms 100` child process was measured to slow the host side of short steps by up to 2x while it polls, and
+    100 ms NVML polling the c3 step by up to 30 %: the queries contend with CUDA calls for the driver lock)."""
 
     def __init__(self, index: int):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.err = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # no NVML: fall back to one nvidia-smi query at the end
+            self.err = str(e)
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((time.perf_counter(), sm, reasons))
+            except Exception as e:
+                self.err = str(e)
+                return
+            self.stop_flag.wait(0.5)  # NVML queries contend with CUDA calls for the driver lock: 100 ms polling cost up to 30 % of a step
+
+    def stop(self, t0=None, t1=None):
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return self._smi_once()
+        nv = self.nv
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        sel = [x for x in self.samples if t0 is None or (t0 <= x[0] <= t1 + 0.15)] or self.samples
+        reasons = sorted(k for k, b in bits.items() if any(x[2] & b for x in sel))
+        return {"sm_mhz": float(np.median([x[1] for x in sel])), "sm_max_mhz": self.max_sm, "samples": len(sel), "reasons": reasons,
+                "source": "NVML, 500 ms period, samples inside the timed region"}
+
+    def _smi_once(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.perf_counter(), line.strip()))
-
-    def stop(self, t0=None, t1=None):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, ln in self.lines:
-            if t0 is not None and not (t0 <= ts <= t1 + 0.15):
-                continue
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 6:
-                continue
-            try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, parts[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+            out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=20).stdout.strip().splitlines()[0]
+            parts = [p.strip() for p in out.split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(parts[0]), "sm_max_mhz": float(parts[1]), "samples": 1,
+                    "reasons": [n for n, v in zip(names, parts[2:6]) if v.lower().startswith("active")],
+                    "source": f"one nvidia-smi query after the timed region (NVML thread unavailable: {self.err})"}
+        except Exception as e:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": [f"clock sampling unavailable: {e}"]}
 
 
 # ---------------------------------------------------------------------------------------------- CPU arms
@@ -365,6 +384,24 @@ class Job:
         return float(ms.item()), self.ctx.launches - l0, prof, out, (w0, w1)
 
 
+def settle(job, fn, seconds: float = 1.0):
+    """Untimed steps (the same on every rank) while the clock sampler starts up."""
+    n = 1
+    if job.rank == 0:
+        t0 = time.perf_counter()
+        fn()
+        dt = max(time.perf_counter() - t0, 1e-3)
+        n = max(1, min(20, int(seconds / dt)))
+    if job.world > 1:
+        t = job.torch.tensor([n], dtype=job.torch.int64, device=job.dev)
+        job.dist.broadcast(t, 0)
+        n = int(t.item())
+        if job.rank != 0:
+            fn()
+    for _ in range(n - 1):
+        fn()
+
+
 def roofline_of(prof, steps, peak, peak_src):
     """Dominant kernel of the profiled pass.  achieved = its algorithmic bytes / its CUDA-event time (per-launch averages)."""
     prof = sorted(prof, key=lambda k: -k["ms"])
@@ -408,7 +445,8 @@ def run_gpu(args):
         job.step(False)
     sampler = ClockSampler(job.local)
     if job.rank == 0:
-        sampler.start()  # nvidia-smi needs ~0.5 s to produce its first sample
+        sampler.start()
+    settle(job, lambda: job.step(False))  # nvidia-smi initialises NVML for ~0.5 s and stalls driver calls meanwhile: keep that out of the timed region
     job.phase_ms = {}
     ms, launches, _, out, (w0, w1) = job.timed(args.steps, lambda: job.step(False))
     if job.phases_on:
@@ -468,6 +506,7 @@ def run_gpu_compose(args, job):
     sampler = ClockSampler(job.local)
     if job.rank == 0:
         sampler.start()
+    settle(job, lambda: job.compose_step(False, T))
     ms, launches, _, out, (w0, w1) = job.timed(args.steps, lambda: job.compose_step(False, T))
     clocks = sampler.stop(w0, w1) if job.rank == 0 else None
     job.compose_step(True, T)

@@ -2,27 +2,25 @@
 //   <- map_merge_3d/src/matching.cpp:196-221 (pcl::IterativeClosestPoint, TransformationEstimationSVD,
 //      DefaultConvergenceCriteria) and :259-268 (pcl::registration::TransformationValidationEuclidean)
 //
-// The WHOLE ICP loop of every pair is ONE persistent cooperative kernel: per iteration the blocks pull 128-query tiles of
-// the still-active pairs from a device-side queue; a tile applies the previous iteration's step transform, finds each
+// The WHOLE ICP loop of every pair is ONE persistent kernel.  Every pair carries its own tile counter: blocks pull
+// 128-query tiles from whichever pair has tiles left; a tile applies the pair's previous step transform, finds each
 // query's nearest target point within the correspondence distance and adds its share of {n, sum p, sum q, sum q p^T,
 // sum d^2} (fixed-point int64, so the reduction is order-independent and matches the CPU checker bit for bit); the last
-// tile of a pair solves Umeyama (3x3 SVD), updates the transform and tests convergence; a grid-wide barrier ends the
-// iteration, block 0 rebuilds the tile queue from the pairs that are still active, and the loop ends on the device when
-// none is left.  The host launches once and reads the results once.
+// tile of a pair's iteration solves Umeyama (3x3 SVD), updates the transform, tests convergence and — if the pair goes on
+// — re-opens its tile counter for the next iteration.  Pairs therefore iterate independently (no grid-wide barrier: with
+// one, a quarter of the warp time was spent waiting for the slowest pair of every iteration, ncu round 2), and the loop
+// ends on the device when no pair is active.  The host launches once and reads the results once.
 //
 // Nearest-neighbour search: thread per query over the voxel-row index, pruned three ways — (1) the target's reach grid
 // (a lower bound of the distance to the nearest target point per voxel) answers queries that have no target point in
 // range without a search, which is most of the non-overlapping part of a pair; (2) the same bound plus the voxel
 // diagonal caps the radius for the others; (3) the previous iteration's match seeds the running best.
-#include <cooperative_groups.h>
-
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <type_traits>
 
 #include "mm3d_internal.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace mm3d {
 
@@ -50,16 +48,16 @@ struct IcpJob {
   long long* sums;   // NSUM
   IcpState* st;
   int* ticket;       // tiles of this pair that finished the current iteration
+  int* next_tile;    // tile counter of the current iteration (>= n_tiles: nothing left / iteration being solved)
+  int n_tiles;
   float t0[16];      // initial guess, row-major
   long long* sums_log;  // optional max_log x NSUM
   int* nn_slot;      // per source point: the target slot matched in the previous iteration (-1 = none)
 };
 
 struct IcpLoop {
-  int n_active;     // pairs still iterating
-  int iteration;
-  int total_tiles;  // tiles of this iteration (0 = done)
-  int next_tile;    // queue head
+  int n_active;  // pairs still iterating
+  int pad[3];
 };
 
 // ---------------------------------------------------------------- reach grid
@@ -203,17 +201,21 @@ __device__ __forceinline__ bool nearest_block27(const GridView& g, float qx, flo
 // The result is the same as an exhaustive search: the nearest point by (d^2, original index) among those with d^2 <= bound.
 struct TileNn {
   float4 q[IB];   // x, y, z, search radius^2 of the queries handed to phase 2
-  int todo[IB];
+  int todo[IB];        // small windows
+  int todo_large[IB];  // large windows
   float res_d2[IB];
   int res_slot[IB];
-  int n_todo;
+  int n_todo, n_todo_large;
 };
 
 __device__ __forceinline__ bool tile_nearest(TileNn& sh, const GridView& g, const ReachView& r, bool live, float qx, float qy, float qz,
                                              double bound, int guess_slot, float* out_d2, float4* out_pt, int* out_slot)
 {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) sh.n_todo = 0;
+  if (tid == 0) {
+    sh.n_todo = 0;
+    sh.n_todo_large = 0;
+  }
   __syncthreads();
   bool hit = false, pending = false;
   float d2 = 0.f;
@@ -245,20 +247,24 @@ __device__ __forceinline__ bool tile_nearest(TileNn& sh, const GridView& g, cons
       if (!certain) {
         pending = true;
         hit = false;
-        sh.q[tid] = make_float4(qx, qy, qz, r2 * 1.00001f + 1e-12f);  // strict < inside the walk: widen by a hair
-        sh.todo[atomicAdd(&sh.n_todo, 1)] = tid;
+        const float r2w = r2 * 1.00001f + 1e-12f;  // strict < inside the walk: widen by a hair
+        sh.q[tid] = make_float4(qx, qy, qz, r2w);
+        if (r2w * g.inv_leaf * g.inv_leaf <= 12.25f) sh.todo[atomicAdd(&sh.n_todo, 1)] = tid;  // radius <= 3.5 voxels: at most 11 x 11 rows
+        else sh.todo_large[atomicAdd(&sh.n_todo_large, 1)] = tid;
       }
     }
   }
   __syncthreads();
-  const int n_todo = sh.n_todo;
-  for (int t = warp; t < n_todo; t += IB / 32) {
-    const int who = sh.todo[t];
+  // phase 2: small windows (a few dozen rows: queries near the target surface) by groups of 8 lanes, four queries per warp
+  // at a time; large windows (queries up to the correspondence distance away from the target) by whole warps
+  const int n_small = sh.n_todo, n_large = sh.n_todo_large;
+  auto serve = [&](auto G_, int who, unsigned gmask, int glane) {
+    constexpr int G = decltype(G_)::value;
     const float4 q = sh.q[who];
     const int rv = (int)ceilf(sqrtf(q.w) * g.inv_leaf) + 1;
     float bd = 3.0e38f;
     int bi = 0x7fffffff, bs = -1;
-    warp_radius_unordered(g, q.x, q.y, q.z, q.w, rv, [&](bool valid, int k, const float4&, float dd) {
+    group_radius_unordered<G>(g, gmask, glane, q.x, q.y, q.z, q.w, rv, [&](bool valid, int k, const float4&, float dd) {
       if (valid && (double)dd <= bound) {
         const int oi = g.orig ? g.orig[k] : k;
         if (dd < bd || (dd == bd && oi < bi)) {
@@ -269,21 +275,28 @@ __device__ __forceinline__ bool tile_nearest(TileNn& sh, const GridView& g, cons
       }
     });
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float od = __shfl_xor_sync(0xffffffffu, bd, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+    for (int o = G / 2; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(gmask, bd, o, G);
+      const int oi = __shfl_xor_sync(gmask, bi, o, G);
+      const int os = __shfl_xor_sync(gmask, bs, o, G);
       if (od < bd || (od == bd && oi < bi)) {
         bd = od;
         bi = oi;
         bs = os;
       }
     }
-    if (lane == 0) {
+    if (glane == 0) {
       sh.res_d2[who] = bd;
       sh.res_slot[who] = bs;
     }
+  };
+  {
+    const int grp = tid >> 3, glane = tid & 7;
+    const unsigned gmask = 0xffu << (lane & 24);
+    for (int t = grp; t < n_small; t += IB / 8) serve(std::integral_constant<int, 8>(), sh.todo[t], gmask, glane);
   }
+  __syncwarp();
+  for (int t = warp; t < n_large; t += IB / 32) serve(std::integral_constant<int, 32>(), sh.todo_large[t], 0xffffffffu, lane);
   __syncthreads();
   if (pending) {
     slot = sh.res_slot[tid];
@@ -358,6 +371,7 @@ __device__ void icp_solve(const IcpJob& j, int max_iterations, double rotation_t
   if (cnt < 3) {  // "Not enough correspondences found": stop, not converged
     st.active = 0;
     st.converged = 0;
+    __threadfence();
     atomicSub(n_active, 1);
     return;
   }
@@ -400,20 +414,27 @@ __device__ void icp_solve(const IcpJob& j, int max_iterations, double rotation_t
   if (conv) {
     st.active = 0;
     st.converged = 1;
+    __threadfence();
     atomicSub(n_active, 1);
+  } else {
+    __threadfence();             // the new step transform is visible before the next iteration's tiles are handed out
+    atomicExch(j.next_tile, 0);  // re-open the pair
   }
 }
 
 // One 128-query tile of one pair in the current iteration.  Data that other blocks wrote in an earlier iteration (work,
 // nn_slot, the step transform) is read through L2 (__ldcg): L1 is not coherent between SMs.
-__device__ __forceinline__ void icp_tile(const IcpJob& j, int tile, int apply_step, double max_dist_sqr, int rv, int max_iterations,
+__device__ __forceinline__ void icp_tile(const IcpJob& j, int tile, double max_dist_sqr, int rv, int max_iterations,
                                          double rotation_threshold, double translation_threshold, int max_log, int* n_active)
 {
   __shared__ float s_step[16];
+  __shared__ int s_apply;
   __shared__ TileNn nn;
   __syncthreads();
   if (threadIdx.x < 16) s_step[threadIdx.x] = __ldcg(&j.st->step[threadIdx.x]);
+  if (threadIdx.x == 16) s_apply = __ldcg(&j.st->iterations) > 0 ? 1 : 0;  // iterations completed so far = index of this one
   __syncthreads();
+  const int apply_step = s_apply;
   long long v[NSUM];
 #pragma unroll
   for (int k = 0; k < NSUM; ++k) v[k] = 0;
@@ -467,57 +488,40 @@ __device__ __forceinline__ void icp_tile(const IcpJob& j, int tile, int apply_st
   }
 }
 
-// tile_pref[k] = first tile of the k-th active pair, tile_pair[k] = its job index, tile_pair[n_jobs] = number of active pairs
-__global__ void __launch_bounds__(IB) icp_persistent_kernel(const IcpJob* __restrict__ jobs, int n_jobs, IcpLoop* loop, int* tile_pref,
-                                                            int* tile_pair, double max_dist_sqr, int rv, int max_iterations,
-                                                            double rotation_threshold, double translation_threshold, int max_log)
+__global__ void __launch_bounds__(IB) icp_persistent_kernel(const IcpJob* __restrict__ jobs, int n_jobs, IcpLoop* loop, double max_dist_sqr,
+                                                            int rv, int max_iterations, double rotation_threshold,
+                                                            double translation_threshold, int max_log)
 {
-  cg::grid_group grid = cg::this_grid();
-  __shared__ int s_tile, s_nact;
+  __shared__ int s_pair, s_tile;
+  int cur = 0;  // all blocks walk the job list (sorted by target) from the front: neighbouring blocks share a target's tables in L2
   for (;;) {
-    const int total = __ldcg(&loop->total_tiles);
-    if (total == 0) break;
-    const int it = __ldcg(&loop->iteration);
-    if (threadIdx.x == 0) s_nact = __ldcg(&tile_pair[n_jobs]);
-    for (;;) {
-      __syncthreads();
-      if (threadIdx.x == 0) s_tile = atomicAdd(&loop->next_tile, 1);
-      __syncthreads();
-      const int tile = s_tile;
-      if (tile >= total) break;
-      // owner of the tile: last k with tile_pref[k] <= tile
-      int lo = 0, hi = s_nact - 1;
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (__ldcg(&tile_pref[mid]) <= tile) lo = mid;
-        else hi = mid - 1;
-      }
-      const IcpJob& j = jobs[__ldcg(&tile_pair[lo])];
-      icp_tile(j, tile - __ldcg(&tile_pref[lo]), it > 0 ? 1 : 0, max_dist_sqr, rv, max_iterations, rotation_threshold, translation_threshold,
-               max_log, &loop->n_active);
-    }
-    grid.sync();
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      // rebuild the queue from the pairs that are still active (a few hundred at most: one thread)
-      int n = 0, tiles = 0;
-      const int next_it = it + 1;
-      if (next_it < max(max_iterations, 1)) {
-        for (int a = 0; a < n_jobs; ++a)
-          if (__ldcg(&jobs[a].st->active)) {
-            tile_pref[n] = tiles;
-            tile_pair[n] = a;
-            tiles += (jobs[a].ns + IB - 1) / IB;
-            ++n;
+    if (threadIdx.x == 0) {
+      int pair = -1, tile = -1, scanned = 0;
+      while (__ldcg(&loop->n_active) > 0) {
+        const IcpJob& j = jobs[cur];
+        if (__ldcg(j.next_tile) < j.n_tiles) {  // cheap look before the atomic; a stale value only costs one wasted increment
+          const int t = atomicAdd(j.next_tile, 1);
+          if (t < j.n_tiles) {
+            __threadfence();  // what the previous iteration's tiles and its solver wrote is visible to this tile
+            pair = cur;
+            tile = t;
+            break;
           }
+        }
+        cur = cur + 1 == n_jobs ? 0 : cur + 1;
+        if (++scanned >= n_jobs) {  // nothing to hand out right now: the remaining pairs are between two iterations
+          scanned = 0;
+          __nanosleep(500);
+        }
       }
-      tile_pref[n] = tiles;
-      tile_pair[n_jobs] = n;
-      loop->iteration = next_it;
-      loop->next_tile = 0;
-      __threadfence();
-      loop->total_tiles = tiles;
+      s_pair = pair;
+      s_tile = tile;
     }
-    grid.sync();
+    __syncthreads();
+    const int pair = s_pair, tile = s_tile;
+    if (pair < 0) break;
+    icp_tile(jobs[pair], tile, max_dist_sqr, rv, max_iterations, rotation_threshold, translation_threshold, max_log, &loop->n_active);
+    __syncthreads();
   }
 }
 
@@ -639,6 +643,11 @@ void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<D
   }
   const int A = (int)act.size();
   if (A == 0) return;
+  // Pairs that share a target run back to back: the blocks all start at the first job and move on together, so at any time
+  // only a few targets' tables (cell starts, reach grid, points: ~17 MB per 250 k-point map) are live and stay in L2.  In
+  // row-major pair order the 32 targets of config 3 (550 MB of tables) were revisited round-robin — a DRAM-latency-bound
+  // gather.
+  std::stable_sort(act.begin(), act.end(), [&](int x, int y) { return jobs[x].b < jobs[y].b; });
   size_t tot = 0;
   int mx = 0;
   for (int a = 0; a < A; ++a) {
@@ -686,26 +695,25 @@ void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<D
     ij[a].sums_log = max_log ? slog.p + (size_t)a * max_log * NSUM : nullptr;
     off += (size_t)ij[a].ns;
   }
-  DBuf<IcpJob> dij = to_device(c, ij);
-  // the first iteration's queue: every pair with a non-empty source
-  std::vector<int> pref(A + 1, 0), pairs(A + 1, 0);
+  // per-pair tile counters: open (0) for every pair with a non-empty source, closed otherwise
+  std::vector<int> hnext(A, 0);
   IcpLoop hl;
   memset(&hl, 0, sizeof(hl));
-  int n = 0, tiles = 0;
+  int tiles = 0;
   double bytes = 0;
-  for (int a = 0; a < A; ++a)
-    if (hst[a].active) {
-      pref[n] = tiles;
-      pairs[n] = a;
-      tiles += (ij[a].ns + IB - 1) / IB;
-      ++n;
+  for (int a = 0; a < A; ++a) {
+    ij[a].n_tiles = (ij[a].ns + IB - 1) / IB;
+    if (hst[a].active) {  // at least one iteration runs whatever max_iterations says (PCL's do-while)
+      hl.n_active += 1;
+      tiles += ij[a].n_tiles;
       bytes += 16.0 * (2.0 * ij[a].ns + ij[a].tgt.n);
+    } else {
+      hnext[a] = ij[a].n_tiles;
     }
-  pref[n] = tiles;
-  pairs[A] = n;
-  hl.n_active = n;
-  hl.total_tiles = max_it >= 1 ? tiles : 0;
-  DBuf<int> dpref = to_device(c, pref), dpairs = to_device(c, pairs);
+  }
+  DBuf<int> dnext = to_device(c, hnext);
+  for (int a = 0; a < A; ++a) ij[a].next_tile = dnext.p + a;
+  DBuf<IcpJob> dij = to_device(c, ij);
   DBuf<IcpLoop> dloop(c, 1);
   dloop.upload(c, &hl, 1);
   const int iblocks = std::max(1, std::min((mx + 255) / 256, 148 * 8));
@@ -713,25 +721,15 @@ void icp_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector<D
   const double max_dist_sqr = max_dist * max_dist;
   const float leaf = idx[jobs[act[0]].b].v.leaf;
   const int rv = (int)std::ceil(max_dist / (double)leaf) + 1;
-  if (hl.total_tiles > 0) {
-    // persistent cooperative launch: as many blocks as can be co-resident
+  if (hl.n_active > 0) {
+    // persistent launch: as many blocks as can be resident (blocks that find no pair active exit at once)
     int dev = 0, sms = 0, per_sm = 0;
     MM_CUDA(cudaGetDevice(&dev));
     MM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_persistent_kernel, IB, 0));
     const int grid = std::max(1, std::min(sms * std::max(per_sm, 1), tiles));
-    const IcpJob* a_jobs = dij.p;
-    int a_n = A;
-    IcpLoop* a_loop = dloop.p;
-    int* a_pref = dpref.p;
-    int* a_pairs = dpairs.p;
-    double a_md = max_dist_sqr, a_rot = 1.0 - eps, a_tr = eps;
-    int a_rv = rv, a_mi = max_it, a_ml = max_log;
-    void* args[] = {&a_jobs, &a_n, &a_loop, &a_pref, &a_pairs, &a_md, &a_rv, &a_mi, &a_rot, &a_tr, &a_ml};
     MM_BYTES(c, bytes);  // one sweep of every active pair; later iterations repeat it for the pairs still active
-    c.before_launch("icp_persistent_kernel");
-    MM_CUDA(cudaLaunchCooperativeKernel((const void*)icp_persistent_kernel, dim3(grid), dim3(IB), args, 0, c.stream));
-    c.after_launch();
+    MM_LAUNCH(c, icp_persistent_kernel, grid, IB, 0, dij.p, A, dloop.p, max_dist_sqr, rv, max_it, 1.0 - eps, eps, max_log);
   }
   dst.download(c, hst.data(), A);
   std::vector<long long> hlog;
@@ -773,15 +771,20 @@ void score_batch(Ctx& c, const std::vector<CloudView>& clouds, const std::vector
   sums.zero(c);
   std::vector<ScoreJob> sj(P);
   int mx = 0;
-  for (int p = 0; p < P; ++p) {
-    sj[p].tgt = idx[jobs[p].b].v;
-    sj[p].reach = jobs[p].b < (int)reach.size() ? reach[jobs[p].b].v : no_reach();
-    sj[p].src = clouds[jobs[p].a].pts;
-    sj[p].ns = clouds[jobs[p].a].n;
-    for (int k = 0; k < 16; ++k) sj[p].t[k] = T[p][k];
-    sj[p].sums = sums.p + (size_t)p * 2;
-    sj[p].nn_guess = (nn_guess && p < (int)nn_guess->offset.size() && nn_guess->offset[p] >= 0) ? nn_guess->slots.p + nn_guess->offset[p] : nullptr;
-    mx = std::max(mx, sj[p].ns);
+  // launch order = by target (blockIdx.y): the pairs of one target are scored back to back, its tables stay in L2
+  std::vector<int> ord(P);
+  for (int p = 0; p < P; ++p) ord[p] = p;
+  std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return jobs[x].b < jobs[y].b; });
+  for (int q = 0; q < P; ++q) {
+    const int p = ord[q];
+    sj[q].tgt = idx[jobs[p].b].v;
+    sj[q].reach = jobs[p].b < (int)reach.size() ? reach[jobs[p].b].v : no_reach();
+    sj[q].src = clouds[jobs[p].a].pts;
+    sj[q].ns = clouds[jobs[p].a].n;
+    for (int k = 0; k < 16; ++k) sj[q].t[k] = T[p][k];
+    sj[q].sums = sums.p + (size_t)p * 2;
+    sj[q].nn_guess = (nn_guess && p < (int)nn_guess->offset.size() && nn_guess->offset[p] >= 0) ? nn_guess->slots.p + nn_guess->offset[p] : nullptr;
+    mx = std::max(mx, sj[q].ns);
   }
   if (mx == 0) return;
   DBuf<ScoreJob> dsj = to_device(c, sj);

@@ -540,6 +540,81 @@ __device__ __forceinline__ void warp_radius_unordered(const GridView& g, float q
   }
 }
 
+// The same walk for a GROUP of G lanes (G = 8, 16 or 32; the groups of a warp serve different queries and may diverge from
+// each other, so every collective names only the group's lanes).  gmask = the group's lanes, glane = lane index inside it.
+template <int G, typename F>
+__device__ __forceinline__ void group_radius_unordered(const GridView& g, unsigned gmask, int glane, float qx, float qy, float qz, float r2,
+                                                       int rv, F f)
+{
+  const int vx = floor_to_int(qx * g.inv_leaf) - g.min_b[0];
+  const int vy = floor_to_int(qy * g.inv_leaf) - g.min_b[1];
+  const int vz = floor_to_int(qz * g.inv_leaf) - g.min_b[2];
+  int zlo = vz - rv, zhi = vz + rv, ylo = vy - rv, yhi = vy + rv;
+  if (zhi < 0 || yhi < 0 || vx + rv < 0 || zlo >= g.div_v[2] || ylo >= g.div_v[1] || vx - rv >= g.div_v[0]) return;
+  zlo = max(zlo, 0) >> g.shift[2];
+  zhi = min(zhi, g.div_v[2] - 1) >> g.shift[2];
+  ylo = max(ylo, 0) >> g.shift[1];
+  yhi = min(yhi, g.div_v[1] - 1) >> g.shift[1];
+  const int ny = yhi - ylo + 1;
+  const int n_rows = (zhi - zlo + 1) * ny;
+  const unsigned ny_magic = 0xFFFFFFFFu / (unsigned)ny + 1u;
+  const float r2v = r2 * g.inv_leaf * g.inv_leaf;
+  for (int row0 = 0; row0 < n_rows; row0 += G) {
+    int s = 0, e = 0;
+    const int row = row0 + glane;
+    if (row < n_rows) {
+      const int rq = (int)__umulhi((unsigned)row, ny_magic);  // row / ny (exact for row < 2^18, ny < 512)
+      const int cz = zlo + rq, cy = ylo + (row - rq * ny);
+      const int z0 = cz << g.shift[2], z1 = z0 + (1 << g.shift[2]) - 1;
+      const int y0 = cy << g.shift[1], y1 = y0 + (1 << g.shift[1]) - 1;
+      const float fz = (float)max(max(max(z0 - vz, vz - z1), 0) - 1, 0);
+      const float fy = (float)max(max(max(y0 - vy, vy - y1), 0) - 1, 0);
+      const float rem = r2v - fz * fz - fy * fy;
+      if (rem >= 0.0f) {
+        const int rx = (int)sqrtf(rem) + 2;
+        int xlo = vx - rx, xhi = vx + rx;
+        if (xhi >= 0 && xlo < g.div_v[0]) {
+          xlo = max(xlo, 0) >> g.shift[0];
+          xhi = min(xhi, g.div_v[0] - 1) >> g.shift[0];
+          const int base = (cz * g.dim[1] + cy) * g.dim[0];
+          s = g.cell_start[base + xlo];
+          e = g.cell_start[base + xhi + 1];
+        }
+      }
+    }
+    int incl = e - s;
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) {
+      const int t = __shfl_up_sync(gmask, incl, o, G);
+      if (glane >= o) incl += t;
+    }
+    const int total = __shfl_sync(gmask, incl, G - 1, G);
+    const int excl = incl - (e - s);
+    for (int t0 = 0; t0 < total; t0 += G) {
+      const int t = t0 + glane;
+      int L = 0;  // owner row of flattened candidate t: smallest L with incl[L] > t
+#pragma unroll
+      for (int step = G / 2; step >= 1; step >>= 1) {
+        const int v = __shfl_sync(gmask, incl, L + step - 1, G);
+        if (v <= t) L += step;
+      }
+      L = min(L, G - 1);
+      const int ls = __shfl_sync(gmask, s, L, G), le = __shfl_sync(gmask, excl, L, G);
+      bool valid = false;
+      int k = 0;
+      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+      float d2 = 0.f;
+      if (t < total) {
+        k = ls + (t - le);
+        p = g.pts[k];
+        d2 = em::dist2_3(qx, qy, qz, p.x, p.y, p.z);
+        valid = d2 < r2;
+      }
+      f(valid, k, p, d2);
+    }
+  }
+}
+
 // Nearest neighbour among points with (double)d2 <= bound; ties -> lower
 // original index.  Rows are visited outward from the query row so the running
 // best prunes the rest.  rv = ceil(sqrt(bound) / leaf) + 1 voxels.

@@ -66,34 +66,41 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
   return r;
 }
 
-// one block per segment: exclusive scan over (digit-major, tile-minor)
-__global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t* __restrict__ hist, const Seg* __restrict__ segs, int tiles_max)
+// Exclusive scan of the tile histogram in (digit-major, tile-minor) order, two levels so that ONE long segment (composeMaps:
+// 40 M points = 9 766 tiles) is not scanned by a single block: one block per (segment, digit) scans that digit's tile counts
+// in place and leaves the digit's total; a second, tiny kernel turns the 256 totals of a segment into digit bases, which the
+// scatter adds.
+__global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t* __restrict__ hist, const Seg* __restrict__ segs, int tiles_max,
+                                                      uint32_t* __restrict__ digit_total)
 {
   __shared__ uint32_t ws[32];
-  const Seg sg = segs[blockIdx.x];
+  const Seg sg = segs[blockIdx.y];
   const int ntiles = (sg.n + RS_TILE - 1) / RS_TILE;
-  const int total_e = 256 * ntiles;
+  uint32_t* h = hist + ((size_t)blockIdx.y * 256 + blockIdx.x) * tiles_max;
   uint32_t carry = 0;
-  for (int base = 0; base < total_e; base += 1024) {
-    const int e = base + threadIdx.x;
-    uint32_t v = 0;
-    size_t addr = 0;
-    if (e < total_e) {
-      const int d = e / ntiles, t = e - d * ntiles;
-      addr = ((size_t)blockIdx.x * 256 + d) * tiles_max + t;
-      v = hist[addr];
-    }
+  for (int base = 0; base < ntiles; base += 1024) {
+    const int t = base + threadIdx.x;
+    const uint32_t v = t < ntiles ? h[t] : 0;
     uint32_t tot;
     const uint32_t ex = block_exclusive_scan<1024>(v, ws, &tot);
-    if (e < total_e) hist[addr] = carry + ex;
+    if (t < ntiles) h[t] = carry + ex;
     carry += tot;
   }
+  if (threadIdx.x == 0) digit_total[blockIdx.y * 256 + blockIdx.x] = carry;
+}
+
+__global__ void __launch_bounds__(256) rs_digit_scan_kernel(uint32_t* __restrict__ digit_total)
+{
+  __shared__ uint32_t ws[8];
+  uint32_t tot;
+  const uint32_t v = digit_total[blockIdx.x * 256 + threadIdx.x];
+  digit_total[blockIdx.x * 256 + threadIdx.x] = block_exclusive_scan<256>(v, ws, &tot);
 }
 
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                                const Seg* __restrict__ segs, int shift, const uint32_t* __restrict__ hist,
-                                                               int tiles_max)
+                                                               int tiles_max, const uint32_t* __restrict__ digit_base)
 {
   const Seg sg = segs[blockIdx.y];
   const int tile = blockIdx.x;
@@ -132,7 +139,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* 
       whist[ww][d] = run;
       run += t;
     }
-    gbase[d] = hist[((size_t)blockIdx.y * 256 + d) * tiles_max + tile];
+    gbase[d] = digit_base[blockIdx.y * 256 + d] + hist[((size_t)blockIdx.y * 256 + d) * tiles_max + tile];
   }
   __syncthreads();
   uint32_t* kout = keys_out + sg.off;
@@ -231,7 +238,7 @@ void radix_sort_pairs_batch(Ctx& c, uint32_t* keys, uint32_t* vals, uint32_t* ke
   if (max_n == 0 || nbits <= 0) return;
   const int tiles_max = (max_n + RS_TILE - 1) / RS_TILE;
   DBuf<Seg> dsegs = to_device(c, segs);
-  DBuf<uint32_t> hist(c, (size_t)segs.size() * 256 * tiles_max);
+  DBuf<uint32_t> hist(c, (size_t)segs.size() * 256 * tiles_max), digit(c, segs.size() * 256);
   const dim3 grid(tiles_max, (unsigned)segs.size());
   uint32_t *kin = keys, *vin = vals, *kout = keys_tmp, *vout = vals_tmp;
   for (int shift = 0; shift < nbits; shift += 8) {
@@ -239,9 +246,10 @@ void radix_sort_pairs_batch(Ctx& c, uint32_t* keys, uint32_t* vals, uint32_t* ke
     for (const Seg& s : segs) tot_n += s.n;
     MM_BYTES(c, 4.0 * tot_n);
     MM_LAUNCH(c, rs_hist_kernel, grid, RS_THREADS, 0, kin, dsegs.p, shift, hist.p, tiles_max);
-    MM_LAUNCH(c, rs_scan_kernel, (unsigned)segs.size(), 1024, 0, hist.p, dsegs.p, tiles_max);
+    MM_LAUNCH(c, rs_scan_kernel, dim3(256, (unsigned)segs.size()), 1024, 0, hist.p, dsegs.p, tiles_max, digit.p);
+    MM_LAUNCH(c, rs_digit_scan_kernel, (unsigned)segs.size(), 256, 0, digit.p);
     MM_BYTES(c, 16.0 * tot_n);
-    MM_LAUNCH(c, rs_scatter_kernel, grid, RS_THREADS, 0, kin, vin, kout, vout, dsegs.p, shift, hist.p, tiles_max);
+    MM_LAUNCH(c, rs_scatter_kernel, grid, RS_THREADS, 0, kin, vin, kout, vout, dsegs.p, shift, hist.p, tiles_max, digit.p);
     std::swap(kin, kout);
     std::swap(vin, vout);
   }

@@ -33,15 +33,40 @@ def pair_costs(ij, n_points, n_keypoints, dim):
     return [float(n_keypoints[i]) * n_keypoints[j] * dim * 2e-3 + 4.0 * n_points[i] + n_points[j] for i, j in ij]
 
 
-def lpt_assign(costs, n_bins: int):
-    """Longest-processing-time-first assignment; deterministic, identical on every rank."""
-    order = np.argsort(-np.asarray(costs, np.float64), kind="stable")
-    load = np.zeros(n_bins)
+def lpt_assign(costs, n_bins: int, ij=None):
+    """Who registers which pair (Python restatement of csrc/dist.cu::lpt_assign; deterministic, identical on every rank).
+    Pairs are dealt out in chunks that share a TARGET map (a rank builds the neighbour index and reach grid of every target
+    its pairs name): the pairs of one target in ascending source order, cut into chunks of at most a quarter of a rank's
+    fair share of the total cost, chunks assigned longest-processing-time-first.  Without `ij` every pair is its own chunk."""
+    costs = np.asarray(costs, np.float64)
     owner = np.zeros(len(costs), np.int64)
-    for k in order:
+    if len(costs) == 0 or n_bins <= 1:
+        return owner
+    if ij is None:
+        chunks = [([k], float(costs[k])) for k in range(len(costs))]
+    else:
+        cap = float(costs.sum()) / n_bins / 4.0
+        by_target = {}
+        for k, (_a, b) in enumerate(ij):
+            by_target.setdefault(int(b), []).append(k)
+        chunks = []
+        for b in sorted(by_target):
+            v = by_target[b]
+            i = 0
+            while i < len(v):
+                ids, c = [], 0.0
+                while True:
+                    c += float(costs[v[i]]); ids.append(v[i]); i += 1
+                    if not (i < len(v) and c + float(costs[v[i]]) <= cap):
+                        break
+                chunks.append((ids, c))
+    order = np.argsort(-np.array([c for _, c in chunks]), kind="stable")
+    load = np.zeros(n_bins)
+    for ci in order:
+        ids, c = chunks[ci]
         b = int(np.argmin(load))
-        owner[k] = b
-        load[b] += costs[k]
+        load[b] += c
+        owner[ids] = b
     return owner
 
 

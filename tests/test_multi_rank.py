@@ -61,7 +61,7 @@ def _worker(rank, world, port, n_maps, seed, q):
         assert g_pts == [int(x) for x in n_pts] and g_kp == [int(x) for x in n_kp]
         # stage B: shard the pair list, "register" the local share, exchange
         ij = sh.pair_list(g_kp)
-        owner = sh.lpt_assign(sh.pair_costs(ij, g_pts, g_kp, 33), world)
+        owner = sh.lpt_assign(sh.pair_costs(ij, g_pts, g_kp, 33), world, ij)
         mine = [k for k in range(len(ij)) if owner[k] == rank]
         T = np.stack([tab[ij[k]][0] for k in mine]) if mine else np.zeros((0, 4, 4), np.float32)
         conf = np.array([tab[ij[k]][1] for k in mine])
@@ -245,12 +245,16 @@ def test_library_pair_plan_matches_python_restatement(mm):
         pairs, owner = mm.dist_plan(n_pts, n_kp, 33, world)
         ij = sh.pair_list(n_kp.tolist())
         assert pairs.tolist() == [list(p) for p in ij]
-        want = sh.lpt_assign(sh.pair_costs(ij, n_pts.tolist(), n_kp.tolist(), 33), world) if ij else np.zeros(0, np.int64)
+        want = sh.lpt_assign(sh.pair_costs(ij, n_pts.tolist(), n_kp.tolist(), 33), world, ij) if ij else np.zeros(0, np.int64)
         assert owner.tolist() == [int(x) for x in want]
-        if len(ij) >= world:
+        if len(ij) >= 4 * world:
             costs = np.array(sh.pair_costs(ij, n_pts.tolist(), n_kp.tolist(), 33))
             loads = np.array([costs[owner == r].sum() for r in range(world)])
-            assert loads.max() <= loads.mean() + costs.max()  # LPT: no rank is more than one job above the mean
+            assert loads.max() <= loads.mean() * 1.25 + costs.max()  # chunks are at most a quarter of a fair share
+            if n_maps == 32 and world == 8:
+                # the point of chunking by target: a rank names few target maps (it builds their index and reach grid)
+                targets = [len({ij[k][1] for k in range(len(ij)) if owner[k] == r}) for r in range(world)]
+                assert max(targets) <= 12, targets
         covered = []
         for r in range(world):
             first, count = mm.dist_block(r, world, n_maps)
