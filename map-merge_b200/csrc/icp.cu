@@ -117,6 +117,55 @@ __device__ __forceinline__ bool reach_lookup(const GridView& g, const ReachView&
   return true;
 }
 
+// Walk downhill on the reach grid from cell (x, y, z) — one axis step at a time to the neighbour with the smallest lower
+// bound — until a cell with lower bound 0 (an occupied voxel in its 3 x 3 x 3 block).  The field is a min-plus transform with
+// the per-axis cost max(|d| - 1, 0)^2, so while the value is positive some axis neighbour is strictly smaller: the walk
+// ends after at most sum(|d_i| - 1) steps.  Returns false if it leaves the grid or stalls (saturated values).
+__device__ __forceinline__ bool reach_descend(const ReachView& r, int& x, int& y, int& z, int cur)
+{
+  for (int step = 0; step < 48 && cur > 0; ++step) {
+    int best = cur, bx = x, by = y, bz = z;
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+      const int nx = x + (t == 0) - (t == 1), ny = y + (t == 2) - (t == 3), nz = z + (t == 4) - (t == 5);
+      if (nx < 0 || ny < 0 || nz < 0 || nx >= r.dim[0] || ny >= r.dim[1] || nz >= r.dim[2]) continue;
+      const int v = (int)__ldg(&r.lb2[((size_t)nz * r.dim[1] + ny) * r.dim[0] + nx]);
+      if (v < best) {
+        best = v;
+        bx = nx;
+        by = ny;
+        bz = nz;
+      }
+    }
+    if (best >= cur) return false;
+    cur = best;
+    x = bx;
+    y = by;
+    z = bz;
+  }
+  return cur == 0;
+}
+
+// squared distance from the query to the nearest point of the 3 x 3 x 3 voxel block around index voxel (vx, vy, vz) — any
+// point there is a real target point, so the result is an upper bound of the nearest-neighbour distance; 3e38 if none
+__device__ __forceinline__ float block27_any(const GridView& g, int vx, int vy, int vz, float qx, float qy, float qz)
+{
+  float best = 3.0e38f;
+  const int xlo = max(vx - 1, 0), xhi = min(vx + 1, g.div_v[0] - 1);
+  if (xlo > xhi) return best;
+  for (int t = 0; t < 9; ++t) {
+    const int cz = vz + t / 3 - 1, cy = vy + t % 3 - 1;
+    if (cz < 0 || cz >= g.div_v[2] || cy < 0 || cy >= g.div_v[1]) continue;
+    const int base = (cz * g.dim[1] + cy) * g.dim[0];
+    const int s = __ldg(&g.cell_start[base + xlo]), e = __ldg(&g.cell_start[base + xhi + 1]);
+    for (int k = s; k < e; ++k) {
+      const float4 p = g.pts[k];
+      best = fminf(best, em::dist2_3(qx, qy, qz, p.x, p.y, p.z));
+    }
+  }
+  return best;
+}
+
 // The 3 x 3 x 3 voxel block around the query in an index with one-voxel cells: nine (z, y) rows of three cells each, every
 // row one contiguous run of points.  All nine run bounds are loaded up front (independent loads), rows are skipped when
 // their slab distance already exceeds the running best.  Every point outside the block is at least one voxel away, so a
@@ -236,6 +285,18 @@ __device__ __forceinline__ bool tile_nearest(TileNn& sh, const GridView& g, cons
         r2 = fminf(r2, (ub * ub * 1.001f + 0.01f) * g.leaf * g.leaf);
       }
       block_has_points = inside && lb2 == 0;  // lower bound 0 <=> an occupied voxel inside the 3 x 3 x 3 block
+      // A query off the surface: the voxel diagonal slack above makes the window (and with it the number of rows and
+      // candidates phase 2 has to touch) 2-3x larger than necessary.  Walking downhill on the reach grid finds a REAL target
+      // point nearby in a few steps; its distance is the tightest radius one can ask for without knowing the answer.
+      if (!rejected && inside && lb2 > 0 && lb2 < r.none && guess_slot < 0 && g.shift[0] == 0 && g.shift[1] == 0 && g.shift[2] == 0) {
+        int cx = floor_to_int(qx * g.inv_leaf) - g.min_b[0] - r.org[0];
+        int cy = floor_to_int(qy * g.inv_leaf) - g.min_b[1] - r.org[1];
+        int cz = floor_to_int(qz * g.inv_leaf) - g.min_b[2] - r.org[2];
+        if (reach_descend(r, cx, cy, cz, lb2)) {
+          const float dd = block27_any(g, cx + r.org[0], cy + r.org[1], cz + r.org[2], qx, qy, qz);
+          if (dd < 3.0e38f) r2 = fminf(r2, dd);
+        }
+      }
     }
     if (!rejected) {
       bool certain = false;

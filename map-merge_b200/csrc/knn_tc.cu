@@ -36,18 +36,21 @@ constexpr int KMAXTC = 16;
 constexpr int ACC_BUFS = 4;                 // TMEM accumulator buffers (4 x 128 columns = all 512): the epilogue warps may lag the
                                             // MMA by three tiles, so one warp's burst of exact evaluations no longer stalls the rest
 constexpr int EPI_WARPS = 8;                // two per scheduler: warps w and w + 4 share a TMEM lane quarter and split every tile's columns
-constexpr int TC_THREADS = 64 + EPI_WARPS * 32;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
+constexpr int EVAL_WARPS = 6;                // candidate pass only: warps that evaluate pending candidates exactly, any row of the CTA
+constexpr int TC_THREADS = 64 + (EPI_WARPS + EVAL_WARPS) * 32;  // warp 0: TMA producer, 1: MMA issuer + TMEM owner, 2-9: epilogue, 10-15: evaluators
+constexpr int N_SLOTS = TM * 2;              // one pending list per (query row, column half)
 constexpr int LIST_BYTES = TM * 2 * LIST_STRIDE * 2;
-constexpr int PARK_BYTES = TM * KMAXTC * 8;  // the half-merge parks (distance, index) lists here: separate from the pending lists
+constexpr int PARK_BYTES = N_SLOTS * KMAXTC * 8;  // per slot: the k best (distance, index) so far (candidate pass) / parked bounds (threshold pass)
+constexpr int SLOT_STATE_BYTES = N_SLOTS * 16 + TM * 4 + 64;  // tail, head, exact bound, busy flag per slot; (1 - ES)||a'||^2 per row; counters
 constexpr int APAD = 36;                    // floats per row of the shared-memory copy of the original query rows (D = 33 path)
 constexpr int AORIG_BYTES = TM * APAD * 4;
 // shared memory: [A resident (3 k-blocks for D = 33, else 4)] [B (or A + B) stages] [pending lists] [parking] [query rows] [barriers]
 __host__ __device__ constexpr int tc_a_kb(int dreg, bool a_res) { return a_res ? (dreg > 0 ? 3 : A_RES_MAX_KB) : 0; }
-__host__ __device__ constexpr int tc_stages(int dreg, bool a_res) { return a_res ? (dreg > 0 ? 6 : 5) : 4; }
+__host__ __device__ constexpr int tc_stages(int dreg, bool a_res) { return a_res ? (dreg > 0 ? 5 : 4) : 3; }
 __host__ __device__ constexpr size_t tc_smem(int dreg, bool a_res)
 {
   return (size_t)tc_a_kb(dreg, a_res) * KB_BYTES + (size_t)tc_stages(dreg, a_res) * (a_res ? 1 : 2) * KB_BYTES + LIST_BYTES + PARK_BYTES +
-         AORIG_BYTES + 1024 + 256;
+         AORIG_BYTES + SLOT_STATE_BYTES + 1024 + 256;
 }
 
 struct TcJob {
@@ -146,7 +149,8 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t* r)
 }
 
 // named barrier for the epilogue warps only (the producer / MMA warps never join it)
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
+template <int THREADS>
+__device__ __forceinline__ void named_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 
 __device__ __forceinline__ float fmin3(float a, float b, float c)
 {
@@ -213,10 +217,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
   uint8_t* a_res = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* tiles = a_res + A_RES_BYTES;
   unsigned short* list = (unsigned short*)(tiles + (size_t)STAGES * STAGE_BYTES);  // [TM][2][LIST_STRIDE]
-  float* park_d = (float*)(list + TM * 2 * LIST_STRIDE);                           // [TM][KCAP] distances, then indices
-  int* park_i = (int*)(park_d + TM * KMAXTC);
-  float* a_orig = (float*)(park_i + TM * KMAXTC);                                  // [TM][APAD] (D = 33 path)
-  uint64_t* full_bar = (uint64_t*)(a_orig + TM * APAD);
+  float* park_d = (float*)(list + TM * 2 * LIST_STRIDE);                           // [N_SLOTS][KCAP] distances, then indices
+  int* park_i = (int*)(park_d + N_SLOTS * KMAXTC);
+  float* a_orig = (float*)(park_i + N_SLOTS * KMAXTC);                             // [TM][APAD] (D = 33 path)
+  uint32_t* s_tail = (uint32_t*)(a_orig + TM * APAD);                              // [N_SLOTS] entries published by the producer
+  uint32_t* s_head = s_tail + N_SLOTS;                                             // [N_SLOTS] entries consumed by the evaluators
+  float* s_thr = (float*)(s_head + N_SLOTS);                                       // [N_SLOTS] exact k-th distance so far, accumulator space
+  uint32_t* s_busy = (uint32_t*)(s_thr + N_SLOTS);                                 // [N_SLOTS] an evaluator warp owns the slot
+  float* s_nalow = (float*)(s_busy + N_SLOTS);                                     // [TM]
+  uint32_t* s_done = (uint32_t*)(s_nalow + TM);                                    // producers that have finished
+  uint64_t* full_bar = (uint64_t*)(s_done + 16);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + ACC_BUFS;
@@ -305,7 +315,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
         tc_commit(&tmem_full[buf]);  // accumulator ready for the epilogue
       }
     }
-  } else {
+  } else if (warp < 2 + EPI_WARPS) {
     // ===== epilogue: one query row per thread, two warps per TMEM lane quarter (each takes 64 of a tile's 128 columns) =====
     // Per (row, column half):
     //   * t5[]: the KCAP smallest UPPER bounds seen so far, fed with one value per 32-column chunk — the chunk's smallest
@@ -329,7 +339,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
     const float na = live ? job.normA[row] : 0.f;
     const float na_low = (1.0f - TC_ERR_STORE) * na;  // acc + na_low <= exact distance
     const float INF = __int_as_float(0x7f800000);
-    unsigned evals = 0, flushes = 0;
     if constexpr (PASS == 0) {
       // ---- threshold pass: K-th smallest upper bound over one value per 32-column chunk (chunk minima are distinct columns)
       float t5[KCAP];
@@ -388,7 +397,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
 #pragma unroll
         for (int t = 0; t < KCAP; ++t) park_d[lrow * KCAP + t] = t5[t];
       }
-      epi_bar_sync();
+      named_bar_sync<EPI_WARPS * 32>();
       if (half == 0 && live) {
         int ia = 0, ib = 0;
         float kth = INF;
@@ -403,208 +412,261 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
         job.thr[row] = kth;
       }
     } else {
-    float bd[KCAP];
-    int bi[KCAP];
-#pragma unroll
-    for (int i = 0; i < KCAP; ++i) { bd[i] = INF; bi[i] = -1; }
-    // shared copy of the original query rows (D = 33 path)
-    if (DREG > 0) {
-      for (int e = (ew * 32 + lane); e < TM * (APAD / 4); e += EPI_WARPS * 32) {
-        const int r = e / (APAD / 4), t = e - r * (APAD / 4);
-        const float4 v = (m0 + r < job.na) ? job.padA[(size_t)(m0 + r) * (APAD / 4) + t] : make_float4(0.f, 0.f, 0.f, 0.f);
-        reinterpret_cast<float4*>(a_orig)[r * (APAD / 4) + t] = v;
-      }
-      epi_bar_sync();
-    }
-    float thr = live ? job.thr[row] : -INF;  // acc-space filter bound from the threshold pass, only ever shrinks
-    float thr_exact = INF;
-    int n = 0;
-    unsigned short* my_list = list + (lrow * 2 + half) * LIST_STRIDE;
-
-    // the warp evaluates up to 32 pending candidates of lane L's row exactly and merges them into L's top list
-    auto flush = [&](int L) {
-      const int nL = __shfl_sync(0xffffffffu, n, L);
-      const int cnt = min(nL, 32);
-      const int rL = q * 32 + L;
-      unsigned short* lst = list + (rL * 2 + half) * LIST_STRIDE;
-      const int jcol = lane < cnt ? (int)lst[lane] : 0;
-      float d = INF;
-      if (lane < cnt) {
-        float acc = 0.f;
-        if (DREG > 0) {
-          constexpr int Q = DREG > 0 ? (DREG + 3) / 4 : 1;
-          const float4* bp = job.padB + (size_t)jcol * Q;
-          const float4* ap = reinterpret_cast<const float4*>(a_orig + rL * APAD);
-          float a_[Q * 4], b_[Q * 4];
-#pragma unroll
-          for (int t = 0; t < Q; ++t) {
-            const float4 v = __ldg(&bp[t]);
-            b_[4 * t] = v.x; b_[4 * t + 1] = v.y; b_[4 * t + 2] = v.z; b_[4 * t + 3] = v.w;
-            const float4 w = ap[t];
-            a_[4 * t] = w.x; a_[4 * t + 1] = w.y; a_[4 * t + 2] = w.z; a_[4 * t + 3] = w.w;
-          }
-#pragma unroll
-          for (int t = 0; t < DREG; ++t) {
-            const float diff = a_[t] - b_[t];
-            acc += diff * diff;
-          }
-        } else {
-          const float* a = job.origA + (size_t)(m0 + rL) * D;
-          const float* b = job.origB + (size_t)jcol * D;
-          for (int t = 0; t < D; ++t) {
-            const float diff = __ldg(&a[t]) - __ldg(&b[t]);
-            acc += diff * diff;
-          }
-        }
-        d = acc;
-      }
-      const float kth = __shfl_sync(0xffffffffu, bd[KCAP - 1], L);
-      unsigned better = __ballot_sync(0xffffffffu, d < kth);
-      while (better) {
-        const int b = __ffs(better) - 1;
-        const float dv = __shfl_sync(0xffffffffu, d, b);
-        const int jv = __shfl_sync(0xffffffffu, jcol, b);
-        if (lane == L) topk_insert<KCAP>(bd, bi, dv, jv);
-        // the k-th distance just shrank: candidates that no longer beat it drop out (in the first flushes most of the 32 do)
-        const float kth2 = __shfl_sync(0xffffffffu, bd[KCAP - 1], L);
-        better &= __ballot_sync(0xffffffffu, d < kth2) & ~((2u << b) - 1u);
-      }
-      // the rest of the list moves to the front
-      const int rest = nL - cnt;
-      unsigned short moved = 0;
-      if (lane < rest) moved = lst[32 + lane];
-      __syncwarp();
-      if (lane < rest) lst[lane] = moved;
-      __syncwarp();
-      if (lane == L) {
-        n = rest;
-        evals += (unsigned)cnt;
-        ++flushes;
-        thr_exact = (bd[KCAP - 1] - na_low) + 1e-6f * (1.0f + fabsf(bd[KCAP - 1]) + na);  // acc <= exact k-th - na_low (+ rounding pad)
-        thr = fminf(thr, thr_exact);
-      }
-    };
-
-    const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int n_chunks = n_tiles * 2;  // this warp's chunks: two per tile
-    uint32_t r[32], rn[32];
-    mbar_wait(&tmem_full[0], 0);
-    tc_fence_after();
-    tmem_ld_32x32_issue(tmem_row + (uint32_t)(half * 64), r);
-    tmem_ld_wait(r);
-    for (int ch = 0; ch < n_chunks; ++ch) {
-      const int nt = ch >> 1, c0 = half * 64 + (ch & 1) * 32;
-      const bool tile_end = (ch & 1) == 1;
-      if (ch + 1 < n_chunks) {
-        const int nt1 = (ch + 1) >> 1, buf1 = nt1 % ACC_BUFS;
-        if (tile_end) {
-          mbar_wait(&tmem_full[buf1], (uint32_t)(nt1 / ACC_BUFS) & 1u);
-          tc_fence_after();
-        }
-        tmem_ld_32x32_issue(tmem_row + (uint32_t)(buf1 * TN + half * 64 + ((ch + 1) & 1) * 32), rn);
-      }
-      const int jbase = nt * TN + c0;
-      const int left = job.nb - jbase;  // columns past nb are zero rows of the B form: keep them out of the minimum
-      if (AUDIT) {
-        if (live) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (c < left) job.audit[(size_t)row * job.nb + jbase + c] = __uint_as_float(r[c]);
-        }
-      }
-      if (left < 32) {
-#pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (c >= left) r[c] = 0x7f800000u;
-      }
-      if (left > 0) {
-        // smallest accumulator of the chunk: 16 three-input minima
-        float m = fmin3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
-#pragma unroll
-        for (int c = 3; c < 31; c += 2) m = fmin3(m, __uint_as_float(r[c]), __uint_as_float(r[c + 1]));
-        m = fminf(m, __uint_as_float(r[31]));
-        if (m <= thr) {
-          // which columns pass (one compare + one bit each), then one append per set bit
-          uint32_t m0_ = 0, m1_ = 0, m2_ = 0, m3_ = 0;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            m0_ |= (__uint_as_float(r[c]) <= thr) ? (1u << c) : 0u;
-            m1_ |= (__uint_as_float(r[8 + c]) <= thr) ? (1u << (8 + c)) : 0u;
-            m2_ |= (__uint_as_float(r[16 + c]) <= thr) ? (1u << (16 + c)) : 0u;
-            m3_ |= (__uint_as_float(r[24 + c]) <= thr) ? (1u << (24 + c)) : 0u;
-          }
-          uint32_t msk = (m0_ | m1_) | (m2_ | m3_);
-          if (left < 32) msk &= (1u << left) - 1u;  // columns past nb (masked to +inf above) would still pass an infinite bound
-          while (msk) {
-            const int c = __ffs(msk) - 1;
-            msk &= msk - 1;
-            my_list[n++] = (unsigned short)(jbase + c);
-          }
-        }
-      }
-      __syncwarp();
-      // full lists are evaluated by the whole warp
-      unsigned full = __ballot_sync(0xffffffffu, n >= 32);
-      while (full) {
-        const int L = __ffs(full) - 1;
-        flush(L);
-        full = __ballot_sync(0xffffffffu, n >= 32);
-      }
-      tmem_ld_wait(rn);  // rn has landed (and, at a tile end, every read of this tile's accumulator is done)
-      if (tile_end) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[nt % ACC_BUFS]);
-      }
-#pragma unroll
-      for (int c = 0; c < 32; ++c) r[c] = rn[c];
-    }
-    // what is still pending
-    unsigned pending = __ballot_sync(0xffffffffu, n > 0);
-    while (pending) {
-      const int L = __ffs(pending) - 1;
-      flush(L);
-      pending = __ballot_sync(0xffffffffu, n > 0);
-    }
-    // merge the two column halves of every row: half 1 parks its list in shared memory (the pending lists are empty now)
-    epi_bar_sync();
-    if (half == 1) {
+      // ---- candidate pass, producer side: columns whose accumulator is within the row's bound go — index only — into the
+      // row's pending ring in shared memory; the evaluator warps (below) pick full rings up.  The producer never evaluates
+      // anything itself, so its work per chunk is uniform and the eight epilogue warps stay in step with the MMA.
+      const int slot = lrow * 2 + half;
+      unsigned short* my_list = list + slot * LIST_STRIDE;
+      if (half == 0) s_nalow[lrow] = na_low;
+      s_tail[slot] = 0;
+      s_head[slot] = 0;
+      s_busy[slot] = 0;
+      s_thr[slot] = INF;
 #pragma unroll
       for (int t = 0; t < KCAP; ++t) {
-        park_d[lrow * KCAP + t] = bd[t];
-        park_i[lrow * KCAP + t] = bi[t];
+        park_d[slot * KCAP + t] = INF;
+        park_i[slot * KCAP + t] = -1;
       }
-    }
-    epi_bar_sync();
-    if (half == 0 && live) {
-      const int k = job.k;
-      int ia = 0, ib = 0;
-      for (int t = 0; t < k; ++t) {
-        // the smaller (distance, index) of the two heads
-        float da = INF, db = INF;
-        int ja = -1, jb = -1;
-#pragma unroll
-        for (int u = 0; u < KCAP; ++u) {
-          if (u == ia) { da = bd[u]; ja = bi[u]; }
+      if (ew == 0 && lane == 0) *s_done = 0;
+      if (DREG > 0) {
+        for (int e = (ew * 32 + lane); e < TM * (APAD / 4); e += EPI_WARPS * 32) {
+          const int r_ = e / (APAD / 4), t = e - r_ * (APAD / 4);
+          const float4 v = (m0 + r_ < job.na) ? job.padA[(size_t)(m0 + r_) * (APAD / 4) + t] : make_float4(0.f, 0.f, 0.f, 0.f);
+          reinterpret_cast<float4*>(a_orig)[r_ * (APAD / 4) + t] = v;
         }
-        if (ib < KCAP) { db = park_d[lrow * KCAP + ib]; jb = park_i[lrow * KCAP + ib]; }
-        const bool take_b = jb >= 0 && (ja < 0 || db < da || (db == da && jb < ja));
-        const float dsel = take_b ? db : da;
-        const int jsel = take_b ? jb : ja;
-        if (take_b) ++ib; else ++ia;
-        job.idx[(size_t)row * k + t] = jsel;
-        job.dist[(size_t)row * k + t] = jsel >= 0 ? dsel : 0.f;
+      }
+      named_bar_sync<(EPI_WARPS + EVAL_WARPS) * 32>();  // producers + evaluators: rings, bounds and the query rows are in place
+      float thr = live ? job.thr[row] : -INF;  // acc-space filter bound from the threshold pass, only ever shrinks
+      uint32_t tail = 0;
+      const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
+      const int n_chunks = n_tiles * 2;  // this warp's chunks: two per tile
+      uint32_t r[32], rn[32];
+      mbar_wait(&tmem_full[0], 0);
+      tc_fence_after();
+      tmem_ld_32x32_issue(tmem_row + (uint32_t)(half * 64), r);
+      tmem_ld_wait(r);
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        const int nt = ch >> 1, c0 = half * 64 + (ch & 1) * 32;
+        const bool tile_end = (ch & 1) == 1;
+        if (ch + 1 < n_chunks) {
+          const int nt1 = (ch + 1) >> 1, buf1 = nt1 % ACC_BUFS;
+          if (tile_end) {
+            mbar_wait(&tmem_full[buf1], (uint32_t)(nt1 / ACC_BUFS) & 1u);
+            tc_fence_after();
+          }
+          tmem_ld_32x32_issue(tmem_row + (uint32_t)(buf1 * TN + half * 64 + ((ch + 1) & 1) * 32), rn);
+        }
+        const int jbase = nt * TN + c0;
+        const int left = job.nb - jbase;  // columns past nb are zero rows of the B form: keep them out of the minimum
+        if (AUDIT) {
+          if (live) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (c < left) job.audit[(size_t)row * job.nb + jbase + c] = __uint_as_float(r[c]);
+          }
+        }
+        if (left < 32) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c >= left) r[c] = 0x7f800000u;
+        }
+        if (left > 0) {
+          thr = fminf(thr, *(volatile float*)&s_thr[slot]);  // what the evaluators have learned about this row so far
+          // smallest accumulator of the chunk: 16 three-input minima
+          float m = fmin3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
+#pragma unroll
+          for (int c = 3; c < 31; c += 2) m = fmin3(m, __uint_as_float(r[c]), __uint_as_float(r[c + 1]));
+          m = fminf(m, __uint_as_float(r[31]));
+          if (m <= thr) {
+            // which columns pass (one compare + one bit each), then one append per set bit
+            uint32_t m0_ = 0, m1_ = 0, m2_ = 0, m3_ = 0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              m0_ |= (__uint_as_float(r[c]) <= thr) ? (1u << c) : 0u;
+              m1_ |= (__uint_as_float(r[8 + c]) <= thr) ? (1u << (8 + c)) : 0u;
+              m2_ |= (__uint_as_float(r[16 + c]) <= thr) ? (1u << (16 + c)) : 0u;
+              m3_ |= (__uint_as_float(r[24 + c]) <= thr) ? (1u << (24 + c)) : 0u;
+            }
+            uint32_t msk = (m0_ | m1_) | (m2_ | m3_);
+            if (left < 32) msk &= (1u << left) - 1u;  // columns past nb (masked to +inf above) would still pass an infinite bound
+            // room for the whole chunk (the evaluators free 32 entries at a time; a full ring means they are behind)
+            const uint32_t need = (uint32_t)__popc(msk);
+            while (tail + need - *(volatile uint32_t*)&s_head[slot] > (uint32_t)LIST_CAP) __nanosleep(64);
+            while (msk) {
+              const int c = __ffs(msk) - 1;
+              msk &= msk - 1;
+              my_list[tail & (LIST_CAP - 1)] = (unsigned short)(jbase + c);
+              ++tail;
+            }
+            __threadfence_block();
+            *(volatile uint32_t*)&s_tail[slot] = tail;  // publish
+          }
+        }
+        tmem_ld_wait(rn);  // rn has landed (and, at a tile end, every read of this tile's accumulator is done)
+        if (tile_end) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[nt % ACC_BUFS]);
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) r[c] = rn[c];
+      }
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        atomicAdd(s_done, 1u);
       }
     }
-    }
-    if (stats) {
-      const unsigned rows = __reduce_add_sync(0xffffffffu, (live && half == 0) ? 1u : 0u);
-      const unsigned fl = __reduce_add_sync(0xffffffffu, live ? flushes : 0u);
-      const unsigned ev = __reduce_add_sync(0xffffffffu, live ? evals : 0u);
-      if (lane == 0) {
-        atomicAdd(&stats[0], (unsigned long long)rows);
-        atomicAdd(&stats[1], (unsigned long long)fl);
-        atomicAdd(&stats[2], (unsigned long long)ev);
+  } else {
+    // ===== evaluator warps (candidate pass only) =====
+    // Any evaluator warp serves any row of the CTA: it claims a pending ring that holds 32 candidates (or, once the
+    // producers are done, whatever is left), lane c computes the exact sequential FP32 distance of candidate c (query row
+    // broadcast from shared memory, B row as float4 loads), and the few that beat the row's current k-th distance are
+    // inserted — in ring order = ascending column order, strict < — into the row's list, which lives in shared memory.  The
+    // exact k-th distance goes back to the producer as a tighter bound.  Decoupling evaluation from the epilogue warps
+    // matters because the candidates are very unevenly spread over the rows (clustered descriptors): inline evaluation
+    // made every tile wait for the epilogue warp with the most ties.
+    if constexpr (PASS == 1) {
+      const int ev = warp - 2 - EPI_WARPS;
+      const float INF = __int_as_float(0x7f800000);
+      unsigned evals = 0, flushes = 0;
+      named_bar_sync<(EPI_WARPS + EVAL_WARPS) * 32>();
+      int scan0 = ev * (N_SLOTS / EVAL_WARPS);  // evaluators start their sweeps at different slots
+      for (;;) {
+        const bool draining = *(volatile uint32_t*)s_done == (uint32_t)EPI_WARPS;
+        // sweep: every lane looks at 8 slots
+        int found = -1;
+        for (int pass_ = 0; pass_ < N_SLOTS / 32 && found < 0; ++pass_) {
+          const int s_ = (scan0 + pass_ * 32 + lane) & (N_SLOTS - 1);
+          const uint32_t cnt = *(volatile uint32_t*)&s_tail[s_] - *(volatile uint32_t*)&s_head[s_];
+          const bool want = (cnt >= 32u || (draining && cnt > 0u)) && *(volatile uint32_t*)&s_busy[s_] == 0u;
+          const unsigned vote = __ballot_sync(0xffffffffu, want);
+          if (vote) found = (scan0 + pass_ * 32 + (__ffs(vote) - 1)) & (N_SLOTS - 1);
+        }
+        if (found < 0) {
+          if (draining) {
+            // nothing pending anywhere and no producer left: done (a ring another evaluator is working on is its business)
+            bool any = false;
+            for (int s_ = lane; s_ < N_SLOTS; s_ += 32)
+              if (*(volatile uint32_t*)&s_tail[s_] != *(volatile uint32_t*)&s_head[s_] && *(volatile uint32_t*)&s_busy[s_] == 0u) any = true;
+            if (!__any_sync(0xffffffffu, any)) break;
+          } else {
+            __nanosleep(200);
+          }
+          continue;
+        }
+        scan0 = found + 1;
+        int claimed = 0;
+        if (lane == 0) claimed = atomicCAS(&s_busy[found], 0u, 1u) == 0u ? 1 : 0;
+        claimed = __shfl_sync(0xffffffffu, claimed, 0);
+        if (!claimed) continue;
+        __threadfence_block();
+        const uint32_t head = *(volatile uint32_t*)&s_head[found];
+        const uint32_t cnt_all = *(volatile uint32_t*)&s_tail[found] - head;
+        const int cnt = (int)min(cnt_all, 32u);
+        if (cnt > 0) {
+          const int rL = found >> 1;
+          const unsigned short* lst = list + found * LIST_STRIDE;
+          const int jcol = lane < cnt ? (int)lst[(head + lane) & (LIST_CAP - 1)] : 0;
+          float d = INF;
+          if (lane < cnt) {
+            float acc = 0.f;
+            if (DREG > 0) {
+              constexpr int Q = DREG > 0 ? (DREG + 3) / 4 : 1;
+              const float4* bp = job.padB + (size_t)jcol * Q;
+              const float4* ap = reinterpret_cast<const float4*>(a_orig + rL * APAD);
+              float a_[Q * 4], b_[Q * 4];
+#pragma unroll
+              for (int t = 0; t < Q; ++t) {
+                const float4 v = __ldg(&bp[t]);
+                b_[4 * t] = v.x; b_[4 * t + 1] = v.y; b_[4 * t + 2] = v.z; b_[4 * t + 3] = v.w;
+                const float4 w = ap[t];
+                a_[4 * t] = w.x; a_[4 * t + 1] = w.y; a_[4 * t + 2] = w.z; a_[4 * t + 3] = w.w;
+              }
+#pragma unroll
+              for (int t = 0; t < DREG; ++t) {
+                const float diff = a_[t] - b_[t];
+                acc += diff * diff;
+              }
+            } else {
+              const float* a = job.origA + (size_t)(m0 + rL) * D;
+              const float* b = job.origB + (size_t)jcol * D;
+              for (int t = 0; t < D; ++t) {
+                const float diff = __ldg(&a[t]) - __ldg(&b[t]);
+                acc += diff * diff;
+              }
+            }
+            d = acc;
+          }
+          // the row's list: lane 0 works on a register copy
+          float bd[KCAP];
+          int bi[KCAP];
+#pragma unroll
+          for (int t = 0; t < KCAP; ++t) {
+            bd[t] = park_d[found * KCAP + t];
+            bi[t] = park_i[found * KCAP + t];
+          }
+          unsigned better = __ballot_sync(0xffffffffu, d < bd[KCAP - 1]);
+          const bool changed = better != 0u;
+          while (better) {
+            const int b = __ffs(better) - 1;
+            const float dv = __shfl_sync(0xffffffffu, d, b);
+            const int jv = __shfl_sync(0xffffffffu, jcol, b);
+            topk_insert<KCAP>(bd, bi, dv, jv);  // every lane keeps the same copy: no broadcast of the new k-th needed
+            better &= __ballot_sync(0xffffffffu, d < bd[KCAP - 1]) & ~((2u << b) - 1u);
+          }
+          if (changed && lane == 0) {
+#pragma unroll
+            for (int t = 0; t < KCAP; ++t) {
+              park_d[found * KCAP + t] = bd[t];
+              park_i[found * KCAP + t] = bi[t];
+            }
+            const float nl = s_nalow[rL];
+            // acc <= exact k-th - (1 - ES)||a'||^2 (+ rounding pad)
+            *(volatile float*)&s_thr[found] = (bd[KCAP - 1] - nl) + 1e-6f * (1.0f + fabsf(bd[KCAP - 1]) + nl);
+          }
+          evals += (unsigned)cnt;
+          ++flushes;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();
+          *(volatile uint32_t*)&s_head[found] = head + (uint32_t)cnt;  // frees the ring entries
+          __threadfence_block();
+          *(volatile uint32_t*)&s_busy[found] = 0u;
+        }
+        __syncwarp();
+      }
+      // all evaluators done: merge the two column halves of every row and write the result
+      asm volatile("bar.sync 2, %0;" ::"n"(EVAL_WARPS * 32) : "memory");
+      for (int lr = (int)threadIdx.x - (2 + EPI_WARPS) * 32; lr < TM; lr += EVAL_WARPS * 32) {
+        const int row = m0 + lr;
+        if (row >= job.na) continue;
+        const int k = job.k;
+        const float* da_ = park_d + (lr * 2) * KCAP;
+        const int* ja_ = park_i + (lr * 2) * KCAP;
+        const float* db_ = park_d + (lr * 2 + 1) * KCAP;
+        const int* jb_ = park_i + (lr * 2 + 1) * KCAP;
+        int ia = 0, ib = 0;
+        for (int t = 0; t < k; ++t) {
+          const float da = ia < KCAP ? da_[ia] : INF, db = ib < KCAP ? db_[ib] : INF;
+          const int ja = ia < KCAP ? ja_[ia] : -1, jb = ib < KCAP ? jb_[ib] : -1;
+          const bool take_b = jb >= 0 && (ja < 0 || db < da || (db == da && jb < ja));
+          const float dsel = take_b ? db : da;
+          const int jsel = take_b ? jb : ja;
+          if (take_b) ++ib; else ++ia;
+          job.idx[(size_t)row * k + t] = jsel;
+          job.dist[(size_t)row * k + t] = jsel >= 0 ? dsel : 0.f;
+        }
+      }
+      if (stats) {
+        const unsigned fl = __reduce_add_sync(0xffffffffu, lane == 0 ? flushes : 0u);
+        const unsigned evs = __reduce_add_sync(0xffffffffu, lane == 0 ? evals : 0u);
+        if (lane == 0) {
+          if (ev == 0) atomicAdd(&stats[0], (unsigned long long)min(TM, job.na - m0));
+          atomicAdd(&stats[1], (unsigned long long)fl);
+          atomicAdd(&stats[2], (unsigned long long)evs);
+        }
       }
     }
   }

@@ -9,7 +9,10 @@ mm = mm3d_pkg.load(); synth = mm3d_pkg.load_synth()
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 t0 = time.time()
-maps, _ = synth.make_maps(**synth.CONFIGS[name])
+cfg = dict(synth.CONFIGS[name])
+if os.environ.get("MM3D_NMAPS"):  # the same map size with fewer maps (short ncu captures)
+    cfg["n_maps"] = int(os.environ["MM3D_NMAPS"])
+maps, _ = synth.make_maps(**cfg)
 print(f"generated {len(maps)} maps x {len(maps[0])} points in {time.time() - t0:.1f} s", flush=True)
 ctx = mm.Context(0)
 p = mm.default_params(descriptor_type="FPFH")
