@@ -27,30 +27,27 @@ namespace mm3d {
 
 namespace {
 
-constexpr int TM = 128, TN = 128, TK = 32;  // A rows, B rows, floats per k-block (one 128-byte swizzle row = 16 dimensions, hi | lo)
-constexpr int KB_BYTES = TM * TK * 4;       // one k-block of one operand: 16 KB
+constexpr int TM = 128, TN = 128, TK = 32;  // rows of one MMA operand tile, B rows, floats per k-block (one 128-byte swizzle row = 16 dimensions, hi | lo)
+constexpr int A_TILES = 2;                  // A tiles per CTA: 256 query rows share every B tile that comes in from L2
+constexpr int CTA_ROWS = A_TILES * TM;
+constexpr int KB_BYTES = TM * TK * 4;       // one k-block of one operand tile: 16 KB
 constexpr int A_RES_MAX_KB = 4;             // A stays resident in shared memory when it has at most this many k-blocks (D <= 61)
-constexpr int LIST_CAP = 64;                // pending candidates per (query row, column half), 16-bit column indices (nb <= 65535)
-constexpr int LIST_STRIDE = LIST_CAP + 2;   // 33 words per list: appends by 32 rows (2-way) and reads of one row's 32 entries (none) stay cheap
 constexpr int KMAXTC = 16;
-constexpr int ACC_BUFS = 4;                 // TMEM accumulator buffers (4 x 128 columns = all 512): the epilogue warps may lag the
-                                            // MMA by three tiles, so one warp's burst of exact evaluations no longer stalls the rest
-constexpr int EPI_WARPS = 8;                // two per scheduler: warps w and w + 4 share a TMEM lane quarter and split every tile's columns
-constexpr int EVAL_WARPS = 6;                // candidate pass only: warps that evaluate pending candidates exactly, any row of the CTA
-constexpr int TC_THREADS = 64 + (EPI_WARPS + EVAL_WARPS) * 32;  // warp 0: TMA producer, 1: MMA issuer + TMEM owner, 2-9: epilogue, 10-15: evaluators
-constexpr int N_SLOTS = TM * 2;              // one pending list per (query row, column half)
-constexpr int LIST_BYTES = TM * 2 * LIST_STRIDE * 2;
-constexpr int PARK_BYTES = N_SLOTS * KMAXTC * 8;  // per slot: the k best (distance, index) so far (candidate pass) / parked bounds (threshold pass)
-constexpr int SLOT_STATE_BYTES = N_SLOTS * 16 + TM * 4 + 64;  // tail, head, exact bound, busy flag per slot; (1 - ES)||a'||^2 per row; counters
-constexpr int APAD = 36;                    // floats per row of the shared-memory copy of the original query rows (D = 33 path)
-constexpr int AORIG_BYTES = TM * APAD * 4;
-// shared memory: [A resident (3 k-blocks for D = 33, else 4)] [B (or A + B) stages] [pending lists] [parking] [query rows] [barriers]
+constexpr int ACC_BUFS = 2;                 // TMEM accumulator buffers of A_TILES x 128 columns (2 x 256 = all 512 columns)
+constexpr int EPI_WARPS = 8;                // two per scheduler: warps w and w + 4 share a TMEM lane quarter, one A tile each
+constexpr int TC_THREADS = 64 + EPI_WARPS * 32;  // warp 0: TMA producer, 1: MMA issuer + TMEM owner, 2-9: epilogue
+constexpr int APAD = 36;                    // floats per row of the padded copy of the original descriptors (D = 33 path)
+constexpr int EV_WARPS = 24;                // evaluation kernel: warps per block (one block per SM), one query row at a time each
+constexpr int EV_LIST = 1024 + 32;          // evaluation kernel: candidates of 32 mask words + the leftovers of the previous group
+constexpr int EV_WORDS = 288;               // evaluation kernel: mask words of a row fetched at once (9 per lane)
+constexpr int EV_BLOCKS_X = 16;             // evaluation kernel: blocks per job, each a contiguous range of query rows
+__host__ __device__ constexpr size_t ev_smem(int q) { return (size_t)EV_WARPS * (EV_LIST * 2 + EV_WORDS * 4 + (size_t)32 * q * 16); }
+// shared memory: [A resident: A_TILES x (3 k-blocks for D = 33, else 4)] [stages: B (+ A_TILES x A when A is streamed)] [barriers]
 __host__ __device__ constexpr int tc_a_kb(int dreg, bool a_res) { return a_res ? (dreg > 0 ? 3 : A_RES_MAX_KB) : 0; }
-__host__ __device__ constexpr int tc_stages(int dreg, bool a_res) { return a_res ? (dreg > 0 ? 5 : 4) : 3; }
+__host__ __device__ constexpr int tc_stages(int dreg, bool a_res) { return a_res ? (dreg > 0 ? 6 : 5) : 3; }
 __host__ __device__ constexpr size_t tc_smem(int dreg, bool a_res)
 {
-  return (size_t)tc_a_kb(dreg, a_res) * KB_BYTES + (size_t)tc_stages(dreg, a_res) * (a_res ? 1 : 2) * KB_BYTES + LIST_BYTES + PARK_BYTES +
-         AORIG_BYTES + SLOT_STATE_BYTES + 1024 + 256;
+  return (size_t)A_TILES * tc_a_kb(dreg, a_res) * KB_BYTES + (size_t)tc_stages(dreg, a_res) * (a_res ? 1 : 1 + A_TILES) * KB_BYTES + 1024 + 256;
 }
 
 struct TcJob {
@@ -61,12 +58,13 @@ struct TcJob {
   const float* origB;
   const float4* padA;  // rows padded to a multiple of 4 floats (D = 33 only), else null
   const float4* padB;
-  const float* cmaxB;  // max ||b - mean||^2 over every 32 rows of B
   int k;
   int* idx;     // na x k
   float* dist;  // na x k
   float* audit; // optional na x nb: the raw accumulator (tests: error-bound audit)
-  float* thr;   // na: per row, upper bound (accumulator space) of the k-th nearest distance — written by pass 0, read by pass 1
+  int* pick;    // na x KCAP: per row k distinct columns with small filter values — written by pass 0, read by knn_thr_kernel
+  float* thr;   // na: per row, upper bound (accumulator space) of the k-th nearest distance — written by knn_thr_kernel, read by pass 1
+  uint32_t* masks;  // candidate bits of pass 1: [row][32-column chunk], 4 chunks per B tile
 };
 
 // ---- PTX wrappers ------------------------------------------------------------
@@ -166,9 +164,10 @@ __device__ __forceinline__ float fmin3(float a, float b, float c)
 //   v(i, j) <= d(i, j) <= v(i, j) + 2 ES (||a'_i||^2 + ||b'_j||^2)      d = the sequential FP32 distance of the exact scan
 // The true deviation of the dot product has three parts: the dropped lo.lo products and the TF32 truncation of the lo parts
 // (|x_lo| <= 2^-11 |x|, truncated to 11 bits: <= (2^-22 + 2 * 2^-21) |a_k||b_k| per dimension, i.e. <= 1.2e-6 ||a'|| ||b'||), the
-// FP32 accumulation inside the tensor core (18 chained MMAs of 8 products; each partial sum is bounded by ||b'||^2 + 2 ||a'|| ||b'||),
+// FP32 accumulation inside the tensor core (15-18 chained MMAs of 8 products; each partial sum is bounded by ||b'||^2 + 2 ||a'|| ||b'||),
 // and the FP32 rounding of the norms and of d itself (<= 35 * 2^-24 relative).  With 2 ||a'|| ||b'|| <= ||a'||^2 + ||b'||^2 the sum
-// of the three stays below EG (||a'||^2 + ||b'||^2); ES = EG + margin, so v is a lower bound and v + 2 ES (...) an upper bound.
+// of the three stays below EG (||a'||^2 + ||b'||^2); ES = EG + margin, so v is a lower bound of d.  Only the LOWER bound is used
+// by the filter: the k-th nearest distance is bounded from above by EXACT distances (below).
 constexpr float TC_ERR_STORE = 3.1e-5f;  // ES
 
 // Insertion of (d, j) into a list sorted by (distance, arrival): candidates arrive in ascending column order, so a new
@@ -194,50 +193,81 @@ __device__ __forceinline__ void topk_insert(float (&bd)[KCAP], int (&bi)[KCAP], 
   }
 }
 
-// KCAP = capacity of the register top lists (>= k; the first k are written out); DREG = descriptor length when the query
-// rows sit in shared memory and rows are read as float4 from the padded copies, 0 = scalar reads from global memory;
-// A_RES = the A tile stays in shared memory for the whole CTA (kblocks <= A_RES_MAX_KB); AUDIT = also dump the accumulators.
-// PASS 0 = threshold pass: the same GEMM with a minimal epilogue that only derives, per row, an upper bound of the k-th nearest
-// distance (job.thr); PASS 1 = candidate pass: columns whose lower bound is within that bound are evaluated exactly.
-// Two passes instead of one running threshold: a streaming top-k meets ~k ln(n / k) record breakers per row that all need
-// an exact evaluation and a list insertion (measured: 2/3 of the single-pass epilogue's instructions); with the bound known
-// up front only the columns inside the error margin of the k-th distance are ever touched, and the tensor pipe — 5 % busy
-// in the single-pass kernel — pays for the second GEMM.
+// The exact sequential FP32 distance of the brute-force scan (knn_small_kernel): acc += (a_t - b_t)^2 for t = 0 .. D-1, no
+// contraction.  DREG = descriptor length when rows are read as float4 from the padded copies, 0 = scalar reads.
+template <int DREG>
+__device__ __forceinline__ float exact_dist(const TcJob& job, int D, int row, int col)
+{
+  float acc = 0.f;
+  if constexpr (DREG > 0) {
+    constexpr int Q = (DREG + 3) / 4;
+    const float4* bp = job.padB + (size_t)col * Q;
+    const float4* ap = job.padA + (size_t)row * Q;
+    float a_[Q * 4], b_[Q * 4];
+#pragma unroll
+    for (int t = 0; t < Q; ++t) {
+      const float4 v = __ldg(&bp[t]);
+      b_[4 * t] = v.x; b_[4 * t + 1] = v.y; b_[4 * t + 2] = v.z; b_[4 * t + 3] = v.w;
+      const float4 w = __ldg(&ap[t]);
+      a_[4 * t] = w.x; a_[4 * t + 1] = w.y; a_[4 * t + 2] = w.z; a_[4 * t + 3] = w.w;
+    }
+#pragma unroll
+    for (int t = 0; t < DREG; ++t) {
+      const float diff = a_[t] - b_[t];
+      acc += diff * diff;
+    }
+  } else {
+    const float* a = job.origA + (size_t)row * D;
+    const float* b = job.origB + (size_t)col * D;
+    for (int t = 0; t < D; ++t) {
+      const float diff = __ldg(&a[t]) - __ldg(&b[t]);
+      acc += diff * diff;
+    }
+  }
+  return acc;
+}
+
+// KCAP = capacity of the top lists (>= k); DREG = descriptor length when rows are read as float4 from the padded copies,
+// 0 = scalar reads; A_RES = the A tiles stay in shared memory for the whole CTA (kblocks <= A_RES_MAX_KB); AUDIT = also dump
+// the accumulators (tests).  A CTA owns 256 query rows — two 128-row A tiles, so every B tile that comes in from L2 feeds
+// two MMAs (with 128 rows per CTA both passes were bound by the L2 -> shared-memory stream of B: 5.5-6.7 TB/s, tensor pipe
+// 41-61 % busy, ncu round 2) — and the same GEMM runs twice with two minimal epilogues, one query row per thread:
+//   PASS 0 (picks): per 32-column chunk the smallest accumulator, its column carried in the five low mantissa bits (an
+//     error of <= 32 ulp on a value that is only used to PICK columns); per row the k chunks with the smallest minima.
+//     They are k distinct columns, so the largest of their EXACT distances (knn_thr_kernel) bounds the row's k-th nearest
+//     distance from above, with no error term at all: thr = that - (1 - ES)||a'||^2.
+//   PASS 1 (candidates): a column can be among the k nearest only if its lower bound acc <= thr.  One bit per (row,
+//     column) goes to global memory (zeroed beforehand, only non-zero words are stored); knn_eval_kernel turns the bits
+//     into the exact result.
+// Why not evaluate inside the epilogue (round 2's first versions): candidates are very unevenly spread over the rows
+// (clustered descriptors: a thousand columns within the margin of some rows, five for most), and one CTA per SM with
+// 10-16 warps cannot hide the latency of the exact evaluations — that pass ran at 17 % tensor-pipe utilisation.
 template <int KCAP, int DREG, bool A_RES, bool AUDIT, int PASS>
-__global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __restrict__ jobs, const CUtensorMap* __restrict__ mapsA,
-                                                              const CUtensorMap* __restrict__ mapsB, int kblocks, int D,
-                                                              unsigned long long* __restrict__ stats)
+__global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __restrict__ jobs, int job0, const CUtensorMap* __restrict__ mapsA,
+                                                              const CUtensorMap* __restrict__ mapsB, int kblocks, int last_kb_half)
 {
   constexpr int STAGES = tc_stages(DREG, A_RES);
-  constexpr int STAGE_BYTES = A_RES ? KB_BYTES : 2 * KB_BYTES;
-  constexpr int A_RES_BYTES = tc_a_kb(DREG, A_RES) * KB_BYTES;
+  constexpr int STAGE_BYTES = (A_RES ? 1 : 1 + A_TILES) * KB_BYTES;
+  constexpr int A_RES_BYTES = A_TILES * tc_a_kb(DREG, A_RES) * KB_BYTES;
+  constexpr int ACC_COLS = A_TILES * TN;  // TMEM columns of one accumulator buffer
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment by OFFSET, so that every pointer below stays a shared-memory pointer for the compiler (rounding the
-  // address through uintptr_t turned all list / query-row accesses into generic LD.E / ST.E)
-  uint8_t* a_res = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // 1024-byte alignment by OFFSET, so that every pointer below stays a shared-memory pointer for the compiler
+  uint8_t* a_res = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // [A tile][k-block]
   uint8_t* tiles = a_res + A_RES_BYTES;
-  unsigned short* list = (unsigned short*)(tiles + (size_t)STAGES * STAGE_BYTES);  // [TM][2][LIST_STRIDE]
-  float* park_d = (float*)(list + TM * 2 * LIST_STRIDE);                           // [N_SLOTS][KCAP] distances, then indices
-  int* park_i = (int*)(park_d + N_SLOTS * KMAXTC);
-  float* a_orig = (float*)(park_i + N_SLOTS * KMAXTC);                             // [TM][APAD] (D = 33 path)
-  uint32_t* s_tail = (uint32_t*)(a_orig + TM * APAD);                              // [N_SLOTS] entries published by the producer
-  uint32_t* s_head = s_tail + N_SLOTS;                                             // [N_SLOTS] entries consumed by the evaluators
-  float* s_thr = (float*)(s_head + N_SLOTS);                                       // [N_SLOTS] exact k-th distance so far, accumulator space
-  uint32_t* s_busy = (uint32_t*)(s_thr + N_SLOTS);                                 // [N_SLOTS] an evaluator warp owns the slot
-  float* s_nalow = (float*)(s_busy + N_SLOTS);                                     // [TM]
-  uint32_t* s_done = (uint32_t*)(s_nalow + TM);                                    // producers that have finished
-  uint64_t* full_bar = (uint64_t*)(s_done + 16);
+  uint64_t* full_bar = (uint64_t*)(tiles + (size_t)STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + ACC_BUFS;
   uint64_t* a_full = tmem_empty + ACC_BUFS;
   uint32_t* tmem_slot = (uint32_t*)(a_full + 1);
 
-  const TcJob job = jobs[blockIdx.y];
-  const int m0 = blockIdx.x * TM;
-  if (m0 >= job.na) return;  // block-uniform
+  const TcJob& job = jobs[job0 + blockIdx.y];
+  const int na = job.na, nb = job.nb;
+  const int m0 = blockIdx.x * CTA_ROWS;
+  if (m0 >= na) return;  // block-uniform
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = (job.nb + TN - 1) / TN;
+  const int n_tiles = (nb + TN - 1) / TN;
+  const int a_map = job.a_map, b_map = job.b_map;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -252,7 +282,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(ACC_BUFS * TN)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(ACC_BUFS * ACC_COLS)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -261,11 +291,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer =====  (rows past the end of a set are zero-filled by the TMA unit)
     if (lane == 0) {
       if (A_RES) {
-        mbar_arrive_expect_tx(a_full, (uint32_t)kblocks * KB_BYTES);
-        for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(&mapsA[job.a_map], a_full, a_res + (size_t)kb * KB_BYTES, kb * TK, m0);
+        mbar_arrive_expect_tx(a_full, (uint32_t)(A_TILES * kblocks) * KB_BYTES);
+        for (int at = 0; at < A_TILES; ++at)
+          for (int kb = 0; kb < kblocks; ++kb)
+            tma_load_2d(&mapsA[a_map], a_full, a_res + (size_t)(at * tc_a_kb(DREG, A_RES) + kb) * KB_BYTES, kb * TK, m0 + at * TM);
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -274,8 +306,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
           uint8_t* st = tiles + (size_t)stage * STAGE_BYTES;
-          tma_load_2d(&mapsB[job.b_map], &full_bar[stage], st, kb * TK, nt * TN);
-          if (!A_RES) tma_load_2d(&mapsA[job.a_map], &full_bar[stage], st + KB_BYTES, kb * TK, m0);
+          tma_load_2d(&mapsB[b_map], &full_bar[stage], st, kb * TK, nt * TN);
+          if (!A_RES)
+            for (int at = 0; at < A_TILES; ++at) tma_load_2d(&mapsA[a_map], &full_bar[stage], st + (size_t)(1 + at) * KB_BYTES, kb * TK, m0 + at * TM);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
     }
@@ -295,190 +328,121 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
         const uint32_t acc_phase = (uint32_t)(nt / ACC_BUFS) & 1u;
         mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TN);
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           uint8_t* st = tiles + (size_t)stage * STAGE_BYTES;
           const uint64_t db = umma_desc_k_sw128(st);
-          const uint64_t da = umma_desc_k_sw128(A_RES ? a_res + (size_t)kb * KB_BYTES : st + KB_BYTES);
           // a k-block row = [hi(8) hi(8) | lo(8) lo(8)] of 16 dimensions; 8 TF32 = 32 bytes = +2 in the (address >> 4) field.
-          // hi.hi + lo.hi + hi.lo per 8-dimension slice: the dot product to ~2^-20 relative.
-          constexpr int PA[6] = {0, 1, 2, 3, 0, 1};
-          constexpr int PB[6] = {0, 1, 0, 1, 2, 3};
+          // hi.hi + lo.hi + hi.lo per 8-dimension slice: the dot product to ~2^-20 relative.  When the last k-block holds
+          // at most 8 dimensions (D = 33: 33 + 3 norm dimensions = 36 = 2 k-blocks + 4) its second slice is all zeros and
+          // is skipped: 15 MMAs per A tile and B tile instead of 18.
+          constexpr int PA[6] = {0, 2, 0, 1, 3, 1};
+          constexpr int PB[6] = {0, 0, 2, 1, 1, 3};
+          const int np = (last_kb_half && kb == kblocks - 1) ? 3 : 6;  // the first three products are the first slice's
 #pragma unroll
-          for (int p = 0; p < 6; ++p)
-            tc_mma_tf32(tmem_d, da + (uint64_t)(PA[p] * 2), db + (uint64_t)(PB[p] * 2), idesc, (kb | p) != 0 ? 1u : 0u);
+          for (int at = 0; at < A_TILES; ++at) {
+            const uint64_t da = umma_desc_k_sw128(A_RES ? a_res + (size_t)(at * tc_a_kb(DREG, A_RES) + kb) * KB_BYTES : st + (size_t)(1 + at) * KB_BYTES);
+            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * ACC_COLS + at * TN);
+#pragma unroll
+            for (int p = 0; p < 6; ++p)
+              if (p < np) tc_mma_tf32(tmem_d, da + (uint64_t)(PA[p] * 2), db + (uint64_t)(PB[p] * 2), idesc, (kb | p) != 0 ? 1u : 0u);
+          }
           tc_commit(&empty_bar[stage]);  // the smem slot is free once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tmem_full[buf]);  // accumulator ready for the epilogue
+        tc_commit(&tmem_full[buf]);  // both accumulators ready for the epilogue
       }
     }
-  } else if (warp < 2 + EPI_WARPS) {
-    // ===== epilogue: one query row per thread, two warps per TMEM lane quarter (each takes 64 of a tile's 128 columns) =====
-    // Per (row, column half):
-    //   * t5[]: the KCAP smallest UPPER bounds seen so far, fed with one value per 32-column chunk — the chunk's smallest
-    //     accumulator plus the error term of the chunk's largest norm.  Chunk minima belong to distinct columns, so their
-    //     KCAP-th smallest upper bound bounds the row's k-th nearest distance; thr = min(that, the exact k-th distance so far);
-    //   * a column can be among the exact nearest only if its lower bound acc <= thr: such columns are appended (index
-    //     only) to the row's pending list in shared memory.  The common case — no column of the chunk passes — costs the
-    //     min tree (16 three-input minima) and ten min/max for the bound, no branch per column;
-    //   * when a list holds 32 candidates the WARP evaluates them together: lane c computes the exact sequential FP32
-    //     distance of candidate c (query row broadcast from shared memory, B row as float4 loads), the few that beat the
-    //     row's current k-th distance are inserted by the owning lane in ascending column order with strict <, which is
-    //     the brute-force scan's (distance, index) order bit for bit.  Tie-heavy rows (clustered descriptors: hundreds of
-    //     columns inside the error margin of the k-th distance) therefore cost one full-warp evaluation per 32 ties
-    //     instead of diverged per-lane work or a brute-force fallback.
+  } else {
+    // ===== epilogue: one query row per thread; warps w and w + 4 share a TMEM lane quarter and take one A tile each =====
     const int ew = warp - 2;
-    const int q = warp & 3;        // TMEM lane quarter this warp may access
-    const int half = ew >> 2;      // which 64 columns of every tile
-    const int lrow = q * 32 + lane;
-    const int row = m0 + lrow;
-    const bool live = row < job.na;
-    const float na = live ? job.normA[row] : 0.f;
-    const float na_low = (1.0f - TC_ERR_STORE) * na;  // acc + na_low <= exact distance
+    const int q = warp & 3;   // TMEM lane quarter this warp may access
+    const int at = ew >> 2;   // which A tile
+    const int row = m0 + at * TM + q * 32 + lane;
+    const bool live = row < na;
     const float INF = __int_as_float(0x7f800000);
-    if constexpr (PASS == 0) {
-      // ---- threshold pass: K-th smallest upper bound over one value per 32-column chunk (chunk minima are distinct columns)
-      float t5[KCAP];
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(at * TN);
+    // PASS 0 state: the KCAP smallest chunk minima (column in the low 5 bits) and their chunk ids
+    float t5[KCAP];
+    int c5[KCAP];
 #pragma unroll
-      for (int i = 0; i < KCAP; ++i) t5[i] = INF;
-      const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
-      const int n_chunks = n_tiles * 2;
-      uint32_t r[32], rn[32];
-      mbar_wait(&tmem_full[0], 0);
-      tc_fence_after();
-      tmem_ld_32x32_issue(tmem_row + (uint32_t)(half * 64), r);
-      tmem_ld_wait(r);
-      for (int ch = 0; ch < n_chunks; ++ch) {
-        const int nt = ch >> 1, c0 = half * 64 + (ch & 1) * 32;
-        const bool tile_end = (ch & 1) == 1;
-        if (ch + 1 < n_chunks) {
-          const int nt1 = (ch + 1) >> 1, buf1 = nt1 % ACC_BUFS;
-          if (tile_end) {
-            mbar_wait(&tmem_full[buf1], (uint32_t)(nt1 / ACC_BUFS) & 1u);
-            tc_fence_after();
-          }
-          tmem_ld_32x32_issue(tmem_row + (uint32_t)(buf1 * TN + half * 64 + ((ch + 1) & 1) * 32), rn);
-        }
-        const int jbase = nt * TN + c0;
-        const int left = job.nb - jbase;  // columns past nb are zero rows of the B form: keep them out of the minimum
-        if (left < 32) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (c >= left) r[c] = 0x7f800000u;
-        }
+    for (int i = 0; i < KCAP; ++i) {
+      t5[i] = INF;
+      c5[i] = -1;
+    }
+    uint32_t keep = 0xffffffe0u;
+    asm volatile("" : "+r"(keep));  // a register, so that (r & keep) | column is ONE LOP3 (two immediates would be two)
+    // PASS 1 state
+    float thr = -INF;
+    uint32_t* mrow = nullptr;
+    float* audit_row = nullptr;
+    if constexpr (PASS == 1) {
+      thr = live ? job.thr[row] : -INF;
+      mrow = job.masks + (size_t)row * (size_t)(n_tiles * 4);
+      if (AUDIT) audit_row = job.audit + (size_t)row * nb;
+    }
+    // one chunk: r = the thread's 32 accumulators of columns chunk_id * 32 .. (destroyed); returns the candidate bits (pass 1)
+    auto process = [&](uint32_t (&r)[32], int chunk_id) -> uint32_t {
+      const int jbase = chunk_id * 32;
+      const int left = nb - jbase;  // columns past nb are zero rows of the B form: keep them out
+      uint32_t msk = 0;
+      if constexpr (PASS == 0) {
         if (left > 0) {
-          float m = fmin3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
 #pragma unroll
-          for (int c = 3; c < 31; c += 2) m = fmin3(m, __uint_as_float(r[c]), __uint_as_float(r[c + 1]));
-          m = fminf(m, __uint_as_float(r[31]));
-          const float cmax = __ldg(&job.cmaxB[jbase >> 5]);
-          float ub = m + ((2.0f * TC_ERR_STORE) * (na + cmax) + 1e-6f * (1.0f + fabsf(m)));
+          for (int c = 0; c < 32; ++c) r[c] = (r[c] & keep) | (uint32_t)c;
+          if (left < 32) {
 #pragma unroll
-          for (int t = 0; t < KCAP; ++t) {
-            const float lo_ = fminf(t5[t], ub);
-            ub = fmaxf(t5[t], ub);
-            t5[t] = lo_;
+            for (int c = 0; c < 32; ++c)
+              if (c >= left) r[c] = 0x7f800000u;
+          }
+          // minimum as a tree (depth 4 of three-input minima): the chunk is a dependent chain otherwise
+          float l1[11];
+#pragma unroll
+          for (int c = 0; c < 10; ++c) l1[c] = fmin3(__uint_as_float(r[3 * c]), __uint_as_float(r[3 * c + 1]), __uint_as_float(r[3 * c + 2]));
+          l1[10] = fminf(__uint_as_float(r[30]), __uint_as_float(r[31]));
+          const float l2a = fmin3(l1[0], l1[1], l1[2]), l2b = fmin3(l1[3], l1[4], l1[5]), l2c = fmin3(l1[6], l1[7], l1[8]);
+          const float l2d = fminf(l1[9], l1[10]);
+          const float m = fminf(fmin3(l2a, l2b, l2c), l2d);
+          if (m < t5[KCAP - 1]) {
+            float cd = m;
+            int ci = chunk_id;
+#pragma unroll
+            for (int u = 0; u < KCAP; ++u) {
+              if (cd < t5[u]) {
+                const float td = t5[u];
+                const int ti = c5[u];
+                t5[u] = cd;
+                c5[u] = ci;
+                cd = td;
+                ci = ti;
+              }
+            }
           }
         }
-        tmem_ld_wait(rn);
-        if (tile_end) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[nt % ACC_BUFS]);
-        }
-#pragma unroll
-        for (int c = 0; c < 32; ++c) r[c] = rn[c];
-      }
-      // K-th smallest of the two halves' sorted lists
-      if (half == 1) {
-#pragma unroll
-        for (int t = 0; t < KCAP; ++t) park_d[lrow * KCAP + t] = t5[t];
-      }
-      named_bar_sync<EPI_WARPS * 32>();
-      if (half == 0 && live) {
-        int ia = 0, ib = 0;
-        float kth = INF;
-        for (int t = 0; t < KCAP; ++t) {
-          float da = INF;
-#pragma unroll
-          for (int u = 0; u < KCAP; ++u)
-            if (u == ia) da = t5[u];
-          const float db = ib < KCAP ? park_d[lrow * KCAP + ib] : INF;
-          if (db < da) { kth = db; ++ib; } else { kth = da; ++ia; }
-        }
-        job.thr[row] = kth;
-      }
-    } else {
-      // ---- candidate pass, producer side: columns whose accumulator is within the row's bound go — index only — into the
-      // row's pending ring in shared memory; the evaluator warps (below) pick full rings up.  The producer never evaluates
-      // anything itself, so its work per chunk is uniform and the eight epilogue warps stay in step with the MMA.
-      const int slot = lrow * 2 + half;
-      unsigned short* my_list = list + slot * LIST_STRIDE;
-      if (half == 0) s_nalow[lrow] = na_low;
-      s_tail[slot] = 0;
-      s_head[slot] = 0;
-      s_busy[slot] = 0;
-      s_thr[slot] = INF;
-#pragma unroll
-      for (int t = 0; t < KCAP; ++t) {
-        park_d[slot * KCAP + t] = INF;
-        park_i[slot * KCAP + t] = -1;
-      }
-      if (ew == 0 && lane == 0) *s_done = 0;
-      if (DREG > 0) {
-        for (int e = (ew * 32 + lane); e < TM * (APAD / 4); e += EPI_WARPS * 32) {
-          const int r_ = e / (APAD / 4), t = e - r_ * (APAD / 4);
-          const float4 v = (m0 + r_ < job.na) ? job.padA[(size_t)(m0 + r_) * (APAD / 4) + t] : make_float4(0.f, 0.f, 0.f, 0.f);
-          reinterpret_cast<float4*>(a_orig)[r_ * (APAD / 4) + t] = v;
-        }
-      }
-      named_bar_sync<(EPI_WARPS + EVAL_WARPS) * 32>();  // producers + evaluators: rings, bounds and the query rows are in place
-      float thr = live ? job.thr[row] : -INF;  // acc-space filter bound from the threshold pass, only ever shrinks
-      uint32_t tail = 0;
-      const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
-      const int n_chunks = n_tiles * 2;  // this warp's chunks: two per tile
-      uint32_t r[32], rn[32];
-      mbar_wait(&tmem_full[0], 0);
-      tc_fence_after();
-      tmem_ld_32x32_issue(tmem_row + (uint32_t)(half * 64), r);
-      tmem_ld_wait(r);
-      for (int ch = 0; ch < n_chunks; ++ch) {
-        const int nt = ch >> 1, c0 = half * 64 + (ch & 1) * 32;
-        const bool tile_end = (ch & 1) == 1;
-        if (ch + 1 < n_chunks) {
-          const int nt1 = (ch + 1) >> 1, buf1 = nt1 % ACC_BUFS;
-          if (tile_end) {
-            mbar_wait(&tmem_full[buf1], (uint32_t)(nt1 / ACC_BUFS) & 1u);
-            tc_fence_after();
-          }
-          tmem_ld_32x32_issue(tmem_row + (uint32_t)(buf1 * TN + half * 64 + ((ch + 1) & 1) * 32), rn);
-        }
-        const int jbase = nt * TN + c0;
-        const int left = job.nb - jbase;  // columns past nb are zero rows of the B form: keep them out of the minimum
+      } else {
         if (AUDIT) {
           if (live) {
 #pragma unroll
             for (int c = 0; c < 32; ++c)
-              if (c < left) job.audit[(size_t)row * job.nb + jbase + c] = __uint_as_float(r[c]);
+              if (c < left) audit_row[jbase + c] = __uint_as_float(r[c]);
           }
         }
-        if (left < 32) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (c >= left) r[c] = 0x7f800000u;
-        }
         if (left > 0) {
-          thr = fminf(thr, *(volatile float*)&s_thr[slot]);  // what the evaluators have learned about this row so far
-          // smallest accumulator of the chunk: 16 three-input minima
-          float m = fmin3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
+          if (left < 32) {
 #pragma unroll
-          for (int c = 3; c < 31; c += 2) m = fmin3(m, __uint_as_float(r[c]), __uint_as_float(r[c + 1]));
-          m = fminf(m, __uint_as_float(r[31]));
+            for (int c = 0; c < 32; ++c)
+              if (c >= left) r[c] = 0x7f800000u;
+          }
+          // smallest accumulator of the chunk; the common case — nothing passes — ends here
+          float l1[11];
+#pragma unroll
+          for (int c = 0; c < 10; ++c) l1[c] = fmin3(__uint_as_float(r[3 * c]), __uint_as_float(r[3 * c + 1]), __uint_as_float(r[3 * c + 2]));
+          l1[10] = fminf(__uint_as_float(r[30]), __uint_as_float(r[31]));
+          const float l2a = fmin3(l1[0], l1[1], l1[2]), l2b = fmin3(l1[3], l1[4], l1[5]), l2c = fmin3(l1[6], l1[7], l1[8]);
+          const float l2d = fminf(l1[9], l1[10]);
+          const float m = fminf(fmin3(l2a, l2b, l2c), l2d);
           if (m <= thr) {
-            // which columns pass (one compare + one bit each), then one append per set bit
             uint32_t m0_ = 0, m1_ = 0, m2_ = 0, m3_ = 0;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -487,186 +451,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
               m2_ |= (__uint_as_float(r[16 + c]) <= thr) ? (1u << (16 + c)) : 0u;
               m3_ |= (__uint_as_float(r[24 + c]) <= thr) ? (1u << (24 + c)) : 0u;
             }
-            uint32_t msk = (m0_ | m1_) | (m2_ | m3_);
+            msk = (m0_ | m1_) | (m2_ | m3_);
             if (left < 32) msk &= (1u << left) - 1u;  // columns past nb (masked to +inf above) would still pass an infinite bound
-            // room for the whole chunk (the evaluators free 32 entries at a time; a full ring means they are behind)
-            const uint32_t need = (uint32_t)__popc(msk);
-            while (tail + need - *(volatile uint32_t*)&s_head[slot] > (uint32_t)LIST_CAP) __nanosleep(64);
-            while (msk) {
-              const int c = __ffs(msk) - 1;
-              msk &= msk - 1;
-              my_list[tail & (LIST_CAP - 1)] = (unsigned short)(jbase + c);
-              ++tail;
-            }
-            __threadfence_block();
-            *(volatile uint32_t*)&s_tail[slot] = tail;  // publish
           }
         }
-        tmem_ld_wait(rn);  // rn has landed (and, at a tile end, every read of this tile's accumulator is done)
-        if (tile_end) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[nt % ACC_BUFS]);
-        }
-#pragma unroll
-        for (int c = 0; c < 32; ++c) r[c] = rn[c];
       }
+      return msk;
+    };
+    // Four chunks (the 128 columns of this warp's accumulator) per tile, two register arrays in turn: while one chunk is being
+    // processed the TMEM load of the next is in flight, and nothing is copied between the arrays.
+    uint32_t r0[32], r1[32];
+    mbar_wait(&tmem_full[0], 0);
+    tc_fence_after();
+    tmem_ld_32x32_issue(tmem_row, r0);
+    tmem_ld_wait(r0);
+    for (int nt = 0; nt < n_tiles; ++nt) {
+      const int buf = nt % ACC_BUFS;
+      const uint32_t trow = tmem_row + (uint32_t)(buf * ACC_COLS);
+      tmem_ld_32x32_issue(trow + 32, r1);
+      const uint32_t k0 = process(r0, nt * 4);
+      tmem_ld_wait(r1);
+      tmem_ld_32x32_issue(trow + 64, r0);
+      const uint32_t k1 = process(r1, nt * 4 + 1);
+      tmem_ld_wait(r0);
+      tmem_ld_32x32_issue(trow + 96, r1);
+      const uint32_t k2 = process(r0, nt * 4 + 2);
+      tmem_ld_wait(r1);  // every read of this tile's accumulator is done
+      tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        __threadfence_block();
-        atomicAdd(s_done, 1u);
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (nt + 1 < n_tiles) {
+        const int buf1 = (nt + 1) % ACC_BUFS;
+        mbar_wait(&tmem_full[buf1], (uint32_t)((nt + 1) / ACC_BUFS) & 1u);
+        tc_fence_after();
+        tmem_ld_32x32_issue(tmem_row + (uint32_t)(buf1 * ACC_COLS), r0);
       }
+      const uint32_t k3 = process(r1, nt * 4 + 3);
+      if constexpr (PASS == 1) {
+        if ((k0 | k1) | (k2 | k3)) *reinterpret_cast<uint4*>(mrow + nt * 4) = make_uint4(k0, k1, k2, k3);  // the buffer is zeroed beforehand
+      }
+      if (nt + 1 < n_tiles) tmem_ld_wait(r0);
     }
-  } else {
-    // ===== evaluator warps (candidate pass only) =====
-    // Any evaluator warp serves any row of the CTA: it claims a pending ring that holds 32 candidates (or, once the
-    // producers are done, whatever is left), lane c computes the exact sequential FP32 distance of candidate c (query row
-    // broadcast from shared memory, B row as float4 loads), and the few that beat the row's current k-th distance are
-    // inserted — in ring order = ascending column order, strict < — into the row's list, which lives in shared memory.  The
-    // exact k-th distance goes back to the producer as a tighter bound.  Decoupling evaluation from the epilogue warps
-    // matters because the candidates are very unevenly spread over the rows (clustered descriptors): inline evaluation
-    // made every tile wait for the epilogue warp with the most ties.
-    if constexpr (PASS == 1) {
-      const int ev = warp - 2 - EPI_WARPS;
-      const float INF = __int_as_float(0x7f800000);
-      unsigned evals = 0, flushes = 0;
-      named_bar_sync<(EPI_WARPS + EVAL_WARPS) * 32>();
-      int scan0 = ev * (N_SLOTS / EVAL_WARPS);  // evaluators start their sweeps at different slots
-      for (;;) {
-        const bool draining = *(volatile uint32_t*)s_done == (uint32_t)EPI_WARPS;
-        // sweep: every lane looks at 8 slots
-        int found = -1;
-        for (int pass_ = 0; pass_ < N_SLOTS / 32 && found < 0; ++pass_) {
-          const int s_ = (scan0 + pass_ * 32 + lane) & (N_SLOTS - 1);
-          const uint32_t cnt = *(volatile uint32_t*)&s_tail[s_] - *(volatile uint32_t*)&s_head[s_];
-          const bool want = (cnt >= 32u || (draining && cnt > 0u)) && *(volatile uint32_t*)&s_busy[s_] == 0u;
-          const unsigned vote = __ballot_sync(0xffffffffu, want);
-          if (vote) found = (scan0 + pass_ * 32 + (__ffs(vote) - 1)) & (N_SLOTS - 1);
-        }
-        if (found < 0) {
-          if (draining) {
-            // nothing pending anywhere and no producer left: done (a ring another evaluator is working on is its business)
-            bool any = false;
-            for (int s_ = lane; s_ < N_SLOTS; s_ += 32)
-              if (*(volatile uint32_t*)&s_tail[s_] != *(volatile uint32_t*)&s_head[s_] && *(volatile uint32_t*)&s_busy[s_] == 0u) any = true;
-            if (!__any_sync(0xffffffffu, any)) break;
-          } else {
-            __nanosleep(200);
-          }
-          continue;
-        }
-        scan0 = found + 1;
-        int claimed = 0;
-        if (lane == 0) claimed = atomicCAS(&s_busy[found], 0u, 1u) == 0u ? 1 : 0;
-        claimed = __shfl_sync(0xffffffffu, claimed, 0);
-        if (!claimed) continue;
-        __threadfence_block();
-        const uint32_t head = *(volatile uint32_t*)&s_head[found];
-        const uint32_t cnt_all = *(volatile uint32_t*)&s_tail[found] - head;
-        const int cnt = (int)min(cnt_all, 32u);
-        if (cnt > 0) {
-          const int rL = found >> 1;
-          const unsigned short* lst = list + found * LIST_STRIDE;
-          const int jcol = lane < cnt ? (int)lst[(head + lane) & (LIST_CAP - 1)] : 0;
-          float d = INF;
-          if (lane < cnt) {
-            float acc = 0.f;
-            if (DREG > 0) {
-              constexpr int Q = DREG > 0 ? (DREG + 3) / 4 : 1;
-              const float4* bp = job.padB + (size_t)jcol * Q;
-              const float4* ap = reinterpret_cast<const float4*>(a_orig + rL * APAD);
-              float a_[Q * 4], b_[Q * 4];
+    if constexpr (PASS == 0) {
+      if (live) {
+        int* pk = job.pick + (size_t)row * KCAP;
 #pragma unroll
-              for (int t = 0; t < Q; ++t) {
-                const float4 v = __ldg(&bp[t]);
-                b_[4 * t] = v.x; b_[4 * t + 1] = v.y; b_[4 * t + 2] = v.z; b_[4 * t + 3] = v.w;
-                const float4 w = ap[t];
-                a_[4 * t] = w.x; a_[4 * t + 1] = w.y; a_[4 * t + 2] = w.z; a_[4 * t + 3] = w.w;
-              }
-#pragma unroll
-              for (int t = 0; t < DREG; ++t) {
-                const float diff = a_[t] - b_[t];
-                acc += diff * diff;
-              }
-            } else {
-              const float* a = job.origA + (size_t)(m0 + rL) * D;
-              const float* b = job.origB + (size_t)jcol * D;
-              for (int t = 0; t < D; ++t) {
-                const float diff = __ldg(&a[t]) - __ldg(&b[t]);
-                acc += diff * diff;
-              }
-            }
-            d = acc;
-          }
-          // the row's list: lane 0 works on a register copy
-          float bd[KCAP];
-          int bi[KCAP];
-#pragma unroll
-          for (int t = 0; t < KCAP; ++t) {
-            bd[t] = park_d[found * KCAP + t];
-            bi[t] = park_i[found * KCAP + t];
-          }
-          unsigned better = __ballot_sync(0xffffffffu, d < bd[KCAP - 1]);
-          const bool changed = better != 0u;
-          while (better) {
-            const int b = __ffs(better) - 1;
-            const float dv = __shfl_sync(0xffffffffu, d, b);
-            const int jv = __shfl_sync(0xffffffffu, jcol, b);
-            topk_insert<KCAP>(bd, bi, dv, jv);  // every lane keeps the same copy: no broadcast of the new k-th needed
-            better &= __ballot_sync(0xffffffffu, d < bd[KCAP - 1]) & ~((2u << b) - 1u);
-          }
-          if (changed && lane == 0) {
-#pragma unroll
-            for (int t = 0; t < KCAP; ++t) {
-              park_d[found * KCAP + t] = bd[t];
-              park_i[found * KCAP + t] = bi[t];
-            }
-            const float nl = s_nalow[rL];
-            // acc <= exact k-th - (1 - ES)||a'||^2 (+ rounding pad)
-            *(volatile float*)&s_thr[found] = (bd[KCAP - 1] - nl) + 1e-6f * (1.0f + fabsf(bd[KCAP - 1]) + nl);
-          }
-          evals += (unsigned)cnt;
-          ++flushes;
-        }
-        __syncwarp();
-        if (lane == 0) {
-          __threadfence_block();
-          *(volatile uint32_t*)&s_head[found] = head + (uint32_t)cnt;  // frees the ring entries
-          __threadfence_block();
-          *(volatile uint32_t*)&s_busy[found] = 0u;
-        }
-        __syncwarp();
-      }
-      // all evaluators done: merge the two column halves of every row and write the result
-      asm volatile("bar.sync 2, %0;" ::"n"(EVAL_WARPS * 32) : "memory");
-      for (int lr = (int)threadIdx.x - (2 + EPI_WARPS) * 32; lr < TM; lr += EVAL_WARPS * 32) {
-        const int row = m0 + lr;
-        if (row >= job.na) continue;
-        const int k = job.k;
-        const float* da_ = park_d + (lr * 2) * KCAP;
-        const int* ja_ = park_i + (lr * 2) * KCAP;
-        const float* db_ = park_d + (lr * 2 + 1) * KCAP;
-        const int* jb_ = park_i + (lr * 2 + 1) * KCAP;
-        int ia = 0, ib = 0;
-        for (int t = 0; t < k; ++t) {
-          const float da = ia < KCAP ? da_[ia] : INF, db = ib < KCAP ? db_[ib] : INF;
-          const int ja = ia < KCAP ? ja_[ia] : -1, jb = ib < KCAP ? jb_[ib] : -1;
-          const bool take_b = jb >= 0 && (ja < 0 || db < da || (db == da && jb < ja));
-          const float dsel = take_b ? db : da;
-          const int jsel = take_b ? jb : ja;
-          if (take_b) ++ib; else ++ia;
-          job.idx[(size_t)row * k + t] = jsel;
-          job.dist[(size_t)row * k + t] = jsel >= 0 ? dsel : 0.f;
-        }
-      }
-      if (stats) {
-        const unsigned fl = __reduce_add_sync(0xffffffffu, lane == 0 ? flushes : 0u);
-        const unsigned evs = __reduce_add_sync(0xffffffffu, lane == 0 ? evals : 0u);
-        if (lane == 0) {
-          if (ev == 0) atomicAdd(&stats[0], (unsigned long long)min(TM, job.na - m0));
-          atomicAdd(&stats[1], (unsigned long long)fl);
-          atomicAdd(&stats[2], (unsigned long long)evs);
-        }
+        for (int t = 0; t < KCAP; ++t) pk[t] = c5[t] >= 0 ? c5[t] * 32 + (int)(__float_as_uint(t5[t]) & 31u) : -1;
       }
     }
   }
@@ -674,7 +504,211 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_kernel(const TcJob* __re
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(ACC_BUFS * TN)) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(ACC_BUFS * ACC_COLS)) : "memory");
+  }
+}
+
+// Upper bound of every row's k-th nearest distance from the EXACT distances of the k distinct columns pass 0 picked; in
+// accumulator space: a column j is needed only if d_j <= dmax, and acc_j + (1 - ES)||a'||^2 <= d_j.
+template <int KCAP, int DREG>
+__global__ void __launch_bounds__(128) knn_thr_kernel(const TcJob* __restrict__ jobs, int job0, int D)
+{
+  const TcJob& job = jobs[job0 + blockIdx.y];
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= job.na) return;
+  const float INF = __int_as_float(0x7f800000);
+  const int k = min(job.k, KCAP);
+  const int* pk = job.pick + (size_t)row * KCAP;
+  float dmax = 0.f;
+  bool all = true;
+  for (int t = 0; t < k; ++t) {
+    const int col = pk[t];
+    if (col < 0) {  // fewer than k columns in B: everything is a candidate
+      all = false;
+      break;
+    }
+    dmax = fmaxf(dmax, exact_dist<DREG>(job, D, row, col));
+  }
+  const float na_low = (1.0f - TC_ERR_STORE) * job.normA[row];
+  job.thr[row] = all ? (dmax - na_low) + 1e-6f * (1.0f + fabsf(dmax) + na_low) : INF;  // + rounding pad of the two FP32 operations
+}
+
+// Exact evaluation of the candidates pass 1 marked.  One warp per query row at a time: the row's mask words are fetched
+// (lane = 32-column chunk), the set bits expanded — column index only, ascending — into the warp's list in shared memory,
+// and every 32 candidates are evaluated by the warp together, lane c = candidate c: the exact sequential FP32 distance on
+// the original descriptors, the few that beat the row's current k-th distance inserted in list order = ascending column
+// order with strict <, which is the brute-force scan's (distance, index) order bit for bit.  The query row stays in
+// registers; the 32 B rows of a step are fetched by the warp TOGETHER — consecutive lanes read consecutive 16-byte pieces,
+// so one load instruction touches ~4 rows = ~5 cache lines instead of 32 — and every lane picks its own row up from shared
+// memory.  A block is 24 warps = the whole SM, working on 24 CONSECUTIVE query rows at any time: consecutive keypoints have
+// similar descriptors, hence nearly the same candidate columns (clustered descriptors: a thousand columns inside the error
+// margin of the k-th distance for ~15 % of the rows, five for the median row), and all warps sweep them in ascending column
+// order — the B rows one warp pulls in from L2 are L1 hits for the others (the gather ran at the L2 sector rate before).
+template <int KCAP, int DREG>
+__global__ void __launch_bounds__(EV_WARPS * 32, 1) knn_eval_kernel(const TcJob* __restrict__ jobs, int job0, int D,
+                                                                   unsigned long long* __restrict__ stats)
+{
+  constexpr int Q = DREG > 0 ? (DREG + 3) / 4 : 1;  // float4 pieces per padded row
+  extern __shared__ float4 ev_smem_raw[];
+  float4* stage_all = ev_smem_raw;                                                  // [EV_WARPS][32 * Q]: the B rows of one step
+  uint32_t* words_all = (uint32_t*)(stage_all + (size_t)EV_WARPS * 32 * Q);         // [EV_WARPS][EV_WORDS]
+  unsigned short* list_all = (unsigned short*)(words_all + (size_t)EV_WARPS * EV_WORDS);  // [EV_WARPS][EV_LIST]
+  const TcJob& job = jobs[job0 + blockIdx.y];
+  const int na = job.na, nb = job.nb, k = job.k;
+  const uint32_t* masks = job.masks;
+  const float4* padA = job.padA;
+  const float4* padB = job.padB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_chunks = ((nb + TN - 1) / TN) * 4;
+  const float INF = __int_as_float(0x7f800000);
+  const unsigned FULL = 0xffffffffu;
+  unsigned short* lst = list_all + (size_t)warp * EV_LIST;
+  uint32_t* wbuf = words_all + (size_t)warp * EV_WORDS;
+  float4* stage = stage_all + (size_t)warp * 32 * Q;
+  // cooperative fetch geometry: piece f = i * 32 + lane of the 32 x Q pieces of a step belongs to candidate f / Q
+  int gcand[Q], gpiece[Q];
+#pragma unroll
+  for (int i = 0; i < Q; ++i) {
+    const int f = i * 32 + lane;
+    gcand[i] = f / Q;
+    gpiece[i] = f - gcand[i] * Q;
+  }
+  unsigned evals = 0, flushes = 0, rows_done = 0;
+  const int rows_per_block = (na + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int row_end = min(na, ((int)blockIdx.x + 1) * rows_per_block);
+  for (int row = (int)blockIdx.x * rows_per_block + warp; row < row_end; row += EV_WARPS) {
+    float a_[Q * 4];
+    if constexpr (DREG > 0) {
+#pragma unroll
+      for (int t = 0; t < Q; ++t) {
+        const float4 w = __ldg(&padA[(size_t)row * Q + t]);
+        a_[4 * t] = w.x; a_[4 * t + 1] = w.y; a_[4 * t + 2] = w.z; a_[4 * t + 3] = w.w;
+      }
+    }
+    float bd[KCAP];
+    int bi[KCAP];
+#pragma unroll
+    for (int t = 0; t < KCAP; ++t) {
+      bd[t] = INF;
+      bi[t] = -1;
+    }
+    // n candidates at lst[base ..]: every lane keeps the same copy of the row's list, so nothing is broadcast afterwards
+    auto step = [&](int base, int n) {
+      const int jcol = lane < n ? (int)lst[base + lane] : 0;
+      float d = INF;
+      if constexpr (DREG > 0) {
+        constexpr int H = (Q + 1) / 2;  // two rounds: fewer registers in flight
+#pragma unroll
+        for (int h0 = 0; h0 < Q; h0 += H) {
+          float4 v[H];
+#pragma unroll
+          for (int i = 0; i < H; ++i) {
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (h0 + i < Q && gcand[h0 + i] < n) v[i] = __ldg(&padB[(size_t)lst[base + gcand[h0 + i]] * Q + gpiece[h0 + i]]);
+          }
+#pragma unroll
+          for (int i = 0; i < H; ++i)
+            if (h0 + i < Q) stage[(h0 + i) * 32 + lane] = v[i];
+        }
+        __syncwarp();
+        if (lane < n) {
+          float acc = 0.f;
+#pragma unroll
+          for (int t = 0; t < Q; ++t) {
+            const float4 bv = stage[lane * Q + t];
+            const float b_[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (4 * t + u < DREG) {
+                const float diff = a_[4 * t + u] - b_[u];
+                acc += diff * diff;
+              }
+          }
+          d = acc;
+        }
+      } else {
+        if (lane < n) d = exact_dist<DREG>(job, D, row, jcol);
+      }
+      unsigned better = __ballot_sync(FULL, d < bd[KCAP - 1]);
+      while (better) {
+        const int b = __ffs(better) - 1;
+        const float dv = __shfl_sync(FULL, d, b);
+        const int jv = __shfl_sync(FULL, jcol, b);
+        topk_insert<KCAP>(bd, bi, dv, jv);
+        better &= __ballot_sync(FULL, d < bd[KCAP - 1]) & ~((2u << b) - 1u);
+      }
+      evals += (unsigned)n;
+      ++flushes;
+      __syncwarp();  // the stage is free again
+    };
+    int pending = 0;  // candidates waiting at lst[0 .. pending)
+    const uint32_t* mp = masks + (size_t)row * n_chunks;
+    for (int g0 = 0; g0 < n_chunks; g0 += EV_WORDS) {
+      // all mask words of this stretch at once (independent loads), then through shared memory group by group
+      {
+        uint32_t wv[EV_WORDS / 32];
+#pragma unroll
+        for (int u = 0; u < EV_WORDS / 32; ++u) {
+          const int ch = g0 + u * 32 + lane;
+          wv[u] = ch < n_chunks ? __ldcs(&mp[ch]) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < EV_WORDS / 32; ++u) wbuf[u * 32 + lane] = wv[u];
+      }
+      for (int g = 0; g < EV_WORDS && g0 + g < n_chunks; g += 32) {
+        uint32_t w = wbuf[g + lane];  // written by this lane: no synchronisation needed
+        if (!__any_sync(FULL, w != 0u)) continue;
+        const int cnt = __popc(w);
+        int pre = cnt;  // inclusive prefix sum over the lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(FULL, pre, o);
+          if (lane >= o) pre += t;
+        }
+        const int total = __shfl_sync(FULL, pre, 31);
+        int pos = pending + pre - cnt;
+        const int jb = (g0 + g + lane) * 32;
+        while (w) {
+          const int c = __ffs(w) - 1;
+          w &= w - 1;
+          lst[pos++] = (unsigned short)(jb + c);
+        }
+        __syncwarp();
+        pending += total;
+        int done = 0;
+        while (pending - done >= 32) {
+          step(done, 32);
+          done += 32;
+        }
+        if (done > 0) {  // the leftovers move to the front
+          const int rest = pending - done;
+          const unsigned short v = lane < rest ? lst[done + lane] : (unsigned short)0;
+          __syncwarp();
+          if (lane < rest) lst[lane] = v;
+          __syncwarp();
+          pending = rest;
+        }
+      }
+    }
+    if (pending > 0) step(0, pending);
+    if (lane < k) {
+      float dv = 0.f;
+      int jv = -1;
+#pragma unroll
+      for (int u = 0; u < KCAP; ++u)
+        if (u == lane && bi[u] >= 0) {
+          dv = bd[u];
+          jv = bi[u];
+        }
+      job.idx[(size_t)row * k + lane] = jv;
+      job.dist[(size_t)row * k + lane] = dv;
+    }
+    ++rows_done;
+  }
+  if (stats && lane == 0 && rows_done) {
+    atomicAdd(&stats[0], (unsigned long long)rows_done);
+    atomicAdd(&stats[1], (unsigned long long)flushes);
+    atomicAdd(&stats[2], (unsigned long long)evals);
   }
 }
 
@@ -756,23 +790,6 @@ __global__ void __launch_bounds__(128) knn_tc_prep_kernel(const PrepJob* __restr
     for (int t = threadIdx.x; t < padw; t += blockDim.x) j.pad[(size_t)row * padw + t] = t < D ? a[t] : 0.f;
 }
 
-// largest centred norm of every 32 rows (one epilogue chunk): bounds the error term of all columns of the chunk
-struct CmaxJob {
-  const float* norm;
-  float* cmax;
-  int n;
-};
-__global__ void __launch_bounds__(128) knn_tc_cmax_kernel(const CmaxJob* __restrict__ jobs)
-{
-  const CmaxJob& j = jobs[blockIdx.y];
-  const int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (chunk * 32 >= j.n) return;
-  const int r = chunk * 32 + lane;
-  float v = r < j.n ? j.norm[r] : 0.f;
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  if (lane == 0) j.cmax[chunk] = v;
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -813,29 +830,26 @@ void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vect
   if (probs.empty()) return;
   const int M = (int)desc.size();
   const int kblocks = (D + 3 + 15) / 16;
+  const int last_kb_half = ((D + 3) - 16 * (kblocks - 1)) <= 8 ? 1 : 0;
   const int Kp = kblocks * TK;
   const bool reg_path = D == 33;
   const int padw = reg_path ? APAD : 0;
   std::vector<char> used(M, 0);
   for (const KnnProblem& p : probs) { used[p.a] = 1; used[p.b] = 1; }
-  std::vector<DBuf<float>> formA(M), formB(M), norm(M), pad(M), cmax(M);
+  std::vector<DBuf<float>> formA(M), formB(M), norm(M), pad(M);
   std::vector<PrepJob> pj;
-  std::vector<CmaxJob> cj;
   int mxn = 0;
   for (int m = 0; m < M; ++m) {
     if (!used[m] || n_rows[m] == 0) continue;
     formA[m].alloc(c, (size_t)n_rows[m] * Kp);
     formB[m].alloc(c, (size_t)n_rows[m] * Kp);
     norm[m].alloc(c, n_rows[m]);
-    cmax[m].alloc(c, (size_t)(n_rows[m] + 31) / 32);
     if (reg_path) pad[m].alloc(c, (size_t)n_rows[m] * padw);
     pj.push_back(PrepJob{desc[m], formA[m].p, formB[m].p, norm[m].p, reg_path ? pad[m].p : nullptr, n_rows[m]});
-    cj.push_back(CmaxJob{norm[m].p, cmax[m].p, n_rows[m]});
     mxn = std::max(mxn, n_rows[m]);
   }
   if (pj.empty()) return;
   DBuf<PrepJob> dpj = to_device(c, pj);
-  DBuf<CmaxJob> dcj = to_device(c, cj);
   size_t rows_all = 0;
   for (const PrepJob& j : pj) rows_all += (size_t)j.n;
   DBuf<double> partial(c, pj.size() * MEAN_CHUNKS * (size_t)D);
@@ -843,7 +857,6 @@ void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vect
   MM_LAUNCH(c, knn_tc_mean_partial_kernel, dim3(MEAN_CHUNKS, (unsigned)pj.size()), 128, 0, dpj.p, D, partial.p);
   MM_LAUNCH(c, knn_tc_mean_kernel, (D + 127) / 128, 128, 0, partial.p, (int)pj.size() * MEAN_CHUNKS, D, 1.0 / (double)rows_all, mean.p);
   MM_LAUNCH(c, knn_tc_prep_kernel, dim3(mxn, (unsigned)pj.size()), 128, 0, dpj.p, mean.p, D, Kp, padw);
-  MM_LAUNCH(c, knn_tc_cmax_kernel, dim3((mxn + 127) / 128, (unsigned)cj.size()), 128, 0, dcj.p);
   std::vector<CUtensorMap> hA(M), hB(M);
   for (int m = 0; m < M; ++m) {
     if (!used[m] || n_rows[m] == 0) {
@@ -855,19 +868,32 @@ void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vect
     hB[m] = make_map(formB[m].p, n_rows[m], Kp);
   }
   DBuf<CUtensorMap> dA = to_device(c, hA), dB = to_device(c, hB);
+  // Jobs go through the kernels in batches whose candidate bits fit a fixed buffer (1 bit per distance-matrix entry:
+  // 9.9 MB for 8 800 x 8 800 descriptors, 9.8 GB for the 992 directed problems of config 3 at once).
+  constexpr size_t MASK_WORDS_MAX = (size_t)3 << 27;  // 1.5 GiB
+  struct Batch {
+    int first, count, max_na;
+    size_t words;
+    double bytes;
+  };
+  std::vector<Batch> batches;
   std::vector<TcJob> tj;
-  int max_na = 0, kmax = 0;
-  double bytes = 0;
+  int kmax = 0;
+  for (const KnnProblem& p : probs) kmax = std::max(kmax, p.k);
+  const int kcap = kmax <= 5 ? 5 : (reg_path && kmax <= 10 ? 10 : KMAXTC);  // the KCAP of the kernel variant chosen below
   DBuf<float> audit_acc;
   size_t rows_total = 0;
   for (const KnnProblem& p : probs)
     if (p.na > 0 && n_rows[p.b] > 0) rows_total += (size_t)p.na;
   DBuf<float> thr(c, rows_total);
-  size_t row_off = 0;
+  DBuf<int> pick(c, rows_total * (size_t)kcap);
+  size_t row_off = 0, words_max = 0;
+  std::vector<size_t> mask_off;
   for (const KnnProblem& p : probs) {
     if (p.na == 0 || n_rows[p.b] == 0) continue;
     TcJob j;
     j.thr = thr.p + row_off;
+    j.pick = pick.p + row_off * (size_t)kcap;
     row_off += (size_t)p.na;
     j.a_map = p.a;
     j.b_map = p.b;
@@ -878,17 +904,25 @@ void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vect
     j.origB = desc[p.b];
     j.padA = reg_path ? (const float4*)pad[p.a].p : nullptr;
     j.padB = reg_path ? (const float4*)pad[p.b].p : nullptr;
-    j.cmaxB = cmax[p.b].p;
     j.k = p.k;
     j.idx = p.idx;
     j.dist = p.dist;
     j.audit = nullptr;
+    j.masks = nullptr;
+    const size_t words = (size_t)j.na * (size_t)((j.nb + TN - 1) / TN * 4);  // a multiple of 4: every job's bits start 16-byte aligned
+    if (batches.empty() || batches.back().words + words > MASK_WORDS_MAX) batches.push_back(Batch{(int)tj.size(), 0, 0, 0, 0.0});
+    Batch& b = batches.back();
+    mask_off.push_back(b.words);
+    b.words += words;
+    b.count += 1;
+    b.max_na = std::max(b.max_na, j.na);
+    b.bytes += 4.0 * D * ((double)j.na + j.nb) + 8.0 * j.k * j.na;
+    words_max = std::max(words_max, b.words);
     tj.push_back(j);
-    max_na = std::max(max_na, p.na);
-    kmax = std::max(kmax, p.k);
-    bytes += 4.0 * D * ((double)j.na + j.nb) + 8.0 * j.k * j.na;
   }
   if (tj.empty()) return;
+  DBuf<uint32_t> masks(c, words_max);
+  for (size_t t = 0; t < tj.size(); ++t) tj[t].masks = masks.p + mask_off[t];
   const bool do_audit = audit && tj.size() == 1 && reg_path && kmax <= 5;
   if (do_audit) {
     audit_acc.alloc(c, (size_t)tj[0].na * tj[0].nb);
@@ -899,17 +933,28 @@ void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vect
     MM_CUDA(cudaMalloc((void**)&c.knn_stats, 3 * sizeof(unsigned long long)));
     MM_CUDA(cudaMemsetAsync(c.knn_stats, 0, 3 * sizeof(unsigned long long), c.stream));
   }
-  const dim3 grid((max_na + TM - 1) / TM, (unsigned)tj.size());
 #define MM_TC(KCAP, DREG, RES, AUD)                                                                                                    \
   do {                                                                                                                                 \
     const size_t smem = tc_smem(DREG, RES);                                                                                            \
     /* per device and cheap: set on every call (a process may drive several GPUs) */                                                  \
     MM_CUDA(cudaFuncSetAttribute(knn_tc_kernel<KCAP, DREG, RES, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
     MM_CUDA(cudaFuncSetAttribute(knn_tc_kernel<KCAP, DREG, RES, AUD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    MM_BYTES(c, bytes);                                                                                                                \
-    MM_LAUNCH(c, (knn_tc_kernel<KCAP, DREG, RES, false, 0>), grid, TC_THREADS, smem, dtj.p, dA.p, dB.p, kblocks, D, nullptr);          \
-    MM_BYTES(c, bytes);                                                                                                                \
-    MM_LAUNCH(c, (knn_tc_kernel<KCAP, DREG, RES, AUD, 1>), grid, TC_THREADS, smem, dtj.p, dA.p, dB.p, kblocks, D, c.knn_stats);        \
+    const size_t esmem = ev_smem(DREG > 0 ? (DREG + 3) / 4 : 1);                                                                       \
+    MM_CUDA(cudaFuncSetAttribute(knn_eval_kernel<KCAP, DREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));               \
+    for (const Batch& b : batches) {                                                                                                   \
+      const dim3 grid((b.max_na + CTA_ROWS - 1) / CTA_ROWS, (unsigned)b.count);                                                        \
+      MM_CUDA(cudaMemsetAsync(masks.p, 0, b.words * sizeof(uint32_t), c.stream));                                                      \
+      MM_BYTES(c, b.bytes);                                                                                                            \
+      MM_LAUNCH(c, (knn_tc_kernel<KCAP, DREG, RES, false, 0>), grid, TC_THREADS, smem, dtj.p, b.first, dA.p, dB.p, kblocks,            \
+                last_kb_half);                                                                                                         \
+      MM_LAUNCH(c, (knn_thr_kernel<KCAP, DREG>), dim3((b.max_na + 127) / 128, (unsigned)b.count), 128, 0, dtj.p, b.first, D);          \
+      MM_BYTES(c, b.bytes);                                                                                                            \
+      MM_LAUNCH(c, (knn_tc_kernel<KCAP, DREG, RES, AUD, 1>), grid, TC_THREADS, smem, dtj.p, b.first, dA.p, dB.p, kblocks,              \
+                last_kb_half);                                                                                                         \
+      MM_BYTES(c, b.bytes);                                                                                                            \
+      MM_LAUNCH(c, (knn_eval_kernel<KCAP, DREG>), dim3(EV_BLOCKS_X, (unsigned)b.count), EV_WARPS * 32, esmem, dtj.p, b.first, D,       \
+                c.knn_stats);                                                                                                          \
+    }                                                                                                                                  \
   } while (0)
   const bool res = kblocks <= A_RES_MAX_KB;
   if (do_audit) MM_TC(5, 33, true, true);
