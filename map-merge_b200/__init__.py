@@ -12,6 +12,7 @@ Because the directory name carries a hyphen the package is imported through
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 import os
 import subprocess
 
@@ -164,10 +165,19 @@ class Context:
 
     def _take(self, ptr, n, dtype, shape=None):
         n = int(n)
+        nbytes = n * np.dtype(dtype).itemsize
+        if n and nbytes >= (1 << 20):
+            # large outputs (composed maps) are adopted, not copied: the array keeps the library's buffer alive and
+            # mm3d_free runs when the last view of it goes away
+            addr = C.cast(ptr, C.c_void_p).value
+            buf = (C.c_uint8 * nbytes).from_address(addr)
+            weakref.finalize(buf, self.L.mm3d_free, C.c_void_p(addr))
+            arr = np.frombuffer(buf, dtype)
+            return arr.reshape(shape) if shape is not None else arr
         if n == 0:
             arr = np.zeros(0, dtype)
         else:
-            arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n * np.dtype(dtype).itemsize,)).view(dtype).copy()
+            arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(nbytes,)).view(dtype).copy()
         if ptr:
             self.L.mm3d_free(C.cast(ptr, C.c_void_p))
         return arr.reshape(shape) if shape is not None else arr

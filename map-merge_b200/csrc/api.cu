@@ -63,7 +63,7 @@ struct StageTimer {
 template <typename T>
 T* host_copy(Ctx& c, const T* dev, size_t count)
 {
-  T* h = (T*)malloc(std::max<size_t>(count, 1) * sizeof(T));
+  T* h = (T*)host_out_alloc(std::max<size_t>(count, 1) * sizeof(T));
   if (count) MM_CUDA(cudaMemcpyAsync(h, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c.stream));
   return h;
 }
@@ -84,6 +84,70 @@ void check_supported(const mm3d_params& p)
 }  // namespace
 
 namespace mm3d {
+
+namespace {
+struct PinnedPool {
+  std::mutex mu;
+  std::unordered_map<void*, size_t> live;                     // pinned blocks handed out: pointer -> size class
+  std::unordered_map<size_t, std::vector<void*>> free_blocks;  // size class -> cached blocks
+  size_t cached = 0;
+};
+PinnedPool& pinned_pool()
+{
+  static PinnedPool* p = new PinnedPool();  // never destroyed: blocks may be released after the CUDA runtime has shut down
+  return *p;
+}
+constexpr size_t PINNED_MIN = (size_t)1 << 20, PINNED_CACHE_MAX = (size_t)2 << 30;
+}  // namespace
+
+void* host_out_alloc(size_t bytes)
+{
+  if (bytes < PINNED_MIN) return malloc(std::max<size_t>(bytes, 1));
+  const size_t cls = BlockCache::size_class(bytes);
+  PinnedPool& pp = pinned_pool();
+  {
+    std::lock_guard<std::mutex> lk(pp.mu);
+    auto it = pp.free_blocks.find(cls);
+    if (it != pp.free_blocks.end() && !it->second.empty()) {
+      void* p = it->second.back();
+      it->second.pop_back();
+      pp.cached -= cls;
+      pp.live[p] = cls;
+      return p;
+    }
+  }
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, cls, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return malloc(bytes);
+  }
+  std::lock_guard<std::mutex> lk(pp.mu);
+  pp.live[p] = cls;
+  return p;
+}
+
+void host_out_free(void* p)
+{
+  if (!p) return;
+  PinnedPool& pp = pinned_pool();
+  size_t cls = 0;
+  bool keep = false;
+  {
+    std::lock_guard<std::mutex> lk(pp.mu);
+    auto it = pp.live.find(p);
+    if (it != pp.live.end()) {
+      cls = it->second;
+      pp.live.erase(it);
+      if (pp.cached + cls <= PINNED_CACHE_MAX) {
+        pp.free_blocks[cls].push_back(p);
+        pp.cached += cls;
+        keep = true;
+      }
+    }
+  }
+  if (cls == 0) free(p);
+  else if (!keep) cudaFreeHost(p);
+}
 
 HostProf& host_prof()
 {
@@ -436,7 +500,7 @@ void mm3d_destroy(mm3d_ctx* ctx)
 }
 
 const char* mm3d_last_error(mm3d_ctx* ctx) { return ctx ? ctx->c.err.c_str() : "null context"; }
-void mm3d_free(void* p) { free(p); }
+void mm3d_free(void* p) { mm3d::host_out_free(p); }
 long long mm3d_kernel_launches(mm3d_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
 
 int mm3d_estimate_maps_transforms(mm3d_ctx* ctx, int n_maps, const float* const* clouds, const uint64_t* n_points, const mm3d_params* params,

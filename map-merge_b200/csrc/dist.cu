@@ -373,10 +373,20 @@ void dist_compose(Ctx& c, mm3d_comm* cm, const std::vector<CloudView>& local, co
   constexpr int NB = 4096;
   *out = nullptr;
   *n_out = 0;
+  // MM3D_HOST_TRACE=1: host wall clock between the phases (each ends in a synchronisation of its own)
+  const bool trace = host_prof().on;
+  double t_prev = trace ? now_ms() : 0.0;
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    const double t = now_ms();
+    fprintf(stderr, "[mm3d compose] %s %.2f ms\n", what, t - t_prev);
+    t_prev = t;
+  };
   DCloud cat;
   transform_concat(c, local, transforms_rowmajor, cat);
   float bbox[6];
   compose_bbox(c, cat, bbox);
+  mark("transform + concatenate + bounding box");
   unsigned long long total = (unsigned long long)cat.n;
   if (W > 1) {
     // min over ranks of (lo, -hi) and the point count
@@ -395,10 +405,11 @@ void dist_compose(Ctx& c, mm3d_comm* cm, const std::vector<CloudView>& local, co
     for (int k = 0; k < 3; ++k) { bbox[k] = h[k]; bbox[3 + k] = -h[3 + k]; }
   }
   auto to_host = [&](const float4* p, size_t n) {
-    *out = (float*)malloc(std::max<size_t>(n, 1) * 16);
+    *out = (float*)host_out_alloc(std::max<size_t>(n, 1) * 16);
     if (n) MM_CUDA(cudaMemcpyAsync(*out, p, n * 16, cudaMemcpyDeviceToHost, c.stream));
     *n_out = n;
     c.sync();
+    mark("copy to the host");
   };
   if (total == 0) {
     to_host(nullptr, 0);
@@ -412,6 +423,8 @@ void dist_compose(Ctx& c, mm3d_comm* cm, const std::vector<CloudView>& local, co
   if (W == 1) {
     std::vector<DCloud> res;
     voxel_downsample_batch(c, {cat.view()}, (float)resolution, res, nullptr);
+    if (trace) c.sync();
+    mark("voxel grid");
     to_host(res[0].pts.p, (size_t)res[0].n);
     return;
   }
@@ -559,17 +572,17 @@ void team_compose(mm3d_ctx* master, int n_maps, const float* const* clouds, cons
       dist_compose(c, cm, v, tp, resolution, &parts[r], &sizes[r]);
     });
   } catch (...) {
-    for (float* p : parts) free(p);
+    for (float* p : parts) host_out_free(p);
     throw;
   }
   uint64_t total = 0;
   for (uint64_t s : sizes) total += s;
-  *out = (float*)malloc(std::max<uint64_t>(total, 1) * 16);
+  *out = (float*)host_out_alloc(std::max<uint64_t>(total, 1) * 16);
   uint64_t o = 0;
   for (int r = 0; r < W; ++r) {
     if (sizes[r]) memcpy(*out + o * 4, parts[r], sizes[r] * 16);
     o += sizes[r];
-    free(parts[r]);
+    host_out_free(parts[r]);
   }
   *n_out = total;
 }

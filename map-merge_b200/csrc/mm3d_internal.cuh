@@ -57,6 +57,12 @@ struct HostProf {
 HostProf& host_prof();
 double host_now_ms();
 
+// Host memory for outputs returned through the C ABI (released by mm3d_free).  Large outputs (composed maps: tens of MB) come
+// from a process-wide cache of PINNED blocks: the device-to-host copy runs at PCIe speed instead of being staged through
+// the driver's bounce buffers into freshly mapped pages (config 5: 75 MB per call, 36 ms -> 1.4 ms).  Small ones are plain malloc.
+void* host_out_alloc(size_t bytes);
+void host_out_free(void* p);
+
 // Device-memory block cache of one context.  The path allocates and frees thousands of stage buffers per step (c3: ~4300
 // calls, ~9 GB); handing them to cudaMallocAsync / cudaFreeAsync made the step time erratic — the driver pool re-creates
 // multi-GB physical chunks whenever fragmentation defeats reuse (measured: 5 .. 560 ms per step inside cudaMallocAsync).
