@@ -76,6 +76,8 @@ class ClockSampler:
     `nvidia-smi -lms 100` child process was measured to slow the host side of short steps by up to 2x while it polls, and
     100 ms NVML polling the c3 step by up to 30 %: the queries contend with CUDA calls for the driver lock)."""
 
+    PERIOD = 1.0  # seconds between samples: a query can hold the driver lock for tens of ms, so few of them fall into a step
+
     def __init__(self, index: int):
         self.index = index
         self.samples = []
@@ -107,7 +109,7 @@ class ClockSampler:
             except Exception as e:
                 self.err = str(e)
                 return
-            self.stop_flag.wait(0.5)  # NVML queries contend with CUDA calls for the driver lock: 100 ms polling cost up to 30 % of a step
+            self.stop_flag.wait(self.PERIOD)  # NVML queries contend with CUDA calls for the driver lock: 100 ms polling cost up to 30 % of a step
 
     def stop(self, t0=None, t1=None):
         self.stop_flag.set()
@@ -123,7 +125,7 @@ class ClockSampler:
         sel = [x for x in self.samples if t0 is None or (t0 <= x[0] <= t1 + 0.15)] or self.samples
         reasons = sorted(k for k, b in bits.items() if any(x[2] & b for x in sel))
         return {"sm_mhz": float(np.median([x[1] for x in sel])), "sm_max_mhz": self.max_sm, "samples": len(sel), "reasons": reasons,
-                "source": "NVML, 500 ms period, samples inside the timed region"}
+                "source": f"NVML, {self.PERIOD:g} s period, samples inside the timed region"}
 
     def _smi_once(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -385,19 +387,17 @@ class Job:
 
 
 def settle(job, fn, seconds: float = 1.0):
-    """Untimed steps (the same on every rank) while the clock sampler starts up."""
-    n = 1
-    if job.rank == 0:
-        t0 = time.perf_counter()
-        fn()
-        dt = max(time.perf_counter() - t0, 1e-3)
-        n = max(1, min(20, int(seconds / dt)))
+    """Untimed steps (the same number on every rank) while the clock sampler starts up.  A step is collective at N > 1
+    (NCCL inside the library), so EVERY rank runs the first step — a rank that timed it alone would wait for the others inside
+    the step while they wait for its broadcast — and rank 0's duration decides how many more follow."""
+    t0 = time.perf_counter()
+    fn()
+    dt = max(time.perf_counter() - t0, 1e-3)
+    n = max(1, min(20, int(seconds / dt)))
     if job.world > 1:
         t = job.torch.tensor([n], dtype=job.torch.int64, device=job.dev)
         job.dist.broadcast(t, 0)
         n = int(t.item())
-        if job.rank != 0:
-            fn()
     for _ in range(n - 1):
         fn()
 
@@ -416,16 +416,18 @@ def roofline_of(prof, steps, peak, peak_src):
         roof["achieved"] = top["algorithmic_bytes"] / (top["ms_annotated"] * 1e-3) / 1e9
         roof["frac"] = roof["achieved"] / peak
         roof["algorithmic_bytes_per_launch"] = top["algorithmic_bytes"] / top["launches"]
-    # DRAM traffic of the same kernel from the committed ncu capture: per-launch average over the launches of one step
-    # (like for like with algorithmic_bytes_per_launch), see profiles/README.md
+    # DRAM traffic of the same kernel from the committed ncu captures (profiles/r02_traffic.json, profiles/README.md).  ncu
+    # replays every kernel ~40 times, so the captures ran an 8-map subset of the workload: the capture's DRAM bytes are
+    # reported next to the algorithmic bytes of the SAME capture (like for like), and `traffic` — which would have to be per
+    # launch of THIS run — stays null.
     try:
         with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as fh:
             tr = json.load(fh).get(top["kernel"])
         if tr:
-            roof["traffic"] = tr["dram_bytes_per_launch"]
-            roof["traffic_source"] = tr.get("source")
-            if tr.get("ncu"):
-                roof["ncu"] = tr["ncu"]
+            roof["traffic_capture"] = {"dram_bytes_per_launch": tr["dram_bytes_per_launch"],
+                                       "algorithmic_bytes_per_launch": tr["algorithmic_bytes_per_launch"],
+                                       "dram_over_algorithmic": tr["dram_bytes_per_launch"] / tr["algorithmic_bytes_per_launch"],
+                                       "workload": tr["workload"], "ncu": tr.get("ncu"), "remark": tr.get("remark")}
     except Exception:
         pass
     kernels = [{"kernel": k["kernel"], "launches_per_step": k["launches"] / steps, "ms_per_step": k["ms"] / steps,

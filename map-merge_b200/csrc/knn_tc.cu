@@ -9,13 +9,14 @@
 //   * descriptors are centred on their common mean first (distances are translation invariant, the norms — and with them
 //     the absolute error of the expansion — shrink), -2 is folded into A and ||b||^2 rides along as three virtual
 //     dimensions, so the accumulator IS the filter value ||b||^2 - 2 a.b;
-//   * TMA (cp.async.bulk.tensor, 128-byte swizzle) brings the A tile in once (it stays in shared memory when D <= 61) and
-//     streams 128-column k-blocks of B through an mbarrier ring; one elected thread issues tcgen05.mma (M = 128, N = 128,
-//     K = 8) into a double-buffered TMEM accumulator;
-//   * four epilogue warps read the accumulator with tcgen05.ld (one TMEM lane = one query row per thread) and keep, per
-//     row, a short shared-memory list of the columns that can still be among the k nearest under a rigorous error bound;
-//   * the survivors are evaluated with the EXACT sequential FP32 distance on the original descriptors in ascending column
-//     order — indices and distances are bit-identical to the brute-force scan (and to the CPU checker).
+//   * TMA (cp.async.bulk.tensor, 128-byte swizzle) brings two A tiles (256 query rows) in once — they stay in shared memory
+//     when D <= 61 — and streams 128-column k-blocks of B through an mbarrier ring; one elected thread issues tcgen05.mma
+//     (M = 128, N = 128, K = 8) into two double-buffered TMEM accumulators, so every B tile read from L2 feeds two MMAs;
+//   * eight epilogue warps read the accumulators with tcgen05.ld (one TMEM lane = one query row per thread).  The GEMM runs
+//     twice: pass 0 picks, per row, k distinct columns with small filter values, whose EXACT distances bound the row's k-th
+//     nearest distance; pass 1 marks every column whose rigorous lower bound is within that bound as one bit in memory;
+//   * knn_eval_kernel evaluates the marked columns with the EXACT sequential FP32 distance on the original descriptors in
+//     ascending column order — indices and distances are bit-identical to the brute-force scan (and to the CPU checker).
 #include <cuda.h>
 
 #include <algorithm>

@@ -261,3 +261,49 @@ def test_library_pair_plan_matches_python_restatement(mm):
             assert (first, count) == sh.map_block(r, world, n_maps)[:2]
             covered += list(range(first, first + count))
         assert covered == list(range(n_maps))
+
+
+def _settle_worker(rank, world, port, q):
+    """bench.settle() with a step that is collective, as every N > 1 step is (NCCL inside the library)."""
+    sys.path.insert(0, ROOT)
+    import types
+    import torch
+    import torch.distributed as dist
+    import bench
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        calls = []
+
+        def step():
+            t = torch.ones(1)
+            dist.all_reduce(t)  # blocks until every rank has entered the step
+            calls.append(int(t.item()))
+
+        job = types.SimpleNamespace(rank=rank, world=world, torch=torch, dist=dist, dev="cpu")
+        bench.settle(job, step, seconds=0.05)
+        q.put({"rank": rank, "calls": len(calls), "sum_ok": all(c == world for c in calls)})
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bench_settle_is_collective_safe():
+    """Round 2 regression: rank 0 used to run the first untimed step alone while the others waited for its broadcast —
+    a deadlock at every N > 1 (found by the 8-GPU run, which sat in the NCCL watchdog for ten minutes)."""
+    import torch.multiprocessing as mp
+    import socket
+    world = 2
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_settle_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    try:
+        outs = [q.get(timeout=90) for _ in range(world)]
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.terminate()
+    assert all(o["sum_ok"] for o in outs)
+    assert outs[0]["calls"] == outs[1]["calls"] >= 1  # the same number of steps on every rank
