@@ -8,6 +8,8 @@
 #include <cstring>
 #include <memory>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/mm3d.h"
 #include "mm3d_internal.cuh"
 #include "pipeline.cuh"
@@ -24,11 +26,14 @@ struct StageTimer {
   float* ms;
   cudaEvent_t ev[2];
   bool host_trace;  // MM3D_HOST_TRACE=1: host wall-clock per stage on stderr, no extra synchronisation (where does the host wait?)
+  bool nvtx;        // MM3D_NVTX=1: one NVTX range per stage (registration_visualisation.cpp:51-158 uses pcl::ScopeTime for the same blocks)
   std::chrono::steady_clock::time_point h0;
   explicit StageTimer(Ctx& ctx, float* out) : c(ctx), ms(out)
   {
     const char* e = std::getenv("MM3D_HOST_TRACE");
     host_trace = e && e[0] == '1';
+    const char* n = std::getenv("MM3D_NVTX");
+    nvtx = n && n[0] == '1';
     if (ms) {
       cudaEventCreate(&ev[0]);
       cudaEventCreate(&ev[1]);
@@ -41,13 +46,15 @@ struct StageTimer {
       cudaEventDestroy(ev[1]);
     }
   }
-  void begin()
+  void begin(int stage)
   {
+    if (nvtx) nvtxRangePushA(kStageNames[stage]);  // the reference's eight pcl::ScopeTime labels (+ scoring, graph) as NVTX ranges
     if (host_trace) h0 = std::chrono::steady_clock::now();
     if (ms) cudaEventRecord(ev[0], c.stream);
   }
   void end(int stage)
   {
+    if (nvtx) nvtxRangePop();
     if (host_trace)
       fprintf(stderr, "[mm3d host] %-26s %8.2f ms\n", kStageNames[stage],
               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());
@@ -192,13 +199,13 @@ void compute_features(Ctx& c, const std::vector<CloudView>& raw, const mm3d_para
   StageTimer tm(c, stage_ms);
   const float leaf = (float)p.resolution;
 
-  tm.begin();
+  tm.begin(0);
   std::vector<DCloud> resized;
   std::vector<VoxGeom> vgeom;
   voxel_downsample_batch(c, raw, leaf, resized, &vgeom);
   tm.end(0);
 
-  tm.begin();
+  tm.begin(1);
   std::vector<CloudView> rv(M);
   for (int m = 0; m < M; ++m) rv[m] = resized[m].view();
   std::vector<DCloud> filtered;
@@ -209,7 +216,7 @@ void compute_features(Ctx& c, const std::vector<CloudView>& raw, const mm3d_para
   }
   tm.end(1);
 
-  tm.begin();
+  tm.begin(2);
   std::vector<CloudView> fv(M);
   for (int m = 0; m < M; ++m) fv[m] = filtered[m].view();
   std::vector<DIndex> idx;
@@ -218,7 +225,7 @@ void compute_features(Ctx& c, const std::vector<CloudView>& raw, const mm3d_para
   normals_batch(c, fv, idx, p.normal_radius, normals);
   tm.end(2);
 
-  tm.begin();
+  tm.begin(3);
   std::vector<DCloud> kps;
   std::vector<const float4*> np(M);
   for (int m = 0; m < M; ++m) np[m] = normals[m].p;
@@ -228,7 +235,7 @@ void compute_features(Ctx& c, const std::vector<CloudView>& raw, const mm3d_para
     sift_batch(c, fv, (float)p.resolution, 3, 3, (float)p.keypoint_threshold, kps, nullptr);
   tm.end(3);
 
-  tm.begin();
+  tm.begin(4);
   std::vector<DBuf<float>> desc;
   if (p.descriptor_type == MM3D_DESC_SHOT) shot_batch(c, fv, idx, np, kps, p.descriptor_radius, desc, nullptr);
   else if (p.descriptor_type == MM3D_DESC_PFH) pfh_batch(c, fv, idx, np, kps, p.descriptor_radius, desc, false);
@@ -270,7 +277,7 @@ void register_pairs(Ctx& c, const std::vector<FeatView>& f, int dim, const std::
   if (p.estimation_method == MM3D_EST_SAC_IA) {
     // estimateTransformFromDescriptorsSets(min_sample_distance = inlier_threshold, max_correspondence_distance, max_iterations)
     // (matching.cpp:242-247).  The C rand() stream runs through the complete row-major pair list of the feature set.
-    tm.begin();
+    tm.begin(6);
     std::vector<PairJob> all_pairs;
     for (int i = 0; i < M - 1; ++i)
       for (int j2 = i + 1; j2 < M; ++j2)
@@ -289,11 +296,11 @@ void register_pairs(Ctx& c, const std::vector<FeatView>& f, int dim, const std::
     }
     tm.end(6);
   } else {
-    tm.begin();
+    tm.begin(5);
     match_batch(c, desc, nk, dim, jobs, (size_t)p.matching_k, corr);
     tm.end(5);
 
-    tm.begin();
+    tm.begin(6);
     ransac_batch(c, kps, jobs, corr, p.inlier_threshold, rs, nullptr);
     tm.end(6);
   }
@@ -302,7 +309,7 @@ void register_pairs(Ctx& c, const std::vector<FeatView>& f, int dim, const std::
   std::vector<CloudView> tv(M, CloudView{nullptr, 0});
   for (const PairJob& j : jobs) tv[j.b] = clouds[j.b];
   std::vector<DIndex> tidx;
-  tm.begin();
+  tm.begin(7);
   // One-voxel cells: the clouds are voxel-grid outputs (at most one point per voxel), so the nearest neighbour of a query
   // that lies on the target surface is found in the 3 x 3 x 3 voxel block around it — nine (z, y) rows whose three cells are
   // one contiguous run each (icp.cu, nearest_block27).  The general row search remains the fallback for queries farther
@@ -330,7 +337,7 @@ void register_pairs(Ctx& c, const std::vector<FeatView>& f, int dim, const std::
   }
   tm.end(7);
 
-  tm.begin();
+  tm.begin(8);
   std::vector<const float*> tf(P);
   for (int i = 0; i < P; ++i) tf[i] = icp[i].T;
   std::vector<double> scores;
