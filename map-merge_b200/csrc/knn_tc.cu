@@ -911,7 +911,8 @@ void knn_tc_batch(Ctx& c, const std::vector<const float*>& desc, const std::vect
     j.audit = nullptr;
     j.masks = nullptr;
     const size_t words = (size_t)j.na * (size_t)((j.nb + TN - 1) / TN * 4);  // a multiple of 4: every job's bits start 16-byte aligned
-    if (batches.empty() || batches.back().words + words > MASK_WORDS_MAX) batches.push_back(Batch{(int)tj.size(), 0, 0, 0, 0.0});
+    if (batches.empty() || batches.back().words + words > MASK_WORDS_MAX || batches.back().count >= 65535)  // gridDim.y limit
+      batches.push_back(Batch{(int)tj.size(), 0, 0, 0, 0.0});
     Batch& b = batches.back();
     mask_off.push_back(b.words);
     b.words += words;
